@@ -1,0 +1,340 @@
+"""gossamer_b200 -- B200-native `goss build-graph` / `build-kmer-set`.
+
+Python is only a thin ctypes binding over the C ABI in include/gossamer_b200.h (the product is
+libgossamer_b200.so + the C++ `goss` host).  There is no CPU path: importing works anywhere
+(so that the symbol table can be checked), but every compute call needs a B200.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgossamer_b200.so")
+
+GRAPH, KMERSET = 0, 1
+FASTA, FASTQ, LINE = 0, 1, 2
+LAST_OF_FILE = 1
+ABI_VERSION = 1
+NCCL_ID_BYTES = 128
+
+STATUS_NAMES = {0: "GSB_OK", -1: "GSB_EINVAL", -2: "GSB_EPARSE", -3: "GSB_EIO", -4: "GSB_ENOMEM",
+                -5: "GSB_ECUDA", -6: "GSB_ENCCL", -7: "GSB_ERANGE"}
+
+
+class GossamerError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+        self.message = message
+
+
+class ParseError(GossamerError):
+    pass
+
+
+_LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p)
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("kind", C.c_int32), ("k", C.c_int32), ("device", C.c_int32),
+                ("min_count", C.c_uint64), ("max_batch_keys", C.c_uint64), ("log", _LOG_FN), ("log_user", C.c_void_p)]
+
+
+class Counts(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_instances", C.c_uint64), ("n_distinct", C.c_uint64), ("n_kept", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("ms_h2d", "ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_merge", "ms_emit",
+                                          "ms_d2h", "ms_exchange")] + \
+               [(n, C.c_uint64) for n in ("bytes_in", "bytes_out", "n_symbols", "sort_key_bytes", "sort_passes",
+                                          "sort_passes_model", "n_batches", "kernel_launches", "hbm_peak_bytes")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_OPEN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p))
+_PWRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64)
+_CLOSE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+
+
+class Sink(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("open", _OPEN_FN), ("pwrite", _PWRITE_FN), ("close", _CLOSE_FN)]
+
+
+EXPORTS = ["gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
+           "gsb_emit", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root",
+           "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
+           "gsb_debug_extract"]
+
+_lib = None
+
+
+def lib():
+    """Load libgossamer_b200.so.  Fails loudly when it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `make -C gossamer_b200` (or __graft_entry__.build()); "
+                              "gossamer_b200 has no CPU or pure-Python fallback")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L.gsb_last_error.restype = C.c_char_p
+        L.gsb_last_error.argtypes = [C.c_void_p]
+        L.gsb_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.gsb_destroy.argtypes = [C.c_void_p]
+        L.gsb_push_block.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32]
+        L.gsb_push_device_block.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32]
+        L.gsb_finish_counting.argtypes = [C.c_void_p, C.POINTER(Counts)]
+        L.gsb_emit.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Sink)]
+        L.gsb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.gsb_reset.argtypes = [C.c_void_p]
+        L.gsb_comm_make_id.argtypes = [C.c_void_p]
+        L.gsb_comm_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.gsb_gather_to_root.argtypes = [C.c_void_p]
+        L.gsb_debug_copy_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.gsb_debug_copy_counts.restype = C.c_int64
+        L.gsb_debug_sort_keys.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        L.gsb_debug_sort_keys.restype = C.c_int64
+        L.gsb_debug_emit_sparse_array.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                                  C.c_char_p, C.POINTER(Sink)]
+        L.gsb_debug_emit_graph.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_char_p, C.POINTER(Sink)]
+        L.gsb_debug_extract.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
+                                        C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]
+        L.gsb_debug_extract.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+class MemorySink:
+    """In-memory file store behind the gsb_sink callbacks (the StringFileFactory analogue)."""
+
+    def __init__(self, keep_data=True):
+        self.files = {}
+        self.sizes = {}
+        self.keep_data = keep_data
+        self._handles = {}
+        self._next = 1
+
+        def _open(user, name, size_hint, out):
+            h = self._next
+            self._next += 1
+            nm = name.decode()
+            self._handles[h] = nm
+            self.sizes[nm] = 0
+            if self.keep_data:
+                self.files[nm] = bytearray()
+            out[0] = h
+            return 0
+
+        def _pwrite(user, handle, offset, data, length):
+            nm = self._handles[handle]
+            self.sizes[nm] = max(self.sizes[nm], offset + length)
+            if self.keep_data:
+                buf = self.files[nm]
+                if len(buf) < offset + length:
+                    buf.extend(b"\0" * (offset + length - len(buf)))
+                buf[offset:offset + length] = C.string_at(data, length)
+            return 0
+
+        def _close(user, handle):
+            self._handles.pop(handle, None)
+            return 0
+
+        self._cbs = (_OPEN_FN(_open), _PWRITE_FN(_pwrite), _CLOSE_FN(_close))
+        self.c = Sink(None, *self._cbs)
+
+    def as_bytes(self):
+        return {k: bytes(v) for k, v in self.files.items()}
+
+
+class DirectorySink:
+    """Writes the file set under a directory prefix, like PhysicalFileFactory."""
+
+    def __init__(self):
+        self._handles = {}
+        self._next = 1
+
+        def _open(user, name, size_hint, out):
+            h = self._next
+            self._next += 1
+            self._handles[h] = open(name.decode(), "wb")
+            out[0] = h
+            return 0
+
+        def _pwrite(user, handle, offset, data, length):
+            f = self._handles[handle]
+            f.seek(offset)
+            f.write(C.string_at(data, length))
+            return 0
+
+        def _close(user, handle):
+            self._handles.pop(handle).close()
+            return 0
+
+        self._cbs = (_OPEN_FN(_open), _PWRITE_FN(_pwrite), _CLOSE_FN(_close))
+        self.c = Sink(None, *self._cbs)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Builder:
+    """One counting context: push raw text blocks, finish, emit.  Mirrors GossCmdBuildGraph /
+    GossCmdBuildKmerSet (src/GossCmdBuildGraph.cc:270-426, src/GossCmdBuildKmerSet.tcc:212-332)."""
+
+    def __init__(self, kind, k, min_count=1, device=0, max_batch_keys=0, log=None):
+        self._log_cb = _LOG_FN(lambda u, sev, msg: log(sev, msg.decode())) if log else _LOG_FN()
+        cfg = Config(ABI_VERSION, kind, k, device, min_count, max_batch_keys, self._log_cb, None)
+        self.h = C.c_void_p()
+        rc = lib().gsb_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise GossamerError(rc, lib().gsb_last_error(None).decode())
+        self.kind, self.k = kind, k
+
+    def close(self):
+        if self.h:
+            lib().gsb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = lib().gsb_last_error(self.h).decode()
+            raise (ParseError if rc == -2 else GossamerError)(rc, msg)
+
+    def push(self, data, fmt, last=True):
+        """data: bytes / bytearray / numpy uint8 array in host memory."""
+        if isinstance(data, np.ndarray):
+            buf = np.ascontiguousarray(data, dtype=np.uint8)
+            self._check(lib().gsb_push_block(self.h, buf.ctypes.data, buf.size, fmt, LAST_OF_FILE if last else 0))
+        else:
+            b = bytes(data)
+            self._check(lib().gsb_push_block(self.h, b, len(b), fmt, LAST_OF_FILE if last else 0))
+
+    def push_pointer(self, host_ptr, nbytes, fmt, last=True):
+        self._check(lib().gsb_push_block(self.h, C.c_void_p(host_ptr), nbytes, fmt, LAST_OF_FILE if last else 0))
+
+    def push_device(self, device_ptr, nbytes, fmt, last=True):
+        self._check(lib().gsb_push_device_block(self.h, C.c_void_p(device_ptr), nbytes, fmt, LAST_OF_FILE if last else 0))
+
+    def finish(self):
+        c = Counts()
+        self._check(lib().gsb_finish_counting(self.h, C.byref(c)))
+        return c
+
+    def emit(self, prefix, sink):
+        self._check(lib().gsb_emit(self.h, prefix.encode(), C.byref(sink.c)))
+
+    def stats(self):
+        s = Stats()
+        self._check(lib().gsb_get_stats(self.h, C.byref(s)))
+        return s
+
+    def reset(self):
+        self._check(lib().gsb_reset(self.h))
+
+    def attach(self, nccl_id, n_ranks, rank):
+        self._check(lib().gsb_comm_attach(self.h, nccl_id, n_ranks, rank))
+
+    def gather_to_root(self):
+        self._check(lib().gsb_gather_to_root(self.h))
+
+    def counts_arrays(self):
+        """(lo, hi, counts) of this rank's reduced run (test hook)."""
+        m = lib().gsb_debug_copy_counts(self.h, None, None, None, 0)
+        if m < 0:
+            self._check(int(m))
+        lo, hi, cn = np.zeros(m, np.uint64), np.zeros(m, np.uint64), np.zeros(m, np.uint64)
+        lib().gsb_debug_copy_counts(self.h, _ptr(lo), _ptr(hi), _ptr(cn), m)
+        return lo, hi, cn
+
+
+def make_nccl_id():
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    rc = lib().gsb_comm_make_id(buf)
+    if rc != 0:
+        raise GossamerError(rc, lib().gsb_last_error(None).decode())
+    return buf.raw
+
+
+def build_graph(inputs, k, min_count=1, prefix="graph", sink=None, device=0):
+    """inputs: list of (bytes-like, format).  Returns (sink, Counts, Stats)."""
+    sink = sink or MemorySink()
+    b = Builder(GRAPH, k, min_count=min_count, device=device)
+    try:
+        order = {LINE: 0, FASTA: 1, FASTQ: 2}      # src/GossCmdBuildGraph.cc:284-300
+        for data, fmt in sorted(inputs, key=lambda x: order[x[1]]):
+            b.push(data, fmt)
+        counts = b.finish()
+        b.emit(prefix, sink)
+        return sink, counts, b.stats()
+    finally:
+        b.close()
+
+
+def build_kmer_set(inputs, k, prefix="kset", sink=None, device=0):
+    sink = sink or MemorySink()
+    b = Builder(KMERSET, k, device=device)
+    try:
+        order = {LINE: 0, FASTA: 1, FASTQ: 2}
+        for data, fmt in sorted(inputs, key=lambda x: order[x[1]]):
+            b.push(data, fmt)
+        counts = b.finish()
+        b.emit(prefix, sink)
+        return sink, counts, b.stats()
+    finally:
+        b.close()
+
+
+# ---- component-level debug entry points (tests) --------------------------------------------------
+
+def debug_sort_keys(lo, hi, key_bits, device=0):
+    lo = np.ascontiguousarray(lo, np.uint64).copy()
+    hi = np.ascontiguousarray(hi if hi is not None else np.zeros_like(lo), np.uint64).copy()
+    rc = lib().gsb_debug_sort_keys(device, _ptr(lo), _ptr(hi), lo.size, key_bits)
+    if rc < 0:
+        raise GossamerError(int(rc), lib().gsb_last_error(None).decode())
+    return lo, hi, int(rc)
+
+
+def debug_emit_sparse_array(lo, hi, universe, m_est, base="sa", device=0):
+    lo = np.ascontiguousarray(lo, np.uint64)
+    hi = None if hi is None else np.ascontiguousarray(hi, np.uint64)
+    sink = MemorySink()
+    rc = lib().gsb_debug_emit_sparse_array(device, _ptr(lo), _ptr(hi), lo.size, universe & (2**64 - 1), universe >> 64, m_est,
+                                           base.encode(), C.byref(sink.c))
+    if rc != 0:
+        raise GossamerError(rc, lib().gsb_last_error(None).decode())
+    return sink.as_bytes()
+
+
+def debug_emit_graph(lo, hi, counts, k, prefix="graph", device=0):
+    lo = np.ascontiguousarray(lo, np.uint64)
+    hi = np.ascontiguousarray(hi if hi is not None else np.zeros_like(lo), np.uint64)
+    counts = np.ascontiguousarray(counts, np.uint64)
+    sink = MemorySink()
+    rc = lib().gsb_debug_emit_graph(device, _ptr(lo), _ptr(hi), _ptr(counts), lo.size, k, prefix.encode(), C.byref(sink.c))
+    if rc != 0:
+        raise GossamerError(rc, lib().gsb_last_error(None).decode())
+    return sink.as_bytes()
+
+
+def debug_extract(text, fmt, kind, k, device=0):
+    text = bytes(text)
+    err = C.create_string_buffer(512)
+    nr = C.c_uint64()
+    n = lib().gsb_debug_extract(device, text, len(text), fmt, kind, k, None, None, 0, C.byref(nr), err, 512)
+    if n < 0:
+        raise (ParseError if n == -2 else GossamerError)(int(n), err.value.decode())
+    lo, hi = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    n2 = lib().gsb_debug_extract(device, text, len(text), fmt, kind, k, _ptr(lo), _ptr(hi), n, C.byref(nr), err, 512)
+    assert n2 == n
+    return lo, hi, nr.value

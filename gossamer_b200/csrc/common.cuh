@@ -1,0 +1,138 @@
+// common.cuh -- shared device/host helpers for the gossamer_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+namespace gsb {
+
+// 128-bit key for k+1 > 32 (the reference always uses BigInteger<2>, src/RankSelect.hh:72;
+// a 64-bit key is the specialisation for 2*rho <= 64).
+struct __align__(16) Key128 {
+    u64 lo, hi;
+};
+
+template <typename K> struct KeyOps;
+
+template <> struct KeyOps<u64> {
+    static const int kBytes = 8;
+    __host__ __device__ static __forceinline__ u32 digit(u64 k, int shift) { return (u32)(k >> shift) & 0xFFu; }
+    __host__ __device__ static __forceinline__ bool eq(u64 a, u64 b) { return a == b; }
+    __host__ __device__ static __forceinline__ bool lt(u64 a, u64 b) { return a < b; }
+    __host__ __device__ static __forceinline__ u64 shr64(u64 k, int d) { return d >= 64 ? 0ull : (k >> d); }  // (k >> d) low 64 bits
+    __host__ __device__ static __forceinline__ u64 lo(u64 k) { return k; }
+    __host__ __device__ static __forceinline__ u64 hi(u64) { return 0; }
+    __host__ __device__ static __forceinline__ u64 make(u64 lo, u64) { return lo; }
+};
+
+template <> struct KeyOps<Key128> {
+    static const int kBytes = 16;
+    __host__ __device__ static __forceinline__ u32 digit(const Key128& k, int shift) {
+        return shift < 64 ? (u32)(k.lo >> shift) & 0xFFu : (u32)(k.hi >> (shift - 64)) & 0xFFu;   // digits are byte aligned
+    }
+    __host__ __device__ static __forceinline__ bool eq(const Key128& a, const Key128& b) { return a.lo == b.lo && a.hi == b.hi; }
+    __host__ __device__ static __forceinline__ bool lt(const Key128& a, const Key128& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+    __host__ __device__ static __forceinline__ u64 shr64(const Key128& k, int d) {
+        if (d == 0) return k.lo;
+        if (d < 64) return (k.lo >> d) | (k.hi << (64 - d));
+        if (d < 128) return k.hi >> (d - 64);
+        return 0;
+    }
+    __host__ __device__ static __forceinline__ u64 lo(const Key128& k) { return k.lo; }
+    __host__ __device__ static __forceinline__ u64 hi(const Key128& k) { return k.hi; }
+    __host__ __device__ static __forceinline__ Key128 make(u64 lo, u64 hi) { Key128 k; k.lo = lo; k.hi = hi; return k; }
+};
+
+// Base-4 digit reversal (what Gossamer::rev computes, src/Utils.hh:377-396), via the
+// hardware bit reverse followed by a swap inside each 2-bit group.
+__device__ __forceinline__ u64 rev_base4(u64 x) {
+    u64 r = __brevll(x);
+    return ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);
+}
+
+// ---- decoupled look-back over tiles ---------------------------------------------------------
+// state word = status (top 2 bits: 0 empty, 1 tile aggregate, 2 inclusive prefix) | value.
+template <typename T> struct LookbackWord;
+template <> struct LookbackWord<u32> { static const int kShift = 30; static const u32 kMask = 0x3FFFFFFFu; };
+template <> struct LookbackWord<u64> { static const int kShift = 62; static const u64 kMask = 0x3FFFFFFFFFFFFFFFull; };
+
+template <typename T>
+__device__ __forceinline__ T ld_volatile(const T* p) { return *(const volatile T*)p; }
+template <typename T>
+__device__ __forceinline__ void st_volatile(T* p, T v) { *(volatile T*)p = v; }
+
+// Called by ONE thread per (tile, bin).  `states` is indexed [tile * stride + bin]; tiles must be
+// numbered by an atomic ticket so that every lower tile is already running.
+template <typename T>
+__device__ __forceinline__ T lookback_exclusive(T* states, u32 stride, u32 tile, u32 bin, T aggregate) {
+    const int S = LookbackWord<T>::kShift;
+    const T M = LookbackWord<T>::kMask;
+    T* mine = states + (size_t)tile * stride + bin;
+    if (tile == 0) {
+        st_volatile(mine, (T)(((T)2 << S) | aggregate));
+        return 0;
+    }
+    st_volatile(mine, (T)(((T)1 << S) | aggregate));
+    T excl = 0;
+    for (long long t = (long long)tile - 1;; --t) {
+        const T* p = states + (size_t)t * stride + bin;
+        T s;
+        do { s = ld_volatile(p); } while ((s >> S) == 0);
+        excl += s & M;
+        if ((s >> S) == 2) break;
+    }
+    st_volatile(mine, (T)(((T)2 << S) | (excl + aggregate)));
+    return excl;
+}
+
+// block-wide exclusive scan of one value per thread (THREADS multiple of 32, <= 1024)
+template <typename T, int THREADS>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* total, T* smem /* THREADS/32 + 1 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < THREADS / 32 ? smem[lane] : (T)0;
+        T winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        if (lane < THREADS / 32) smem[lane] = winc - w;
+        if (lane == 31) smem[THREADS / 32] = winc;
+    }
+    __syncthreads();
+    T res = smem[warp] + inc - v;
+    if (total) *total = smem[THREADS / 32];
+    __syncthreads();
+    return res;
+}
+
+static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace gsb
+
+#define GSB_CUDA_TRY(expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) throw gsb::CudaError(_e, #expr, __FILE__, __LINE__);            \
+    } while (0)
+
+namespace gsb {
+struct CudaError {
+    cudaError_t code; const char* expr; const char* file; int line;
+    CudaError(cudaError_t c, const char* e, const char* f, int l) : code(c), expr(e), file(f), line(l) {}
+};
+}  // namespace gsb

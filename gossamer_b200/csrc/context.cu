@@ -1,0 +1,663 @@
+// context.cu -- the C ABI of include/gossamer_b200.h: context, memory, per-block pipeline,
+// batching/merging, emission of the Graph / KmerSet file sets.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <new>
+
+#include "exchange.h"
+#include "kernels.h"
+
+namespace gsb {
+
+// ------------------------------------------------------------------------------------------
+// Workspace
+// ------------------------------------------------------------------------------------------
+void* Workspace::alloc(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw StatusError{GSB_ENOMEM, std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e)};
+    }
+    live_bytes += bytes;
+    peak_bytes = std::max(peak_bytes, live_bytes);
+    return p;
+}
+void Workspace::release(void* p, size_t bytes) {
+    cudaFreeAsync(p, stream);
+    live_bytes -= bytes;
+}
+void Workspace::sync() { GSB_CUDA_TRY(cudaStreamSynchronize(stream)); }
+
+struct PhaseTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t s = nullptr;
+    void init(cudaStream_t st) { s = st; GSB_CUDA_TRY(cudaEventCreate(&e0)); GSB_CUDA_TRY(cudaEventCreate(&e1)); }
+    void destroy() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); e0 = e1 = nullptr; }
+    void start() { GSB_CUDA_TRY(cudaEventRecord(e0, s)); }
+    void stop(double& acc_ms) {
+        GSB_CUDA_TRY(cudaEventRecord(e1, s));
+        GSB_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        acc_ms += ms;
+    }
+};
+
+static const u64 kMaxBlockBytes = 1ull << 30;
+
+}  // namespace gsb
+
+using namespace gsb;
+
+struct gsb_ctx {
+    gsb_config cfg;
+    Workspace ws;
+    std::string err;
+    int key_bytes = 8, key_bits = 0, window = 0, passes = 0;
+
+    // instance keys of the current batch
+    DevBuf<u8> keys;
+    u64 keys_cap = 0, n_keys = 0;
+    DevBuf<u64> cursor;            // device-side append cursor
+    DevBuf<u64> hist;              // fused digit histograms [passes][256]
+    DevBuf<IngestStatus> status;
+    u64 max_batch_keys = 0;
+
+    // per-format open-file state
+    bool file_open[3] = {false, false, false};
+    u64 line_base[3] = {0, 0, 0};
+    DevBuf<u8> carry;              // last window-1 symbols of an unfinished FASTA file
+    u32 n_carry = 0;
+
+    // host<->device staging
+    u8* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    DevBuf<u8> text_dev;
+    size_t text_cap = 0;
+
+    ReducedRun acc;                // merged (key,count) run of all flushed batches
+    bool have_acc = false;
+    bool counted = false;
+    gsb_counts counts;
+    gsb_stats stats;
+    PhaseTimer timer;
+    Exchange* comm = nullptr;
+
+    void log(int sev, const std::string& m) { if (cfg.log) cfg.log(cfg.log_user, sev, m.c_str()); }
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename F>
+int guarded(gsb_ctx* ctx, F&& body) {
+    try {
+        if (ctx) GSB_CUDA_TRY(cudaSetDevice(ctx->ws.device));
+        body();
+        return GSB_OK;
+    } catch (const StatusError& e) {
+        if (ctx) ctx->err = e.message; else g_create_error = e.message;
+        return e.status;
+    } catch (const CudaError& e) {
+        std::string m = std::string("CUDA error: ") + cudaGetErrorString(e.code) + " at " + e.file + ":" + std::to_string(e.line) + " (" + e.expr + ")";
+        cudaGetLastError();
+        if (ctx) ctx->err = m; else g_create_error = m;
+        return GSB_ECUDA;
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "host allocation failed"; else g_create_error = "host allocation failed";
+        return GSB_ENOMEM;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = e.what(); else g_create_error = e.what();
+        return GSB_EINVAL;
+    }
+}
+
+std::string parse_message(int code, u64 line) {
+    const std::string n = std::to_string(line);
+    switch (code) {
+        case GSB_PE_FASTA_EXPECT_GT: return "expected '>' at beginning of line " + n;
+        case GSB_PE_FASTQ_EXPECT_AT: return "expected '@' at beginning of line " + n;
+        case GSB_PE_FASTQ_EXPECT_SEQ: return "expected sequence data or quality header at line " + n;
+        case GSB_PE_FASTQ_EXPECT_PLUS: return "expected '+' at beginning of line " + n;
+        case GSB_PE_FASTQ_TITLE_MISMATCH: return "quality title does not match sequence title at line " + n;
+        case GSB_PE_FASTQ_LEN_MISMATCH: return "length mistmatch between sequence and quality data just before line " + n;
+        default: return "internal ingest error " + std::to_string(code);
+    }
+}
+
+void reset_batch(gsb_ctx* c) {
+    cudaStream_t s = c->ws.stream;
+    GSB_CUDA_TRY(cudaMemsetAsync(c->cursor.p, 0, 8, s));
+    GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), s));
+    c->n_keys = 0;
+}
+
+// merge two reduced runs: concatenate, sort by key carrying the counts, sum equal keys
+void merge_runs(gsb_ctx* c, ReducedRun& into, ReducedRun& other) {
+    Workspace& ws = c->ws;
+    cudaStream_t s = ws.stream;
+    const u64 n = into.m + other.m;
+    const int kb = c->key_bytes;
+    DevBuf<u8> ka(&ws, n * kb), kbuf(&ws, n * kb);
+    DevBuf<u64> va(&ws, n), vb(&ws, n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(ka.p, into.keys.p, into.m * kb, cudaMemcpyDeviceToDevice, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(ka.p + into.m * kb, other.keys.p, other.m * kb, cudaMemcpyDeviceToDevice, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(va.p, into.counts.p, into.m * 8, cudaMemcpyDeviceToDevice, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(va.p + into.m, other.counts.p, other.m * 8, cudaMemcpyDeviceToDevice, s));
+    into.keys.free(); into.counts.free(); other.keys.free(); other.counts.free();
+    int where = sort_keys(ws, kb, c->key_bits, ka.p, kbuf.p, va.p, vb.p, n, nullptr, nullptr);
+    ReducedRun merged; u64 distinct = 0;
+    reduce_sorted(ws, kb, where ? kbuf.p : ka.p, where ? vb.p : va.p, n, 1, merged, &distinct, nullptr);
+    into = std::move(merged);
+    other.m = 0;
+}
+
+// sort + run-length reduce the buffered instance keys; fold into the accumulated run
+void flush_batch(gsb_ctx* c, bool final_and_only) {
+    if (c->n_keys == 0) return;
+    Workspace& ws = c->ws;
+    const int kb = c->key_bytes;
+    DevBuf<u8> alt(&ws, c->n_keys * kb);
+    int passes_run = 0;
+    c->timer.start();
+    int where = sort_keys(ws, kb, c->key_bits, c->keys.p, alt.p, nullptr, nullptr, c->n_keys, c->hist.p, &passes_run);
+    c->timer.stop(c->stats.ms_sort);
+    c->stats.sort_passes += passes_run;
+    c->stats.sort_passes_model += c->passes;
+    c->stats.n_batches += 1;
+    ReducedRun run; u64 distinct = 0;
+    const u64 min_count = (final_and_only && c->cfg.kind == GSB_KIND_GRAPH && !c->comm) ? std::max<u64>(1, c->cfg.min_count) : 1;
+    c->timer.start();
+    reduce_sorted(ws, kb, where ? alt.p : c->keys.p, nullptr, c->n_keys, min_count, run, &distinct, where ? c->keys.p : alt.p);
+    c->timer.stop(c->stats.ms_reduce);
+    c->counts.n_instances += c->n_keys;
+    if (final_and_only) c->counts.n_distinct = distinct;
+    alt.free();
+    if (c->have_acc) {
+        c->timer.start();
+        merge_runs(c, c->acc, run);
+        c->timer.stop(c->stats.ms_merge);
+    } else {
+        c->acc = std::move(run);
+        c->have_acc = true;
+    }
+    reset_batch(c);
+}
+
+void ensure_key_capacity(gsb_ctx* c, u64 extra) {
+    const int kb = c->key_bytes;
+    if (c->n_keys + extra <= c->keys_cap) return;
+    if (c->n_keys + extra > c->max_batch_keys && c->n_keys > 0) {
+        c->log(0, "key buffer full: sorting and reducing a batch of " + std::to_string(c->n_keys) + " keys");
+        flush_batch(c, false);
+    }
+    if (c->n_keys + extra <= c->keys_cap) return;
+    u64 want = std::max<u64>(c->n_keys + extra, std::min<u64>(c->keys_cap * 2, c->max_batch_keys));
+    DevBuf<u8> bigger(&c->ws, want * kb);
+    if (c->n_keys) GSB_CUDA_TRY(cudaMemcpyAsync(bigger.p, c->keys.p, c->n_keys * kb, cudaMemcpyDeviceToDevice, c->ws.stream));
+    c->keys = std::move(bigger);
+    c->keys_cap = want;
+}
+
+// one raw text block already on the device
+void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
+    Workspace& ws = c->ws;
+    cudaStream_t s = ws.stream;
+    if (format < 0 || format > 2) throw StatusError{GSB_EINVAL, "unknown input format"};
+    if (n > kMaxBlockBytes) throw StatusError{GSB_EINVAL, "input blocks are limited to 1 GiB; split the file at record boundaries"};
+    if (c->counted) throw StatusError{GSB_EINVAL, "gsb_push_block after gsb_finish_counting (call gsb_reset first)"};
+    const bool file_start = !c->file_open[format];
+    const bool last = (flags & GSB_BLOCK_LAST_OF_FILE) != 0;
+    c->stats.bytes_in += n;
+
+    // K1: line table
+    c->timer.start();
+    GSB_CUDA_TRY(cudaMemsetAsync(c->status.p, 0, sizeof(IngestStatus), s));
+    const u32 tiles = ingest_newline_tiles(n);
+    DevBuf<u32> tile_counts(&ws, (size_t)tiles + 1), scalars(&ws, 4);
+    ingest_count_newlines(text, n, tile_counts.p, s, &ws.launches);
+    ingest_scan_tiles(tile_counts.p, tiles, scalars.p, s, &ws.launches);
+    u32 n_newlines = 0; u8 last_byte = '\n';
+    GSB_CUDA_TRY(cudaMemcpyAsync(&n_newlines, scalars.p, 4, cudaMemcpyDeviceToHost, s));
+    if (n) GSB_CUDA_TRY(cudaMemcpyAsync(&last_byte, text + n - 1, 1, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    const u32 n_lines = n_newlines + ((n > 0 && last_byte != '\n') ? 1u : 0u);
+    DevBuf<u32> line_start(&ws, (size_t)n_lines + 1), nsym(&ws, (size_t)n_lines + 1), sym_off(&ws, (size_t)n_lines + 1);
+    DevBuf<u8> kind(&ws, (size_t)n_lines + 1);
+    DevBuf<u32> scan_tmp(&ws, (size_t)(n_lines / 2048 + 2));
+    GSB_CUDA_TRY(cudaMemsetAsync(line_start.p, 0, 4, s));
+    ingest_fill_line_starts(text, n, tile_counts.p, line_start.p, n_lines, s, &ws.launches);
+
+    // K1b: framing
+    ingest_classify(text, line_start.p, n_lines, format, file_start ? 1 : 0, c->line_base[format], kind.p, nsym.p, c->status.p, s, &ws.launches);
+    ingest_symbol_offsets(nsym.p, sym_off.p, n_lines, scalars.p + 1, scan_tmp.p, s, &ws.launches);
+    GSB_CUDA_TRY(cudaMemcpyAsync(sym_off.p + n_lines, scalars.p + 1, 4, cudaMemcpyDeviceToDevice, s));
+    IngestStatus st; u32 block_syms = 0;
+    GSB_CUDA_TRY(cudaMemcpyAsync(&st, c->status.p, sizeof(st), cudaMemcpyDeviceToHost, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(&block_syms, scalars.p + 1, 4, cudaMemcpyDeviceToHost, s));
+    c->timer.stop(c->stats.ms_scan);
+    if (st.error) throw StatusError{GSB_EPARSE, parse_message(st.error, st.error_line)};
+    c->counts.n_reads += st.n_reads;
+
+    const u64 per = c->cfg.kind == GSB_KIND_GRAPH ? 2 : 1;
+    ensure_key_capacity(c, (u64)block_syms * per);     // may sort+reduce the current batch first
+
+    // K2: packed symbol stream = [64 pad][carry][block]
+    c->timer.start();
+    const u32 n_carry = (format == GSB_FMT_FASTA && !file_start) ? c->n_carry : 0;
+    const u64 n_sym_total = 64 + (u64)n_carry + block_syms;
+    const u64 n_words = (n_sym_total + 31) / 32;
+    DevBuf<u64> codes(&ws, n_words);
+    DevBuf<u32> valid(&ws, n_words);
+    ingest_pack(text, line_start.p, kind.p, sym_off.p, n_lines, c->carry.p, n_carry, n_sym_total, codes.p, valid.p, n_words, s, &ws.launches);
+    line_start.free(); nsym.free(); sym_off.free(); kind.free();
+    c->stats.n_symbols += block_syms;
+
+    // K3: windows -> keys (+ fused digit histograms)
+    ingest_extract(c->cfg.kind, c->key_bytes, codes.p, valid.p, 64 + n_carry, n_sym_total, c->window, c->passes,
+                   c->keys.p, c->cursor.p, c->keys_cap, c->hist.p, c->status.p, ws.sm_count, s, &ws.launches);
+    u64 cur = 0;
+    GSB_CUDA_TRY(cudaMemcpyAsync(&cur, c->cursor.p, 8, cudaMemcpyDeviceToHost, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(&st, c->status.p, sizeof(st), cudaMemcpyDeviceToHost, s));
+    // carry for a FASTA file that continues in the next block
+    if (format == GSB_FMT_FASTA && !last) {
+        const u32 want = (u32)std::min<u64>((u64)c->window - 1, n_sym_total - 64);
+        ingest_save_carry(codes.p, valid.p, n_sym_total, want, c->carry.p, s, &ws.launches);
+        c->n_carry = want;
+    } else if (format == GSB_FMT_FASTA) {
+        c->n_carry = 0;
+    }
+    c->timer.stop(c->stats.ms_extract);
+    if (st.error) throw StatusError{GSB_EINVAL, "key buffer overflow (internal sizing error)"};
+    c->n_keys = cur;
+    c->file_open[format] = !last;
+    c->line_base[format] = last ? 0 : c->line_base[format] + n_lines;
+}
+
+void write_graph_files(gsb_ctx* c, Emitter& em, const std::string& prefix) {
+    const u64 k = (u64)c->cfg.k;
+    const u64 m = c->acc.m;
+    // Graph::Builder ctor writes the header first (src/Graph.cc:159-166)
+    u64 header[3] = {2011101014ull, k, 0};
+    em.put_host(prefix + ".header", header, sizeof(header));
+    const unsigned rho2 = 2 * (unsigned)(k + 1);
+    U128 universe = rho2 < 64 ? U128{1ull << rho2, 0} : U128{0, 1ull << (rho2 - 64)};
+    emit_sparse_array(em, c->key_bytes, c->acc.keys.p, m, universe, m, universe, prefix + "-edges");
+    emit_counts(em, c->acc.counts.p, m, m, prefix + "-counts");
+    emit_count_histogram(em, c->acc.counts.p, m, prefix + "-counts-hist.txt");
+}
+
+void write_kmer_set_files(gsb_ctx* c, Emitter& em, const std::string& prefix) {
+    const u64 k = (u64)c->cfg.k;
+    const u64 m = c->acc.m;
+    const unsigned bits = 2 * (unsigned)k;
+    U128 universe = bits < 64 ? U128{1ull << bits, 0} : U128{0, 1ull << (bits - 64)};
+    emit_sparse_array(em, c->key_bytes, c->acc.keys.p, m, universe, m, universe, prefix + ".kmers");
+    u64 header[3] = {2011101701ull, k, m};             // KmerSet::Builder::end, src/KmerSet.hh:76-83
+    em.put_host(prefix + ".header", header, sizeof(header));
+}
+
+void init_ctx(gsb_ctx* c) {
+    const gsb_config& cfg = c->cfg;
+    if (cfg.abi_version != GSB_ABI_VERSION) throw StatusError{GSB_EINVAL, "ABI version mismatch"};
+    if (cfg.kind != GSB_KIND_GRAPH && cfg.kind != GSB_KIND_KMERSET) throw StatusError{GSB_EINVAL, "unknown kind"};
+    const int max_k = cfg.kind == GSB_KIND_GRAPH ? 62 : 63;
+    if (cfg.k < 1 || cfg.k > max_k)
+        throw StatusError{GSB_ERANGE, "unable to build a graph with k=" + std::to_string(cfg.k)};
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        throw StatusError{GSB_ECUDA, "no CUDA device available (this library has no CPU path)"};
+    }
+    if (cfg.device < 0 || cfg.device >= n_dev) throw StatusError{GSB_EINVAL, "bad device ordinal"};
+    c->ws.device = cfg.device;
+    GSB_CUDA_TRY(cudaSetDevice(cfg.device));
+    cudaDeviceProp prop;
+    GSB_CUDA_TRY(cudaGetDeviceProperties(&prop, cfg.device));
+    if (prop.major < 10) throw StatusError{GSB_ECUDA, std::string("device ") + prop.name + " is not sm_100-class; this build targets B200 only"};
+    c->ws.sm_count = prop.multiProcessorCount;
+    GSB_CUDA_TRY(cudaStreamCreateWithFlags(&c->ws.stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    GSB_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, cfg.device));
+    u64 threshold = ~0ull;
+    GSB_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    c->timer.init(c->ws.stream);
+
+    c->window = cfg.kind == GSB_KIND_GRAPH ? cfg.k + 1 : cfg.k;
+    c->key_bits = 2 * c->window;
+    c->key_bytes = c->key_bits <= 64 ? 8 : 16;
+    c->passes = (c->key_bits + 7) / 8;
+    c->cursor.reset(&c->ws, 1);
+    c->hist.reset(&c->ws, (size_t)c->passes * 256);
+    c->status.reset(&c->ws, 1);
+    c->carry.reset(&c->ws, 64);
+    size_t free_b = 0, total_b = 0;
+    GSB_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    // per buffered key: two sort buffers + run-length positions
+    const u64 per_key = 2 * (u64)c->key_bytes + 8;
+    c->max_batch_keys = cfg.max_batch_keys ? cfg.max_batch_keys : (u64)(free_b * 0.7) / per_key;
+    c->pinned_bytes = 64ull << 20;
+    GSB_CUDA_TRY(cudaMallocHost((void**)&c->pinned, c->pinned_bytes));
+    memset(&c->counts, 0, sizeof(c->counts));
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.sort_key_bytes = c->key_bytes;
+    reset_batch(c);
+    c->ws.sync();
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsb_create(const gsb_config* cfg, gsb_ctx** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return GSB_EINVAL; }
+    *out = nullptr;
+    gsb_ctx* c = new (std::nothrow) gsb_ctx();
+    if (!c) { g_create_error = "host allocation failed"; return GSB_ENOMEM; }
+    c->cfg = *cfg;
+    int rc = guarded(nullptr, [&] { init_ctx(c); });
+    if (rc != GSB_OK) { gsb_destroy(c); return rc; }
+    *out = c;
+    return GSB_OK;
+}
+
+void gsb_destroy(gsb_ctx* c) {
+    if (!c) return;
+    if (c->ws.stream) {
+        cudaSetDevice(c->ws.device);
+        cudaStreamSynchronize(c->ws.stream);
+    }
+    if (c->comm) { exchange_destroy(c->comm); c->comm = nullptr; }
+    c->keys.free(); c->cursor.free(); c->hist.free(); c->status.free(); c->carry.free(); c->text_dev.free();
+    c->acc.keys.free(); c->acc.counts.free();
+    c->timer.destroy();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->ws.stream) { cudaStreamSynchronize(c->ws.stream); cudaStreamDestroy(c->ws.stream); }
+    delete c;
+}
+
+const char* gsb_last_error(const gsb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int gsb_push_block(gsb_ctx* c, const void* data, size_t nbytes, int format, uint32_t flags) {
+    if (!c || (!data && nbytes)) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (nbytes > kMaxBlockBytes) throw StatusError{GSB_EINVAL, "input blocks are limited to 1 GiB; split the file at record boundaries"};
+        if (nbytes + 16 > c->text_cap) {
+            c->text_dev.free();
+            c->text_cap = std::max<size_t>(nbytes + 16, 1 << 20);
+            c->text_dev.reset(&c->ws, c->text_cap);
+        }
+        c->timer.start();
+        if (nbytes) GSB_CUDA_TRY(cudaMemcpyAsync(c->text_dev.p, data, nbytes, cudaMemcpyHostToDevice, c->ws.stream));
+        c->timer.stop(c->stats.ms_h2d);
+        process_block(c, c->text_dev.p, nbytes, format, flags);
+    });
+}
+
+int gsb_push_device_block(gsb_ctx* c, const void* device_data, size_t nbytes, int format, uint32_t flags) {
+    if (!c || (!device_data && nbytes)) return GSB_EINVAL;
+    return guarded(c, [&] {
+        const u8* text = (const u8*)device_data;
+        if (((uintptr_t)text & 15) != 0) {                     // vector loads need 16-byte alignment: take a private copy
+            if (nbytes + 16 > c->text_cap) {
+                c->text_dev.free();
+                c->text_cap = std::max<size_t>(nbytes + 16, 1 << 20);
+                c->text_dev.reset(&c->ws, c->text_cap);
+            }
+            GSB_CUDA_TRY(cudaMemcpyAsync(c->text_dev.p, device_data, nbytes, cudaMemcpyDeviceToDevice, c->ws.stream));
+            text = c->text_dev.p;
+        }
+        process_block(c, text, nbytes, format, flags);
+    });
+}
+
+int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
+    if (!c) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (!c->counted) {
+            const bool single = !c->have_acc;
+            flush_batch(c, single);
+            if (!c->have_acc) { c->acc.keys.reset(&c->ws, 0); c->acc.counts.reset(&c->ws, 0); c->acc.m = 0; c->have_acc = true; }
+            if (c->comm) {
+                c->timer.start();
+                exchange_runs(c->comm, c->ws, c->key_bytes, c->key_bits, c->acc);
+                c->timer.stop(c->stats.ms_exchange);
+            }
+            const u64 min_count = c->cfg.kind == GSB_KIND_GRAPH ? std::max<u64>(1, c->cfg.min_count) : 1;
+            const bool filtered_already = single && !c->comm;
+            if (!filtered_already) {
+                u64 local_distinct = c->acc.m;
+                if (min_count > 1 && c->acc.m) {
+                    c->timer.start();
+                    DevBuf<u8> fk(&c->ws, c->acc.m * c->key_bytes);
+                    DevBuf<u64> fc(&c->ws, c->acc.m), total(&c->ws, 1);
+                    DevBuf<u8> lb(&c->ws, rle_lookback_bytes(c->acc.m));
+                    sort_filter(c->key_bytes, c->acc.keys.p, c->acc.counts.p, c->acc.m, min_count, fk.p, fc.p, lb.p, total.p, c->ws.stream, &c->ws.launches);
+                    u64 kept = 0;
+                    GSB_CUDA_TRY(cudaMemcpyAsync(&kept, total.p, 8, cudaMemcpyDeviceToHost, c->ws.stream));
+                    c->ws.sync();
+                    c->acc.keys = std::move(fk); c->acc.counts = std::move(fc); c->acc.m = kept;
+                    c->timer.stop(c->stats.ms_reduce);
+                }
+                c->counts.n_distinct = c->comm ? exchange_sum(c->comm, c->ws, local_distinct) : local_distinct;
+            }
+            c->counts.n_kept = c->comm ? exchange_sum(c->comm, c->ws, c->acc.m) : c->acc.m;
+            if (c->comm) c->counts.n_instances = exchange_sum(c->comm, c->ws, c->counts.n_instances);
+            c->counted = true;
+        }
+        if (out) *out = c->counts;
+    });
+}
+
+int gsb_emit(gsb_ctx* c, const char* prefix, const gsb_sink* sink) {
+    if (!c || !prefix || !sink || !sink->open || !sink->pwrite || !sink->close) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_emit before gsb_finish_counting"};
+        Emitter em;
+        em.ws = &c->ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
+        c->timer.start();
+        if (c->cfg.kind == GSB_KIND_GRAPH) write_graph_files(c, em, prefix);
+        else write_kmer_set_files(c, em, prefix);
+        c->timer.stop(c->stats.ms_emit);
+        c->stats.bytes_out += em.bytes_out;
+    });
+}
+
+int gsb_get_stats(const gsb_ctx* c, gsb_stats* out) {
+    if (!c || !out) return GSB_EINVAL;
+    *out = c->stats;
+    out->kernel_launches = c->ws.launches;
+    out->hbm_peak_bytes = c->ws.peak_bytes;
+    return GSB_OK;
+}
+
+int gsb_reset(gsb_ctx* c) {
+    if (!c) return GSB_EINVAL;
+    return guarded(c, [&] {
+        c->acc.keys.free(); c->acc.counts.free(); c->acc.m = 0;
+        c->have_acc = false; c->counted = false;
+        for (int f = 0; f < 3; ++f) { c->file_open[f] = false; c->line_base[f] = 0; }
+        c->n_carry = 0;
+        memset(&c->counts, 0, sizeof(c->counts));
+        const u64 launches = c->ws.launches;
+        memset(&c->stats, 0, sizeof(c->stats));
+        c->stats.sort_key_bytes = c->key_bytes;
+        c->ws.launches = launches;
+        reset_batch(c);
+    });
+}
+
+int gsb_comm_make_id(void* id_out) {
+    if (!id_out) return GSB_EINVAL;
+    return guarded(nullptr, [&] { exchange_make_id(id_out); });
+}
+
+int gsb_comm_attach(gsb_ctx* c, const void* id, int n_ranks, int rank) {
+    if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (c->comm) throw StatusError{GSB_EINVAL, "communicator already attached"};
+        c->comm = exchange_create(id, n_ranks, rank, c->ws);
+    });
+}
+
+int gsb_gather_to_root(gsb_ctx* c) {
+    if (!c) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_gather_to_root before gsb_finish_counting"};
+        if (!c->comm) return;
+        c->timer.start();
+        exchange_gather(c->comm, c->ws, c->key_bytes, c->acc);
+        c->timer.stop(c->stats.ms_exchange);
+    });
+}
+
+int64_t gsb_debug_copy_counts(gsb_ctx* c, uint64_t* key_lo, uint64_t* key_hi, uint64_t* counts, uint64_t cap) {
+    if (!c) return GSB_EINVAL;
+    int64_t result = 0;
+    int rc = guarded(c, [&] {
+        if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_debug_copy_counts before gsb_finish_counting"};
+        const u64 m = c->acc.m, take = std::min<u64>(m, cap);
+        std::vector<u64> raw(take * (c->key_bytes / 8));
+        GSB_CUDA_TRY(cudaMemcpyAsync(raw.data(), c->acc.keys.p, take * c->key_bytes, cudaMemcpyDeviceToHost, c->ws.stream));
+        if (counts) GSB_CUDA_TRY(cudaMemcpyAsync(counts, c->acc.counts.p, take * 8, cudaMemcpyDeviceToHost, c->ws.stream));
+        c->ws.sync();
+        for (u64 i = 0; i < take; ++i) {
+            if (c->key_bytes == 8) { if (key_lo) key_lo[i] = raw[i]; if (key_hi) key_hi[i] = 0; }
+            else { if (key_lo) key_lo[i] = raw[2 * i]; if (key_hi) key_hi[i] = raw[2 * i + 1]; }
+        }
+        result = (int64_t)m;
+    });
+    return rc == GSB_OK ? result : rc;
+}
+
+// ---- test-only entry points -----------------------------------------------------------------
+
+int64_t gsb_debug_extract(int device, const void* text, size_t nbytes, int format, int kind, int k,
+                          uint64_t* key_lo, uint64_t* key_hi, uint64_t cap, uint64_t* n_reads,
+                          char* err, size_t errcap) {
+    gsb_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = GSB_ABI_VERSION; cfg.kind = kind; cfg.k = k; cfg.device = device;
+    gsb_ctx* c = nullptr;
+    int rc = gsb_create(&cfg, &c);
+    auto report = [&](const char* m) { if (err && errcap) { strncpy(err, m, errcap - 1); err[errcap - 1] = 0; } };
+    if (rc != GSB_OK) { report(gsb_last_error(nullptr)); return rc; }
+    rc = gsb_push_block(c, text, nbytes, format, GSB_BLOCK_LAST_OF_FILE);
+    if (rc != GSB_OK) { report(gsb_last_error(c)); gsb_destroy(c); return rc; }
+    int64_t n = (int64_t)c->n_keys;
+    rc = guarded(c, [&] {
+        const u64 take = std::min<u64>(c->n_keys, cap);
+        std::vector<u64> raw(take * (c->key_bytes / 8));
+        GSB_CUDA_TRY(cudaMemcpyAsync(raw.data(), c->keys.p, take * c->key_bytes, cudaMemcpyDeviceToHost, c->ws.stream));
+        c->ws.sync();
+        for (u64 i = 0; i < take; ++i) {
+            if (c->key_bytes == 8) { if (key_lo) key_lo[i] = raw[i]; if (key_hi) key_hi[i] = 0; }
+            else { if (key_lo) key_lo[i] = raw[2 * i]; if (key_hi) key_hi[i] = raw[2 * i + 1]; }
+        }
+        if (n_reads) *n_reads = c->counts.n_reads;
+    });
+    if (rc != GSB_OK) { report(gsb_last_error(c)); n = rc; }
+    gsb_destroy(c);
+    return n;
+}
+
+namespace {
+struct DebugDevice {
+    Workspace ws;
+    u8* pinned = nullptr;
+    void open(int device) {
+        int n_dev = 0;
+        if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); throw StatusError{GSB_ECUDA, "no CUDA device available (this library has no CPU path)"}; }
+        ws.device = device;
+        GSB_CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        GSB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        ws.sm_count = prop.multiProcessorCount;
+        GSB_CUDA_TRY(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+        GSB_CUDA_TRY(cudaMallocHost((void**)&pinned, 16 << 20));
+    }
+    ~DebugDevice() {
+        if (ws.stream) { cudaStreamSynchronize(ws.stream); cudaStreamDestroy(ws.stream); }
+        if (pinned) cudaFreeHost(pinned);
+    }
+};
+
+// host (lo, hi) arrays -> device key array
+void upload_keys(Workspace& ws, int key_bytes, const uint64_t* lo, const uint64_t* hi, u64 n, DevBuf<u8>& out) {
+    out.reset(&ws, n * key_bytes);
+    if (!n) return;
+    if (key_bytes == 8) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.p, lo, n * 8, cudaMemcpyHostToDevice, ws.stream));
+    } else {
+        std::vector<u64> inter(2 * n);
+        for (u64 i = 0; i < n; ++i) { inter[2 * i] = lo[i]; inter[2 * i + 1] = hi ? hi[i] : 0; }
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.p, inter.data(), n * 16, cudaMemcpyHostToDevice, ws.stream));
+        ws.sync();
+    }
+    ws.sync();
+}
+}  // namespace
+
+int64_t gsb_debug_sort_keys(int device, uint64_t* key_lo, uint64_t* key_hi, uint64_t n, int key_bits) {
+    int64_t passes = 0;
+    int rc = guarded(nullptr, [&] {
+        DebugDevice d; d.open(device);
+        const int kb = key_bits <= 64 ? 8 : 16;
+        DevBuf<u8> a, b(&d.ws, n * kb);
+        upload_keys(d.ws, kb, key_lo, key_hi, n, a);
+        int run = 0;
+        int where = sort_keys(d.ws, kb, key_bits, a.p, b.p, nullptr, nullptr, n, nullptr, &run);
+        std::vector<u64> raw(n * (kb / 8));
+        if (n) GSB_CUDA_TRY(cudaMemcpyAsync(raw.data(), where ? b.p : a.p, n * kb, cudaMemcpyDeviceToHost, d.ws.stream));
+        d.ws.sync();
+        for (u64 i = 0; i < n; ++i) {
+            if (kb == 8) key_lo[i] = raw[i];
+            else { key_lo[i] = raw[2 * i]; key_hi[i] = raw[2 * i + 1]; }
+        }
+        passes = run;
+        a.free(); b.free();
+    });
+    return rc == GSB_OK ? passes : rc;
+}
+
+int gsb_debug_emit_sparse_array(int device, const uint64_t* key_lo, const uint64_t* key_hi, uint64_t m,
+                                uint64_t universe_lo, uint64_t universe_hi, uint64_t m_est,
+                                const char* base, const gsb_sink* sink) {
+    return guarded(nullptr, [&] {
+        DebugDevice d; d.open(device);
+        const int kb = key_hi ? 16 : 8;
+        DevBuf<u8> keys;
+        upload_keys(d.ws, kb, key_lo, key_hi, m, keys);
+        Emitter em; em.ws = &d.ws; em.sink = sink; em.pinned = d.pinned; em.pinned_bytes = 16 << 20;
+        U128 u{universe_lo, universe_hi};
+        emit_sparse_array(em, kb, keys.p, m, u, m_est, u, base);
+        keys.free();
+    });
+}
+
+int gsb_debug_emit_graph(int device, const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* counts,
+                         uint64_t m, int k, const char* prefix, const gsb_sink* sink) {
+    gsb_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = GSB_ABI_VERSION; cfg.kind = GSB_KIND_GRAPH; cfg.k = k; cfg.device = device;
+    gsb_ctx* c = nullptr;
+    int rc = gsb_create(&cfg, &c);
+    if (rc != GSB_OK) return rc;
+    rc = guarded(c, [&] {
+        upload_keys(c->ws, c->key_bytes, key_lo, key_hi, m, c->acc.keys);
+        c->acc.counts.reset(&c->ws, m);
+        if (m) GSB_CUDA_TRY(cudaMemcpyAsync(c->acc.counts.p, counts, m * 8, cudaMemcpyHostToDevice, c->ws.stream));
+        c->ws.sync();
+        c->acc.m = m; c->have_acc = true; c->counted = true;
+    });
+    if (rc == GSB_OK) rc = gsb_emit(c, prefix, sink);
+    if (rc != GSB_OK) g_create_error = c->err;
+    gsb_destroy(c);
+    return rc;
+}
+
+}  // extern "C"

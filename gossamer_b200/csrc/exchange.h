@@ -1,0 +1,20 @@
+// exchange.h -- multi-GPU range partition + all-to-all of reduced (key,count) runs over NCCL.
+#pragma once
+#include "kernels.h"
+
+namespace gsb {
+
+struct Exchange;
+
+void exchange_make_id(void* id_out /* GSB_NCCL_ID_BYTES */);
+Exchange* exchange_create(const void* id, int n_ranks, int rank, Workspace& ws);
+void exchange_destroy(Exchange* x);
+// Range-partition `run` (sorted distinct keys + counts) by sampled splitters, all-to-all, merge:
+// afterwards rank r holds the r-th contiguous slice of the global order.
+void exchange_runs(Exchange* x, Workspace& ws, int key_bytes, int key_bits, ReducedRun& run);
+// sum of one u64 over all ranks
+u64 exchange_sum(Exchange* x, Workspace& ws, u64 v);
+// concatenate all ranks' runs on rank 0 in rank order (other ranks end up empty)
+void exchange_gather(Exchange* x, Workspace& ws, int key_bytes, ReducedRun& run);
+
+}  // namespace gsb

@@ -1,0 +1,136 @@
+// kernels.h -- internal interface between the CUDA modules (ingest / sort / emit) and the
+// context that owns memory and orchestrates them.  Not part of the public ABI.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/gossamer_b200.h"
+#include "common.cuh"
+
+namespace gsb {
+
+// parse / capacity errors raised on the device, rendered by the host with the reference's text
+enum {
+    GSB_PE_NONE = 0,
+    GSB_PE_FASTA_EXPECT_GT = 1,        // "expected '>' at beginning of line N"            src/FastaParser.hh:60-67
+    GSB_PE_FASTQ_EXPECT_AT = 2,        // "expected '@' at beginning of line N"            src/FastqParser.hh:89-97
+    GSB_PE_FASTQ_EXPECT_SEQ = 3,       // "expected sequence data or quality header at line N"   :107-113
+    GSB_PE_FASTQ_EXPECT_PLUS = 4,      // "expected '+' at beginning of line N"            :122-129
+    GSB_PE_FASTQ_TITLE_MISMATCH = 5,   // "quality title does not match sequence title at line N" :132-140
+    GSB_PE_FASTQ_LEN_MISMATCH = 6,     // "length mistmatch between sequence and quality data just before line N" :167-174
+    GSB_PE_KEY_OVERFLOW = 100
+};
+
+struct IngestStatus {
+    int error;
+    int fastq_irregular;
+    u64 error_line;
+    u64 n_reads;
+};
+
+// stream-ordered device allocator with a high-water mark (cudaMallocAsync pool underneath)
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    int sm_count = 148;
+    u64 launches = 0;
+    u64 live_bytes = 0, peak_bytes = 0;
+    void* alloc(size_t bytes);
+    void release(void* p, size_t bytes);
+    void sync();
+};
+
+template <typename T>
+struct DevBuf {
+    Workspace* ws = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(Workspace* w, size_t count) { reset(w, count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : ws(o.ws), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { free(); ws = o.ws; p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { free(); }
+    void reset(Workspace* w, size_t count) { free(); ws = w; n = count; p = (T*)w->alloc((count ? count : 1) * sizeof(T)); }
+    void free() { if (p) { ws->release(p, (n ? n : 1) * sizeof(T)); p = nullptr; n = 0; } }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---- ingest.cu -------------------------------------------------------------------------------
+u32 ingest_newline_tiles(u64 nbytes);
+void ingest_count_newlines(const u8* text, u64 n, u32* tile_counts, cudaStream_t s, u64* launches);
+void ingest_scan_tiles(u32* tile_counts, u32 tiles, u32* total, cudaStream_t s, u64* launches);
+void ingest_fill_line_starts(const u8* text, u64 n, const u32* tile_offsets, u32* line_start, u32 n_lines, cudaStream_t s, u64* launches);
+void ingest_classify(const u8* text, const u32* line_start, u32 n_lines, int format, int file_start, u64 line_base,
+                     u8* kind, u32* nsym, IngestStatus* st_dev, cudaStream_t s, u64* launches);
+void ingest_symbol_offsets(const u32* nsym, u32* sym_off, u32 n_lines, u32* total_dev, u32* tmp, cudaStream_t s, u64* launches);
+void ingest_pack(const u8* text, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
+                 const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, cudaStream_t s, u64* launches);
+void ingest_save_carry(const u64* codes, const u32* valid, u64 n_sym_total, u32 want, u8* carry_out, cudaStream_t s, u64* launches);
+void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
+                    void* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s, u64* launches);
+
+// ---- sort.cu ---------------------------------------------------------------------------------
+u64 sort_tile_keys(int key_bytes);
+u64 sort_lookback_bytes(int key_bytes, u64 n);
+void sort_digit_hist(int key_bytes, const void* keys, u64 n, int passes, u64* hist, int sm_count, cudaStream_t s, u64* launches);
+void sort_digit_base(const u64* hist, u64* base, int passes, cudaStream_t s, u64* launches);
+void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vout, u64 n, int pass, const u64* digit_base_all,
+               void* lookback, cudaStream_t s, u64* launches);
+u64 rle_lookback_bytes(u64 n);
+void sort_rle(int key_bytes, const void* keys, u64 n, void* out_keys, u64* out_pos, void* lookback, u64* total_dev, cudaStream_t s, u64* launches);
+void sort_counts_from_pos(const u64* pos, const u64* csum, u64 m, u64* counts, cudaStream_t s, u64* launches);
+void sort_filter(int key_bytes, const void* keys, const u64* counts, u64 m, u64 min_count, void* out_keys, u64* out_counts,
+                 void* lookback, u64* total_dev, cudaStream_t s, u64* launches);
+void sort_scan_weights(const u64* w, u64* csum, u64 n, u64* tmp, cudaStream_t s, u64* launches);
+u64 sort_scan_tmp_elems(u64 n);
+
+// Full sort of n keys (optionally with a u64 payload).  `a` holds the input; `b` is scratch of the
+// same size.  Digit histograms are computed here unless hist_dev (already accumulated, [passes][256])
+// is given.  Returns 0 if the result is in a, 1 if in b.  passes_run gets the number of sweeps.
+int sort_keys(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64* va, u64* vb, u64 n,
+              const u64* hist_dev, int* passes_run);
+
+// sorted keys (+ optional weights) -> distinct keys and summed counts, min-count filtered.
+// Outputs are freshly allocated; *m_distinct is the count before the filter.
+struct ReducedRun {
+    DevBuf<u8> keys;        // key_bytes * m
+    DevBuf<u64> counts;     // m
+    u64 m = 0;
+};
+// `dkeys_scratch` (optional) is a buffer of n keys that may be clobbered (the idle sort buffer).
+void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* weights, u64 n, u64 min_count,
+                   ReducedRun& out, u64* m_distinct, void* dkeys_scratch = nullptr);
+
+// ---- emit.cu ---------------------------------------------------------------------------------
+struct Emitter {
+    Workspace* ws;
+    const gsb_sink* sink;
+    u64 bytes_out = 0;
+    u8* pinned = nullptr;          // staging for device -> sink copies
+    size_t pinned_bytes = 0;
+    // whole file from host memory
+    void put_host(const std::string& name, const void* data, u64 len);
+    // whole file = optional host prefix that overrides the first prefix_len bytes + device payload
+    void put_device(const std::string& name, const void* dev, u64 len, const void* host_prefix = nullptr, u64 prefix_len = 0);
+};
+
+struct U128 { u64 lo, hi; };
+
+// SparseArray::Builder::d (src/SparseArray.cc:47-72), host side, double arithmetic
+u64 sparse_array_d(U128 universe, u64 m_est);
+
+// Elias-Fano set of `m` sorted distinct positions: writes base.header, base.high-bits, base-d0,
+// base-d1, base.low-bits[...] (src/SparseArray.{hh,cc}).
+void emit_sparse_array(Emitter& em, int key_bytes, const void* keys, u64 m, U128 universe_ctor, u64 m_est, U128 universe_end,
+                       const std::string& base);
+// VariableByteArray (src/VariableByteArray.{hh,cc}) from 64-bit counts (truncated to u32 as the reference does)
+void emit_counts(Emitter& em, const u64* counts, u64 m, u64 m_est, const std::string& base);
+// "count\tfrequency\n" lines in ascending count order (src/Graph.cc:127-133)
+void emit_count_histogram(Emitter& em, const u64* counts, u64 m, const std::string& name);
+
+struct ParseFailure { int code; u64 line; };
+struct StatusError { int status; std::string message; };
+
+}  // namespace gsb

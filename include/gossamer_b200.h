@@ -1,0 +1,161 @@
+/* gossamer_b200.h -- C ABI of the B200-native graph-construction path.
+ *
+ * This is the drop-in boundary for the reference's `build-graph` / `build-kmer-set` hot path.
+ * The reference has no FFI; its seam for this path is the command object
+ *   GossCmdBuildGraph::operator()(const GossCmdContext&)      src/GossCmdBuildGraph.cc:270-426
+ *   GossCmdBuildKmerSet::operator()(const GossCmdContext&)    src/GossCmdBuildKmerSet.tcc:212-332
+ * whose body is: read blocks -> (k+1)-mer/k-mer stream -> BackyardHash count -> sort ->
+ * Graph::Builder / KmerSet::Builder -> files through a FileFactory.  Each entry point below
+ * names the piece of that body it replaces.  INTEGRATION.md shows the patch a maintainer
+ * would apply to GossCmdBuildGraph.cc to call it.
+ *
+ * Conventions: plain C, no exceptions, no STL, no torch types.  Every call returns 0 or a
+ * negative gsb_status; gsb_last_error() has the detail text.  One gsb_ctx is driven by one
+ * host thread at a time.  The library owns all device memory and its own pinned staging; the
+ * caller owns the input buffers (until the call returns) and the file handles behind the sink.
+ * There is NO CPU fallback: without a usable CUDA device every call fails with GSB_ECUDA.
+ */
+#ifndef GOSSAMER_B200_H
+#define GOSSAMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_ABI_VERSION 1u
+
+typedef struct gsb_ctx gsb_ctx;
+
+typedef enum gsb_status {
+    GSB_OK = 0,
+    GSB_EINVAL = -1,  /* bad argument / call order */
+    GSB_EPARSE = -2,  /* malformed FASTA/FASTQ; message matches the reference's text (src/FastqParser.hh:89-175) */
+    GSB_EIO = -3,     /* sink callback failed */
+    GSB_ENOMEM = -4,
+    GSB_ECUDA = -5,   /* no device, kernel or runtime failure */
+    GSB_ENCCL = -6,
+    GSB_ERANGE = -7   /* k out of range: Graph::MaxK = 62 (src/Graph.hh:89), KmerSet::MaxK = 63 (src/KmerSet.hh:30) */
+} gsb_status;
+
+typedef enum gsb_kind {
+    GSB_KIND_GRAPH = 0,   /* build-graph: every (k+1)-mer and its reverse complement, with counts */
+    GSB_KIND_KMERSET = 1  /* build-kmer-set: FNV-normalised k-mers, no counts */
+} gsb_kind;
+
+typedef enum gsb_format {
+    GSB_FMT_FASTA = 0,  /* -I / -F   src/FastaParser.hh:51-87  */
+    GSB_FMT_FASTQ = 1,  /* -i / -f   src/FastqParser.hh:78-176 */
+    GSB_FMT_LINE = 2    /* --line-in src/LineParser.hh:71-82   */
+} gsb_format;
+
+/* gsb_push_* flags */
+#define GSB_BLOCK_LAST_OF_FILE 1u /* the file ends with this block; without it the next block of the same
+                                     format continues the same file (FASTA records may straddle blocks) */
+
+typedef void (*gsb_log_fn)(void* user, int severity /*0 info,1 warning,2 error*/, const char* message);
+
+typedef struct gsb_config {
+    uint32_t abi_version;      /* GSB_ABI_VERSION */
+    int32_t kind;              /* gsb_kind */
+    int32_t k;                 /* -k  (src/GossCmdBuildGraph.cc:433-434) */
+    int32_t device;            /* CUDA ordinal */
+    uint64_t min_count;        /* 0/1 = keep all.  m>1 == build-graph followed by `trim-graph -C m-1`
+                                  (src/GossCmdTrimGraph.cc:97-124); ignored for kmer sets */
+    uint64_t max_batch_keys;   /* 0 = choose from free HBM.  Keys buffered before a sort+reduce+merge
+                                  round (the -B analogue, src/GossCmdBuildGraph.cc:436-447) */
+    gsb_log_fn log;            /* may be NULL */
+    void* log_user;
+} gsb_config;
+
+typedef struct gsb_counts {
+    uint64_t n_reads;      /* records framed */
+    uint64_t n_instances;  /* keys fed to counting (both strands for graphs) */
+    uint64_t n_distinct;   /* distinct keys (all ranks when a communicator is attached) */
+    uint64_t n_kept;       /* after the min-count filter == number of edges / k-mers emitted */
+} gsb_counts;
+
+/* Output seam: the FileFactory::out analogue (src/FileFactory.hh:80-164).  The library composes
+ * the reference's file names (`P.header`, `P-edges.high-bits`, ...) and hands each file over
+ * as one or more contiguous pieces at increasing offsets. */
+typedef struct gsb_sink {
+    void* user;
+    int (*open)(void* user, const char* name, uint64_t size_hint, void** handle);
+    int (*pwrite)(void* user, void* handle, uint64_t offset, const void* data, uint64_t len);
+    int (*close)(void* user, void* handle);
+} gsb_sink;
+
+typedef struct gsb_stats {
+    /* device time per phase, milliseconds, CUDA events on the library's stream */
+    double ms_h2d, ms_scan, ms_extract, ms_sort, ms_reduce, ms_merge, ms_emit, ms_d2h, ms_exchange;
+    uint64_t bytes_in;          /* raw text bytes pushed */
+    uint64_t bytes_out;         /* bytes handed to the sink */
+    uint64_t n_symbols;         /* bases + separators in the packed symbol stream */
+    uint64_t sort_key_bytes;    /* 8 or 16 */
+    uint64_t sort_passes;       /* radix passes actually run (after constant-digit skipping) */
+    uint64_t sort_passes_model; /* ceil(keybits/8) */
+    uint64_t n_batches;         /* sort+reduce rounds */
+    uint64_t kernel_launches;   /* launches of this library's kernels so far */
+    uint64_t hbm_peak_bytes;    /* high-water mark of device allocations */
+} gsb_stats;
+
+/* Replaces: GossCmdFactoryBuildGraph::create parameter checks (src/GossCmdBuildGraph.cc:428-477)
+ * and the BackyardHash / consumer-pool construction (:315-322). */
+int gsb_create(const gsb_config* cfg, gsb_ctx** out);
+void gsb_destroy(gsb_ctx* ctx);
+const char* gsb_last_error(const gsb_ctx* ctx); /* ctx may be NULL for gsb_create failures */
+
+/* Replaces: the ingest + k-merising loop, HOT LOOP A/B (src/GossCmdBuildGraph.cc:335-380;
+ * LineSource/Fast{a,q}Parser/GossReadBaseString/ReverseComplementAdapter beneath it).
+ * `data` is host memory (pinned for best throughput); it is copied to the device inside the
+ * call.  A block must end at a line boundary (or end of file); a FASTQ / line block must end at
+ * a record boundary; a FASTA record may continue into the next block. */
+int gsb_push_block(gsb_ctx* ctx, const void* data, size_t nbytes, int format, uint32_t flags);
+/* Same, for text already resident in device memory (no copy). */
+int gsb_push_device_block(gsb_ctx* ctx, const void* device_data, size_t nbytes, int format, uint32_t flags);
+
+/* Replaces: BackyardHash::insert + sort + the duplicate-merging emit loop's counting
+ * (src/BackyardHash.cc:115-271, src/GossCmdBuildGraph.cc:239-258), flushNaked + AsyncMerge for
+ * multi-batch input (:171-220, src/AsyncMerge.tcc:267-324), and trim-graph's predicate. */
+int gsb_finish_counting(gsb_ctx* ctx, gsb_counts* out);
+
+/* Replaces: Graph::Builder / KmerSet::Builder and everything under them (src/Graph.cc:115-167,
+ * src/KmerSet.hh:61-103, SparseArray / DenseSelect / WordyBitVector / IntegerArray /
+ * VariableByteArray builders).  Files are byte-identical to the reference's writers. */
+int gsb_emit(gsb_ctx* ctx, const char* prefix, const gsb_sink* sink);
+
+int gsb_get_stats(const gsb_ctx* ctx, gsb_stats* out);
+/* Forget all input but keep buffers: lets a benchmark loop reuse one context. */
+int gsb_reset(gsb_ctx* ctx);
+
+/* Multi-GPU (one process per GPU).  Rank 0 makes an id, the host program broadcasts its 128
+ * bytes (torch.distributed / MPI / a file), every rank attaches.  After that
+ * gsb_finish_counting range-partitions the locally reduced (key,count) runs by sampled
+ * splitters, exchanges them with one ncclSend/ncclRecv all-to-all and merges; rank r then holds
+ * the r-th contiguous slice of the global order.  gsb_gather_to_root moves all slices to rank 0
+ * (in order) so that rank 0 can gsb_emit the whole graph. */
+#define GSB_NCCL_ID_BYTES 128
+int gsb_comm_make_id(void* id_out /* GSB_NCCL_ID_BYTES */);
+int gsb_comm_attach(gsb_ctx* ctx, const void* id, int n_ranks, int rank);
+int gsb_gather_to_root(gsb_ctx* ctx);
+
+/* Test-only: copy the reduced (key,count) run of this rank to host arrays. */
+int64_t gsb_debug_copy_counts(gsb_ctx* ctx, uint64_t* key_lo, uint64_t* key_hi, uint64_t* counts, uint64_t cap);
+/* Test-only: run one component on host-provided arrays (inputs copied to the device, the
+ * component's kernels run, results returned through the sink or out arrays). */
+int64_t gsb_debug_sort_keys(int device, uint64_t* key_lo, uint64_t* key_hi, uint64_t n, int key_bits);
+int gsb_debug_emit_sparse_array(int device, const uint64_t* key_lo, const uint64_t* key_hi, uint64_t m,
+                                uint64_t universe_lo, uint64_t universe_hi, uint64_t m_est,
+                                const char* base, const gsb_sink* sink);
+int gsb_debug_emit_graph(int device, const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* counts,
+                         uint64_t m, int k, const char* prefix, const gsb_sink* sink);
+int64_t gsb_debug_extract(int device, const void* text, size_t nbytes, int format, int kind, int k,
+                          uint64_t* key_lo, uint64_t* key_hi, uint64_t cap, uint64_t* n_reads,
+                          char* err, size_t errcap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOSSAMER_B200_H */
