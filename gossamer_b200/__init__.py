@@ -47,7 +47,7 @@ class Counts(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ms_h2d", "ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_merge", "ms_emit",
-                                          "ms_d2h", "ms_exchange")] + \
+                                          "ms_d2h", "ms_exchange", "ms_sort_sweeps")] + \
                [(n, C.c_uint64) for n in ("bytes_in", "bytes_out", "n_symbols", "sort_key_bytes", "sort_passes",
                                           "sort_passes_model", "n_batches", "kernel_launches", "hbm_peak_bytes")]
 
@@ -65,8 +65,8 @@ class Sink(C.Structure):
 
 
 EXPORTS = ["gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
-           "gsb_emit", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root",
-           "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
+           "gsb_emit", "gsb_timer_begin", "gsb_timer_end", "gsb_host_alloc", "gsb_host_free", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root", "gsb_plan_splitters", "gsb_samples_per_rank",
+           "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_sort_bench", "gsb_debug_set_tuning", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
            "gsb_debug_extract"]
 
 _lib = None
@@ -89,6 +89,8 @@ def lib():
         L.gsb_finish_counting.argtypes = [C.c_void_p, C.POINTER(Counts)]
         L.gsb_emit.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Sink)]
         L.gsb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.gsb_timer_begin.argtypes = [C.c_void_p]
+        L.gsb_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.gsb_reset.argtypes = [C.c_void_p]
         L.gsb_comm_make_id.argtypes = [C.c_void_p]
         L.gsb_comm_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -231,7 +233,16 @@ class Builder:
         return c
 
     def emit(self, prefix, sink):
-        self._check(lib().gsb_emit(self.h, prefix.encode(), C.byref(sink.c)))
+        """sink=None builds the files on the device and drops them (device-only timing)."""
+        self._check(lib().gsb_emit(self.h, prefix.encode(), C.byref(sink.c) if sink is not None else None))
+
+    def timer_begin(self):
+        self._check(lib().gsb_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_double()
+        self._check(lib().gsb_timer_end(self.h, C.byref(ms)))
+        return ms.value
 
     def stats(self):
         s = Stats()
@@ -255,6 +266,27 @@ class Builder:
         lo, hi, cn = np.zeros(m, np.uint64), np.zeros(m, np.uint64), np.zeros(m, np.uint64)
         lib().gsb_debug_copy_counts(self.h, _ptr(lo), _ptr(hi), _ptr(cn), m)
         return lo, hi, cn
+
+
+def samples_per_rank():
+    f = lib().gsb_samples_per_rank
+    f.restype = C.c_uint32
+    return int(f())
+
+
+def plan_splitters(sample_lo, sample_hi, n_ranks):
+    """Host-only: pooled samples -> (lo, hi) arrays of the n_ranks-1 splitters (no GPU needed)."""
+    lo = np.ascontiguousarray(sample_lo, np.uint64)
+    hi = np.ascontiguousarray(sample_hi, np.uint64)
+    inter = np.empty(2 * lo.size, np.uint64)
+    inter[0::2], inter[1::2] = lo, hi
+    out = np.zeros(2 * (n_ranks - 1), np.uint64)
+    f = lib().gsb_plan_splitters
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    rc = f(_ptr(inter), lo.size, n_ranks, _ptr(out))
+    if rc != 0:
+        raise GossamerError(rc, lib().gsb_last_error(None).decode())
+    return out[0::2].copy(), out[1::2].copy()
 
 
 def make_nccl_id():
@@ -303,6 +335,17 @@ def debug_sort_keys(lo, hi, key_bits, device=0):
     if rc < 0:
         raise GossamerError(int(rc), lib().gsb_last_error(None).decode())
     return lo, hi, int(rc)
+
+
+def debug_sort_bench(n, key_bits, iters=3, tuning=0, device=0):
+    """Random keys generated and sorted on the device -> (mean sweep ms, mean sort ms, sweeps per sort)."""
+    sw, tot, nsw = C.c_double(), C.c_double(), C.c_int()
+    f = lib().gsb_debug_sort_bench
+    f.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    rc = f(device, n, key_bits, iters, tuning, C.byref(sw), C.byref(tot), C.byref(nsw))
+    if rc != 0:
+        raise GossamerError(rc, lib().gsb_last_error(None).decode())
+    return sw.value, tot.value, nsw.value
 
 
 def debug_emit_sparse_array(lo, hi, universe, m_est, base="sa", device=0):

@@ -83,6 +83,7 @@ struct gsb_ctx {
     gsb_counts counts;
     gsb_stats stats;
     PhaseTimer timer;
+    cudaEvent_t user_e0 = nullptr, user_e1 = nullptr;
     Exchange* comm = nullptr;
 
     void log(int sev, const std::string& m) { if (cfg.log) cfg.log(cfg.log_user, sev, m.c_str()); }
@@ -163,7 +164,7 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     DevBuf<u8> alt(&ws, c->n_keys * kb);
     int passes_run = 0;
     c->timer.start();
-    int where = sort_keys(ws, kb, c->key_bits, c->keys.p, alt.p, nullptr, nullptr, c->n_keys, c->hist.p, &passes_run);
+    int where = sort_keys(ws, kb, c->key_bits, c->keys.p, alt.p, nullptr, nullptr, c->n_keys, c->hist.p, &passes_run, &c->stats.ms_sort_sweeps);
     c->timer.stop(c->stats.ms_sort);
     c->stats.sort_passes += passes_run;
     c->stats.sort_passes_model += c->passes;
@@ -326,6 +327,8 @@ void init_ctx(gsb_ctx* c) {
     u64 threshold = ~0ull;
     GSB_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     c->timer.init(c->ws.stream);
+    GSB_CUDA_TRY(cudaEventCreate(&c->user_e0));
+    GSB_CUDA_TRY(cudaEventCreate(&c->user_e1));
 
     c->window = cfg.kind == GSB_KIND_GRAPH ? cfg.k + 1 : cfg.k;
     c->key_bits = 2 * c->window;
@@ -375,6 +378,8 @@ void gsb_destroy(gsb_ctx* c) {
     c->keys.free(); c->cursor.free(); c->hist.free(); c->status.free(); c->carry.free(); c->text_dev.free();
     c->acc.keys.free(); c->acc.counts.free();
     c->timer.destroy();
+    if (c->user_e0) cudaEventDestroy(c->user_e0);
+    if (c->user_e1) cudaEventDestroy(c->user_e1);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ws.stream) { cudaStreamSynchronize(c->ws.stream); cudaStreamDestroy(c->ws.stream); }
     delete c;
@@ -454,7 +459,7 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
 }
 
 int gsb_emit(gsb_ctx* c, const char* prefix, const gsb_sink* sink) {
-    if (!c || !prefix || !sink || !sink->open || !sink->pwrite || !sink->close) return GSB_EINVAL;
+    if (!c || !prefix || (sink && (!sink->open || !sink->pwrite || !sink->close))) return GSB_EINVAL;
     return guarded(c, [&] {
         if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_emit before gsb_finish_counting"};
         Emitter em;
@@ -466,6 +471,33 @@ int gsb_emit(gsb_ctx* c, const char* prefix, const gsb_sink* sink) {
         c->stats.bytes_out += em.bytes_out;
     });
 }
+
+int gsb_timer_begin(gsb_ctx* c) {
+    if (!c) return GSB_EINVAL;
+    return guarded(c, [&] { GSB_CUDA_TRY(cudaEventRecord(c->user_e0, c->ws.stream)); });
+}
+
+int gsb_timer_end(gsb_ctx* c, double* ms_out) {
+    if (!c || !ms_out) return GSB_EINVAL;
+    return guarded(c, [&] {
+        GSB_CUDA_TRY(cudaEventRecord(c->user_e1, c->ws.stream));
+        GSB_CUDA_TRY(cudaEventSynchronize(c->user_e1));
+        float ms = 0;
+        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, c->user_e0, c->user_e1));
+        *ms_out = ms;
+    });
+}
+
+int gsb_host_alloc(size_t nbytes, void** out) {
+    if (!out) return GSB_EINVAL;
+    *out = nullptr;
+    return guarded(nullptr, [&] {
+        cudaError_t e = cudaMallocHost(out, nbytes ? nbytes : 1);
+        if (e != cudaSuccess) { cudaGetLastError(); throw StatusError{e == cudaErrorMemoryAllocation ? GSB_ENOMEM : GSB_ECUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e)}; }
+    });
+}
+
+void gsb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int gsb_get_stats(const gsb_ctx* c, gsb_stats* out) {
     if (!c || !out) return GSB_EINVAL;
@@ -503,6 +535,13 @@ int gsb_comm_attach(gsb_ctx* c, const void* id, int n_ranks, int rank) {
         c->comm = exchange_create(id, n_ranks, rank, c->ws);
     });
 }
+
+int gsb_plan_splitters(const uint64_t* samples, uint64_t n_samples, int n_ranks, uint64_t* splitters_out) {
+    if (!samples || !splitters_out || n_ranks < 1 || n_samples == 0) return GSB_EINVAL;
+    return guarded(nullptr, [&] { plan_splitters((const u64*)samples, n_samples, n_ranks, (u64*)splitters_out); });
+}
+
+uint32_t gsb_samples_per_rank(void) { return kExchangeSamplesPerRank; }
 
 int gsb_gather_to_root(gsb_ctx* c) {
     if (!c) return GSB_EINVAL;
@@ -623,6 +662,38 @@ int64_t gsb_debug_sort_keys(int device, uint64_t* key_lo, uint64_t* key_hi, uint
     });
     return rc == GSB_OK ? passes : rc;
 }
+
+// sorts `iters` fresh random key sets of n keys on the device; returns the mean sweep time and the
+// mean whole-sort time (histogram + sweeps) in milliseconds
+int gsb_debug_sort_bench(int device, uint64_t n, int key_bits, int iters, int tuning, double* sweep_ms, double* sort_ms, int* sweeps) {
+    return guarded(nullptr, [&] {
+        DebugDevice d; d.open(device);
+        sort_set_tuning(tuning);
+        const int kb = key_bits <= 64 ? 8 : 16;
+        DevBuf<u8> a(&d.ws, n * kb), b(&d.ws, n * kb);
+        cudaEvent_t e0, e1;
+        GSB_CUDA_TRY(cudaEventCreate(&e0)); GSB_CUDA_TRY(cudaEventCreate(&e1));
+        double sw = 0, tot = 0; int run = 0, total_run = 0;
+        for (int it = 0; it < iters + 1; ++it) {
+            sort_fill_random(kb, a.p, n, key_bits, 1234567ull * (it + 1), d.ws.stream);
+            double sw_it = 0;
+            GSB_CUDA_TRY(cudaEventRecord(e0, d.ws.stream));
+            sort_keys(d.ws, kb, key_bits, a.p, b.p, nullptr, nullptr, n, nullptr, &run, &sw_it);
+            GSB_CUDA_TRY(cudaEventRecord(e1, d.ws.stream));
+            GSB_CUDA_TRY(cudaEventSynchronize(e1));
+            float ms = 0; GSB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            if (it > 0) { sw += sw_it; tot += ms; total_run += run; }     // first iteration is warm-up
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (sweep_ms) *sweep_ms = total_run ? sw / total_run : 0;
+        if (sort_ms) *sort_ms = tot / iters;
+        if (sweeps) *sweeps = total_run / (iters ? iters : 1);
+        a.free(); b.free();
+        sort_set_tuning(0);
+    });
+}
+
+int gsb_debug_set_tuning(int id) { sort_set_tuning(id); return GSB_OK; }
 
 int gsb_debug_emit_sparse_array(int device, const uint64_t* key_lo, const uint64_t* key_hi, uint64_t m,
                                 uint64_t universe_lo, uint64_t universe_hi, uint64_t m_est,

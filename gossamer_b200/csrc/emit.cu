@@ -38,14 +38,17 @@ u64 sparse_array_d(U128 universe, u64 m_est) {
 static void sink_fail(const std::string& what, const std::string& name) { throw StatusError{GSB_EIO, what + " failed for " + name}; }
 
 void Emitter::put_host(const std::string& name, const void* data, u64 len) {
+    bytes_out += len;
+    if (!sink) return;
     void* h = nullptr;
     if (sink->open(sink->user, name.c_str(), len, &h) != 0) sink_fail("open", name);
     if (len && sink->pwrite(sink->user, h, 0, data, len) != 0) sink_fail("pwrite", name);
     if (sink->close(sink->user, h) != 0) sink_fail("close", name);
-    bytes_out += len;
 }
 
 void Emitter::put_device(const std::string& name, const void* dev, u64 len, const void* host_prefix, u64 prefix_len) {
+    bytes_out += len;
+    if (!sink) return;
     void* h = nullptr;
     if (sink->open(sink->user, name.c_str(), len, &h) != 0) sink_fail("open", name);
     for (u64 off = 0; off < len; off += pinned_bytes) {
@@ -56,7 +59,6 @@ void Emitter::put_device(const std::string& name, const void* dev, u64 len, cons
         if (sink->pwrite(sink->user, h, off, pinned, chunk) != 0) sink_fail("pwrite", name);
     }
     if (sink->close(sink->user, h) != 0) sink_fail("close", name);
-    bytes_out += len;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -62,7 +62,6 @@ void check(ncclResult_t r, const char* what) {
     if (r != ncclSuccess) throw StatusError{GSB_ENCCL, std::string(what) + ": " + nccl().GetErrorString(r)};
 }
 
-static const u32 kSamplesPerRank = 2048;
 
 // sample[i] = key at position floor((i + 0.5) * m / S), as (lo, hi) pairs; slot S holds m
 template <typename K>
@@ -89,6 +88,19 @@ __global__ void bounds_kernel(const K* __restrict__ keys, u64 m, const u64* __re
 }
 
 }  // namespace
+
+// n_ranks - 1 splitters at equal quantiles of the pooled sample; rank r owns keys in
+// [splitter[r-1], splitter[r]).  Pure host code (also exported for the CPU multi-process tests).
+void plan_splitters(const u64* samples /* (lo,hi) pairs */, u64 n_samples, int n_ranks, u64* splitters_out) {
+    struct HK { u64 hi, lo; bool operator<(const HK& o) const { return hi < o.hi || (hi == o.hi && lo < o.lo); } };
+    std::vector<HK> v(n_samples);
+    for (u64 i = 0; i < n_samples; ++i) v[i] = HK{samples[2 * i + 1], samples[2 * i]};
+    std::sort(v.begin(), v.end());
+    for (int j = 0; j < n_ranks - 1; ++j) {
+        const HK& k = v[(size_t)((u64)(j + 1) * n_samples / n_ranks)];
+        splitters_out[2 * j] = k.lo; splitters_out[2 * j + 1] = k.hi;
+    }
+}
 
 struct Exchange {
     ncclComm_t comm = nullptr;
@@ -134,7 +146,7 @@ void exchange_runs(Exchange* x, Workspace& ws, int key_bytes, int key_bits, Redu
     if (n == 1) return;
     cudaStream_t s = ws.stream;
     NcclApi& api = nccl();
-    const u32 S = kSamplesPerRank;
+    const u32 S = kExchangeSamplesPerRank;
     const size_t slot = 2 * (size_t)S + 2;                        // u64 words per rank
     // 1. sample + allgather
     DevBuf<u64> mine(&ws, slot), all(&ws, slot * n);
@@ -146,20 +158,15 @@ void exchange_runs(Exchange* x, Workspace& ws, int key_bytes, int key_bits, Redu
     std::vector<u64> h(slot * n);
     GSB_CUDA_TRY(cudaMemcpyAsync(h.data(), all.p, h.size() * 8, cudaMemcpyDeviceToHost, s));
     ws.sync();
-    struct HK { u64 hi, lo; bool operator<(const HK& o) const { return hi < o.hi || (hi == o.hi && lo < o.lo); } };
-    std::vector<HK> samples;
+    std::vector<u64> samples;                                     // (lo, hi) pairs of every rank that has keys
     for (int r = 0; r < n; ++r) {
         const u64* p = h.data() + slot * r;
         if (p[2 * S] == 0) continue;
-        for (u32 i = 0; i < S; ++i) samples.push_back(HK{p[2 * i + 1], p[2 * i]});
+        samples.insert(samples.end(), p, p + 2 * (size_t)S);
     }
     if (samples.empty()) return;                                  // nothing anywhere
-    std::sort(samples.begin(), samples.end());
     std::vector<u64> split(2 * (size_t)(n - 1));
-    for (int j = 0; j < n - 1; ++j) {
-        const HK& k = samples[(size_t)((u64)(j + 1) * samples.size() / n)];
-        split[2 * j] = k.lo; split[2 * j + 1] = k.hi;
-    }
+    plan_splitters(samples.data(), samples.size() / 2, n, split.data());
     // 2. local partition bounds
     DevBuf<u64> split_d(&ws, split.size()), bounds_d(&ws, (size_t)n + 1);
     GSB_CUDA_TRY(cudaMemcpyAsync(split_d.p, split.data(), split.size() * 8, cudaMemcpyHostToDevice, s));

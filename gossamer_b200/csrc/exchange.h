@@ -6,6 +6,9 @@ namespace gsb {
 
 struct Exchange;
 
+static const u32 kExchangeSamplesPerRank = 2048;
+void plan_splitters(const u64* samples, u64 n_samples, int n_ranks, u64* splitters_out);
+
 void exchange_make_id(void* id_out /* GSB_NCCL_ID_BYTES */);
 Exchange* exchange_create(const void* id, int n_ranks, int rank, Workspace& ws);
 void exchange_destroy(Exchange* x);

@@ -73,11 +73,13 @@ void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid,
 
 // ---- sort.cu ---------------------------------------------------------------------------------
 u64 sort_tile_keys(int key_bytes);
+void sort_set_tuning(int id);
+void sort_fill_random(int key_bytes, void* keys, u64 n, int key_bits, u64 seed, cudaStream_t s);
 u64 sort_lookback_bytes(int key_bytes, u64 n);
 void sort_digit_hist(int key_bytes, const void* keys, u64 n, int passes, u64* hist, int sm_count, cudaStream_t s, u64* launches);
 void sort_digit_base(const u64* hist, u64* base, int passes, cudaStream_t s, u64* launches);
 void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vout, u64 n, int pass, const u64* digit_base_all,
-               void* lookback, cudaStream_t s, u64* launches);
+               void* lookback, cudaStream_t s, u64* launches, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr);
 u64 rle_lookback_bytes(u64 n);
 void sort_rle(int key_bytes, const void* keys, u64 n, void* out_keys, u64* out_pos, void* lookback, u64* total_dev, cudaStream_t s, u64* launches);
 void sort_counts_from_pos(const u64* pos, const u64* csum, u64 m, u64* counts, cudaStream_t s, u64* launches);
@@ -90,7 +92,7 @@ u64 sort_scan_tmp_elems(u64 n);
 // same size.  Digit histograms are computed here unless hist_dev (already accumulated, [passes][256])
 // is given.  Returns 0 if the result is in a, 1 if in b.  passes_run gets the number of sweeps.
 int sort_keys(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64* va, u64* vb, u64 n,
-              const u64* hist_dev, int* passes_run);
+              const u64* hist_dev, int* passes_run, double* sweep_ms = nullptr);
 
 // sorted keys (+ optional weights) -> distinct keys and summed counts, min-count filtered.
 // Outputs are freshly allocated; *m_distinct is the count before the filter.
@@ -106,7 +108,7 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
 // ---- emit.cu ---------------------------------------------------------------------------------
 struct Emitter {
     Workspace* ws;
-    const gsb_sink* sink;
+    const gsb_sink* sink;          // nullptr: build on the device, count the bytes, drop
     u64 bytes_out = 0;
     u8* pinned = nullptr;          // staging for device -> sink copies
     size_t pinned_bytes = 0;

@@ -1,0 +1,179 @@
+// file_io.cc -- see file_io.hh
+#include "file_io.hh"
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <cerrno>
+#include <cstring>
+#include <fstream>
+
+namespace goss {
+
+static bool ends_with(const std::string& s, const char* suf) {
+    size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+InputFile::InputFile(const std::string& name) : name_(name) {
+    if (ends_with(name, ".bz2"))
+        throw Error{"\t'" + name + "': bzip2 input is not supported by this build (no libbz2 in the image); decompress first\n"};
+    if (name == "-") { fd_ = 0; return; }
+    if (ends_with(name, ".gz")) {
+        gz_ = gzopen(name.c_str(), "rb");
+        if (!gz_) throw Error{"\t'" + name + "': " + strerror(errno) + "\n"};
+        gzbuffer((gzFile)gz_, 1 << 20);
+        return;
+    }
+    fd_ = open(name.c_str(), O_RDONLY);
+    if (fd_ < 0) throw Error{"\t'" + name + "': " + strerror(errno) + "\n"};
+#ifdef POSIX_FADV_SEQUENTIAL
+    posix_fadvise(fd_, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+}
+
+InputFile::~InputFile() {
+    if (gz_) gzclose((gzFile)gz_);
+    if (fd_ > 0) close(fd_);
+}
+
+size_t InputFile::read(void* dst, size_t n) {
+    size_t got = 0;
+    while (got < n) {
+        long r;
+        if (gz_) r = gzread((gzFile)gz_, (char*)dst + got, (unsigned)std::min<size_t>(n - got, 1u << 30));
+        else r = ::read(fd_, (char*)dst + got, n - got);
+        if (r < 0) {
+            if (!gz_ && errno == EINTR) continue;
+            throw Error{"\t'" + name_ + "': read error\n"};
+        }
+        if (r == 0) break;
+        got += (size_t)r;
+    }
+    return got;
+}
+
+BlockReader::BlockReader(const std::string& name, int format, size_t block_bytes) : in_(name), format_(format), cap_(block_bytes) {
+    for (int i = 0; i < 2; ++i) {
+        void* p = nullptr;
+        if (gsb_host_alloc(cap_, &p) != GSB_OK) throw Error{std::string("\tcannot allocate pinned staging buffer: ") + gsb_last_error(nullptr) + "\n"};
+        buf_[i] = (uint8_t*)p;
+    }
+}
+
+BlockReader::~BlockReader() {
+    for (int i = 0; i < 2; ++i) gsb_host_free(buf_[i]);
+}
+
+// Index one past the last byte of the block to hand over (the rest is carried to the next block).
+size_t BlockReader::cut_point(size_t filled, bool eof) const {
+    const uint8_t* b = buf_[cur_];
+    if (eof) return filled;
+    // last newline
+    size_t nl = filled;
+    while (nl > 0 && b[nl - 1] != '\n') --nl;
+    if (nl == 0) return 0;                                   // no complete line in the buffer
+    if (format_ != GSB_FMT_FASTQ) return nl;
+    // FASTQ: walk back over line starts until one looks like a record header
+    size_t line_end = nl;                                    // exclusive end (just after a '\n')
+    for (int guard = 0; guard < 100000 && line_end > 0; ++guard) {
+        size_t ls = line_end - 1;                            // start of the line ending at line_end
+        while (ls > 0 && b[ls - 1] != '\n') --ls;
+        if (b[ls] == '@') {
+            // find the start of line+2
+            size_t p = ls; int seen = 0;
+            while (p < nl && seen < 2) { if (b[p] == '\n') ++seen; ++p; }
+            if (seen == 2 && p < nl && b[p] == '+') return ls; // records before this header are complete
+        }
+        line_end = ls;
+    }
+    return 0;
+}
+
+bool BlockReader::next(const uint8_t*& data, size_t& size, bool& last) {
+    if (done_) return false;
+    for (;;) {
+        uint8_t* b = buf_[cur_];
+        size_t filled = carry_;
+        if (!eof_) {
+            size_t got = in_.read(b + filled, cap_ - filled);
+            filled += got;
+            if (filled < cap_) eof_ = true;
+        }
+        size_t cut = cut_point(filled, eof_);
+        if (cut == 0 && !eof_)
+            throw Error{"\t'" + in_.name() + "': a single record is larger than the " + std::to_string(cap_ >> 20) + " MiB input block; raise --block-mb\n"};
+        // carry the tail into the other buffer
+        const int other = cur_ ^ 1;
+        carry_ = filled - cut;
+        if (carry_) memcpy(buf_[other], b + cut, carry_);
+        data = b; size = cut; last = eof_ && carry_ == 0;
+        cur_ = other;
+        if (last) done_ = true;
+        return true;
+    }
+}
+
+OutputFiles::OutputFiles() {
+    sink_.user = this;
+    sink_.open = &OutputFiles::s_open;
+    sink_.pwrite = &OutputFiles::s_pwrite;
+    sink_.close = &OutputFiles::s_close;
+}
+
+int OutputFiles::s_open(void* user, const char* name, uint64_t size_hint, void** handle) {
+    OutputFiles* self = (OutputFiles*)user;
+    int fd = ::open(name, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return -1;
+    if (size_hint) { if (ftruncate(fd, (off_t)size_hint) != 0) { /* best effort */ } }
+    self->names_.push_back(name);
+    *handle = (void*)(intptr_t)(fd + 1);
+    return 0;
+}
+
+int OutputFiles::s_pwrite(void* user, void* handle, uint64_t offset, const void* data, uint64_t len) {
+    OutputFiles* self = (OutputFiles*)user;
+    int fd = (int)(intptr_t)handle - 1;
+    uint64_t done = 0;
+    while (done < len) {
+        ssize_t w = ::pwrite(fd, (const char*)data + done, len - done, (off_t)(offset + done));
+        if (w < 0) { if (errno == EINTR) continue; return -1; }
+        done += (uint64_t)w;
+    }
+    self->bytes_ += len;
+    return 0;
+}
+
+int OutputFiles::s_close(void*, void* handle) {
+    int fd = (int)(intptr_t)handle - 1;
+    return ::close(fd) == 0 ? 0 : -1;
+}
+
+void check_output_prefix(const std::string& prefix) {
+    const std::string probe = prefix + ".test";
+    int fd = ::open(probe.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) throw Error{"cannot create filenames with prefix '" + prefix + "'\n"};
+    ::close(fd);
+    ::unlink(probe.c_str());
+}
+
+void check_readable(const std::string& name) {
+    if (name == "-") return;
+    if (access(name.c_str(), R_OK) != 0) throw Error{"\t'" + name + "': " + strerror(errno) + "\n"};
+}
+
+std::vector<std::string> expand_file_list(const std::string& list_name) {
+    std::ifstream in(list_name);
+    if (!in) throw Error{"\t'" + list_name + "': " + strerror(errno) + "\n"};
+    std::vector<std::string> out;
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty()) out.push_back(line);
+    }
+    return out;
+}
+
+}  // namespace goss

@@ -90,6 +90,7 @@ typedef struct gsb_sink {
 typedef struct gsb_stats {
     /* device time per phase, milliseconds, CUDA events on the library's stream */
     double ms_h2d, ms_scan, ms_extract, ms_sort, ms_reduce, ms_merge, ms_emit, ms_d2h, ms_exchange;
+    double ms_sort_sweeps;      /* sum of the radix sweep kernels alone (events around each launch) */
     uint64_t bytes_in;          /* raw text bytes pushed */
     uint64_t bytes_out;         /* bytes handed to the sink */
     uint64_t n_symbols;         /* bases + separators in the packed symbol stream */
@@ -125,6 +126,16 @@ int gsb_finish_counting(gsb_ctx* ctx, gsb_counts* out);
  * src/KmerSet.hh:61-103, SparseArray / DenseSelect / WordyBitVector / IntegerArray /
  * VariableByteArray builders).  Files are byte-identical to the reference's writers. */
 int gsb_emit(gsb_ctx* ctx, const char* prefix, const gsb_sink* sink);
+/* sink == NULL builds every file in device memory and drops it (device-only timing; bytes_out still counts). */
+
+/* Device-side stopwatch on the library's stream (CUDA events): begin records, end records +
+ * synchronises and returns the elapsed milliseconds between the two. */
+int gsb_timer_begin(gsb_ctx* ctx);
+int gsb_timer_end(gsb_ctx* ctx, double* ms_out);
+
+/* Page-locked host buffers for gsb_push_block (so that the host program need not link CUDA itself). */
+int gsb_host_alloc(size_t nbytes, void** out);
+void gsb_host_free(void* p);
 
 int gsb_get_stats(const gsb_ctx* ctx, gsb_stats* out);
 /* Forget all input but keep buffers: lets a benchmark loop reuse one context. */
@@ -140,12 +151,19 @@ int gsb_reset(gsb_ctx* ctx);
 int gsb_comm_make_id(void* id_out /* GSB_NCCL_ID_BYTES */);
 int gsb_comm_attach(gsb_ctx* ctx, const void* id, int n_ranks, int rank);
 int gsb_gather_to_root(gsb_ctx* ctx);
+/* Host-only piece of the exchange (no device needed): splitters at equal quantiles of the pooled
+ * sample of all ranks' keys, given as (lo,hi) pairs; writes n_ranks-1 (lo,hi) pairs.  Each rank
+ * contributes gsb_samples_per_rank() keys taken at positions floor((i+0.5)*m/S) of its sorted run. */
+int gsb_plan_splitters(const uint64_t* samples, uint64_t n_samples, int n_ranks, uint64_t* splitters_out);
+uint32_t gsb_samples_per_rank(void);
 
 /* Test-only: copy the reduced (key,count) run of this rank to host arrays. */
 int64_t gsb_debug_copy_counts(gsb_ctx* ctx, uint64_t* key_lo, uint64_t* key_hi, uint64_t* counts, uint64_t cap);
 /* Test-only: run one component on host-provided arrays (inputs copied to the device, the
  * component's kernels run, results returned through the sink or out arrays). */
 int64_t gsb_debug_sort_keys(int device, uint64_t* key_lo, uint64_t* key_hi, uint64_t n, int key_bits);
+int gsb_debug_sort_bench(int device, uint64_t n, int key_bits, int iters, int tuning, double* sweep_ms, double* sort_ms, int* sweeps);
+int gsb_debug_set_tuning(int id);
 int gsb_debug_emit_sparse_array(int device, const uint64_t* key_lo, const uint64_t* key_hi, uint64_t m,
                                 uint64_t universe_lo, uint64_t universe_hi, uint64_t m_est,
                                 const char* base, const gsb_sink* sink);

@@ -1,0 +1,107 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol declared in
+include/gossamer_b200.h, fails loudly without a GPU (no CPU fallback), and the `goss` host CLI
+keeps the reference's option / error / exit-code behaviour (src/App.cc:253-276,328-418)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import gossamer_b200 as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOSS = os.path.join(ROOT, "gossamer_b200", "goss")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_header_symbols_are_all_exported():
+    hdr = open(os.path.join(ROOT, "include", "gossamer_b200.h")).read()
+    declared = set(re.findall(r"\b(gsb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"gsb_log_fn"}
+    assert len(declared) >= 20
+    lib = G.lib()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(G.EXPORTS) <= declared
+
+
+def test_library_has_no_torch_or_oracle_dependency():
+    out = subprocess.run(["ldd", G.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "libcudart" in out
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gossamer_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hh", ".cc")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle_py" not in src and "goss_oracle" not in src and "liboracle" not in src, f
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_no_gpu_means_loud_failure_not_fallback():
+    with pytest.raises(G.GossamerError) as e:
+        G.Builder(G.GRAPH, 25)
+    assert e.value.status == -5 and "no CPU path" in e.value.message
+
+
+def test_k_range_is_checked_before_touching_the_device():
+    with pytest.raises(G.GossamerError) as e:
+        G.Builder(G.GRAPH, 63)                       # Graph::MaxK = 62, src/Graph.hh:89
+    assert e.value.status == -7 and e.value.message == "unable to build a graph with k=63"
+    with pytest.raises(G.GossamerError) as e:
+        G.Builder(G.KMERSET, 64)                     # KmerSet::MaxK = 63, src/KmerSet.hh:30
+    assert e.value.status == -7
+
+
+def test_plan_splitters_quantiles():
+    import numpy as np
+    lo = np.arange(1000, dtype=np.uint64)[::-1].copy()
+    slo, shi = G.plan_splitters(lo, np.zeros_like(lo), 4)
+    assert list(slo) == [250, 500, 750] and not shi.any()
+    hi = np.repeat(np.arange(4, dtype=np.uint64), 250)
+    slo, shi = G.plan_splitters(np.zeros(1000, np.uint64), hi, 2)
+    assert list(shi) == [2]
+
+
+def _goss(*args):
+    return subprocess.run([GOSS, *args], capture_output=True, text=True)
+
+
+def test_cli_usage_errors_exit_1(tmp_path):
+    fa = tmp_path / "a.fa"
+    fa.write_text(">a\nACGTACGT\n")
+    r = _goss("frobnicate")
+    assert r.returncode == 1 and "unrecognised command" in r.stderr
+    r = _goss("build-graph", "-O", str(tmp_path / "g"), "-I", str(fa))
+    assert r.returncode == 1 and "--kmer-size" in r.stderr and "for more usage information" in r.stderr
+    r = _goss("build-graph", "-k", "25", "-I", str(fa))
+    assert r.returncode == 1 and "--graph-out" in r.stderr
+    r = _goss("build-graph", "-k", "25", "-O", str(tmp_path / "g"), "-I", str(fa), "--bogus")
+    assert r.returncode == 1 and "unrecognised option '--bogus'" in r.stderr
+    r = _goss("build-graph", "-k", "63", "-O", str(tmp_path / "g"), "-I", str(fa))
+    assert r.returncode == 1 and "at most 62" in r.stderr
+    r = _goss("build-kmer-set", "-k", "63", "-O", str(tmp_path / "g"), "-I", str(tmp_path / "missing.fa"))
+    assert r.returncode == 1 and "missing.fa" in r.stderr
+    r = _goss("build-graph", "-k", "25", "-O", str(tmp_path / "nodir" / "g"), "-I", str(fa))
+    assert r.returncode == 1 and "cannot create filenames with prefix" in r.stderr
+    r = _goss("build-graph", "-h")
+    assert r.returncode == 0 and "--kmer-size" in r.stdout
+    assert _goss("help").returncode == 0
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_cli_without_gpu_fails_loudly(tmp_path):
+    fa = tmp_path / "a.fa"
+    fa.write_text(">a\nACGTACGT\n")
+    r = _goss("build-graph", "-k", "3", "-O", str(tmp_path / "g"), "-I", str(fa))
+    assert r.returncode == 1 and "error performing build-graph" in r.stderr and "no CPU path" in r.stderr
+    assert not list(tmp_path.glob("g*"))
