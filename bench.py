@@ -232,11 +232,14 @@ def main():
     sampler.start()
     b.timer_begin()
     sweeps_ms, sweeps_n, phase = 0.0, 0, {}
+    a2a_ms, a2a_bytes = 0.0, 0
     for _ in range(args.steps):
         counts = step_device()
         st = b.stats()
         sweeps_ms += st.ms_sort_sweeps
         sweeps_n += st.sort_passes
+        a2a_ms += st.ms_all_to_all
+        a2a_bytes += st.exchange_bytes_sent
         for key in ("ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_merge", "ms_exchange", "ms_emit"):
             phase[key] = phase.get(key, 0.0) + getattr(st, key)
     ms_dev = b.timer_end()
@@ -256,8 +259,12 @@ def main():
     barrier()
     b.timer_begin()
     t0 = time.perf_counter()
+    e2e_phase = {}
     for _ in range(args.steps):
         step_e2e(sink)
+        st2 = b.stats()
+        for key in ("ms_h2d", "ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_exchange", "ms_emit"):
+            e2e_phase[key] = e2e_phase.get(key, 0.0) + getattr(st2, key)
     ms_e2e = b.timer_end()
     wall_e2e = time.perf_counter() - t0
     barrier()
@@ -300,7 +307,7 @@ def main():
                    "l2_note": "inputs (FASTQ text and key buffers) are larger than the 126 MB L2; no flush needed"},
         "gb_per_s": n_inst_total * key_bytes * args.steps / (ms_dev * 1e-3) / 1e9,
         "e2e": {"value": e2e_value, "unit": "edge instances/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "phases_ms_per_step": {k: v / args.steps for k, v in e2e_phase.items()}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit radix sweep: read + write every key once)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -310,6 +317,11 @@ def main():
                                     "achieved_gbs": b_sort / t_sort / 1e9 if t_sort > 0 else 0.0,
                                     "frac": (b_sort / t_sort / 1e9 / peak) if t_sort > 0 else 0.0}},
         "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+        "exchange": None if world == 1 else {
+            "what": "one all-to-all of raw instance keys routed to the rank owning their key range (rank 0's view)",
+            "bytes_sent_per_gpu_per_step": a2a_bytes / args.steps, "all_to_all_ms": a2a_ms / args.steps,
+            "gb_per_s_per_gpu": (a2a_bytes / max(a2a_ms, 1e-9)) / 1e6,
+            "frac_of_nvlink_770": (a2a_bytes / max(a2a_ms, 1e-9)) / 1e6 / 770.0},
         "clocks": clocks,
         "hbm_peak_bytes": int(st.hbm_peak_bytes),
     }

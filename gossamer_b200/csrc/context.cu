@@ -60,6 +60,10 @@ struct gsb_ctx {
     // instance keys of the current batch
     DevBuf<u8> keys;
     u64 keys_cap = 0, n_keys = 0;
+    DevBuf<u8> alt;                // second sort buffer (grow-only, kept across steps)
+    u64 alt_cap = 0;
+    DevBuf<u8> third;              // receive buffer of the instance all-to-all (multi-GPU only)
+    u64 third_cap = 0;
     DevBuf<u64> cursor;            // device-side append cursor
     DevBuf<u64> hist;              // fused digit histograms [passes][256]
     DevBuf<IngestStatus> status;
@@ -85,6 +89,8 @@ struct gsb_ctx {
     PhaseTimer timer;
     cudaEvent_t user_e0 = nullptr, user_e1 = nullptr;
     Exchange* comm = nullptr;
+    bool exchanged_instances = false;
+    u64 instances_before_exchange = 0;
 
     void log(int sev, const std::string& m) { if (cfg.log) cfg.log(cfg.log_user, sev, m.c_str()); }
 };
@@ -156,12 +162,20 @@ void merge_runs(gsb_ctx* c, ReducedRun& into, ReducedRun& other) {
     other.m = 0;
 }
 
+void ensure_alt(gsb_ctx* c, u64 n) {
+    if (n <= c->alt_cap) return;
+    c->alt.free();
+    c->alt_cap = std::max<u64>(n, c->keys_cap);
+    c->alt.reset(&c->ws, c->alt_cap * c->key_bytes);
+}
+
 // sort + run-length reduce the buffered instance keys; fold into the accumulated run
 void flush_batch(gsb_ctx* c, bool final_and_only) {
     if (c->n_keys == 0) return;
     Workspace& ws = c->ws;
     const int kb = c->key_bytes;
-    DevBuf<u8> alt(&ws, c->n_keys * kb);
+    ensure_alt(c, c->n_keys);
+    DevBuf<u8>& alt = c->alt;
     int passes_run = 0;
     c->timer.start();
     int where = sort_keys(ws, kb, c->key_bits, c->keys.p, alt.p, nullptr, nullptr, c->n_keys, c->hist.p, &passes_run, &c->stats.ms_sort_sweeps);
@@ -170,13 +184,12 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     c->stats.sort_passes_model += c->passes;
     c->stats.n_batches += 1;
     ReducedRun run; u64 distinct = 0;
-    const u64 min_count = (final_and_only && c->cfg.kind == GSB_KIND_GRAPH && !c->comm) ? std::max<u64>(1, c->cfg.min_count) : 1;
+    const u64 min_count = (final_and_only && c->cfg.kind == GSB_KIND_GRAPH && (!c->comm || c->exchanged_instances)) ? std::max<u64>(1, c->cfg.min_count) : 1;
     c->timer.start();
     reduce_sorted(ws, kb, where ? alt.p : c->keys.p, nullptr, c->n_keys, min_count, run, &distinct, where ? c->keys.p : alt.p);
     c->timer.stop(c->stats.ms_reduce);
     c->counts.n_instances += c->n_keys;
     if (final_and_only) c->counts.n_distinct = distinct;
-    alt.free();
     if (c->have_acc) {
         c->timer.start();
         merge_runs(c, c->acc, run);
@@ -375,7 +388,7 @@ void gsb_destroy(gsb_ctx* c) {
         cudaStreamSynchronize(c->ws.stream);
     }
     if (c->comm) { exchange_destroy(c->comm); c->comm = nullptr; }
-    c->keys.free(); c->cursor.free(); c->hist.free(); c->status.free(); c->carry.free(); c->text_dev.free();
+    c->keys.free(); c->alt.free(); c->third.free(); c->cursor.free(); c->hist.free(); c->status.free(); c->carry.free(); c->text_dev.free();
     c->acc.keys.free(); c->acc.counts.free();
     c->timer.destroy();
     if (c->user_e0) cudaEventDestroy(c->user_e0);
@@ -424,16 +437,40 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
     if (!c) return GSB_EINVAL;
     return guarded(c, [&] {
         if (!c->counted) {
-            const bool single = !c->have_acc;
+            bool single = !c->have_acc;
+            bool exchanged_instances = false;
+            if (c->comm && single) {
+                // Multi-GPU, everything still buffered as raw instances: route each instance to the
+                // rank that owns its key range FIRST (one all-to-all of raw keys over NVLink), then
+                // sort + reduce locally exactly as on one GPU.  No merge step is needed.
+                const u64 local_instances = c->n_keys;
+                c->timer.start();
+                u64 n_recv = 0;
+                ExchangeTiming et;
+                ensure_alt(c, c->n_keys);
+                exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &n_recv, &et);
+                c->stats.ms_all_to_all += et.ms_all_to_all;
+                c->stats.exchange_bytes_sent += et.bytes_sent_remote;
+                std::swap(c->keys, c->third);                    // the received instances become the batch to sort
+                std::swap(c->keys_cap, c->third_cap);
+                c->n_keys = n_recv;
+                GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), c->ws.stream));
+                sort_digit_hist(c->key_bytes, c->keys.p, c->n_keys, c->passes, c->hist.p, c->ws.sm_count, c->ws.stream, &c->ws.launches);
+                c->timer.stop(c->stats.ms_exchange);
+                exchanged_instances = true;
+                c->instances_before_exchange = local_instances;
+            }
+            c->exchanged_instances = exchanged_instances;
             flush_batch(c, single);
             if (!c->have_acc) { c->acc.keys.reset(&c->ws, 0); c->acc.counts.reset(&c->ws, 0); c->acc.m = 0; c->have_acc = true; }
-            if (c->comm) {
+            if (c->comm && !exchanged_instances) {
                 c->timer.start();
                 exchange_runs(c->comm, c->ws, c->key_bytes, c->key_bits, c->acc);
                 c->timer.stop(c->stats.ms_exchange);
             }
             const u64 min_count = c->cfg.kind == GSB_KIND_GRAPH ? std::max<u64>(1, c->cfg.min_count) : 1;
-            const bool filtered_already = single && !c->comm;
+            const bool filtered_already = single && (!c->comm || exchanged_instances);
+            if (exchanged_instances) c->counts.n_distinct = exchange_sum(c->comm, c->ws, c->counts.n_distinct);
             if (!filtered_already) {
                 u64 local_distinct = c->acc.m;
                 if (min_count > 1 && c->acc.m) {

@@ -87,6 +87,89 @@ __global__ void bounds_kernel(const K* __restrict__ keys, u64 m, const u64* __re
     bounds[j + 1] = lo;
 }
 
+static const int kMaxRanks = 32;
+struct Splitters { u64 lo[kMaxRanks], hi[kMaxRanks]; int n; };      // n = number of splitters (ranks - 1)
+
+template <typename K>
+__device__ __forceinline__ int dest_of(const K& k, const Splitters& sp) {
+    int d = 0;                                                  // rank r owns [splitter[r-1], splitter[r])
+    for (int j = 0; j < sp.n; ++j) d += !KeyOps<K>::lt(k, KeyOps<K>::make(sp.lo[j], sp.hi[j]));
+    return d;
+}
+
+// strided sample of the (unsorted) instance keys
+template <typename K>
+__global__ void sample_strided_kernel(const K* __restrict__ keys, u64 n, u32 S, u64* __restrict__ out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S && n) {
+        u64 p = (u64)(((double)i + 0.5) * (double)n / (double)S);
+        if (p >= n) p = n - 1;
+        K k = keys[p];
+        out[2 * i] = KeyOps<K>::lo(k); out[2 * i + 1] = KeyOps<K>::hi(k);
+    }
+    if (i == 0) { out[2 * S] = n; out[2 * S + 1] = 0; }
+}
+
+static const int kPartThreads = 256;
+static const int kPartItems = 8;
+
+// pass 1: how many keys go to each destination
+template <typename K>
+__global__ void __launch_bounds__(kPartThreads) dest_count_kernel(const K* __restrict__ keys, u64 n, Splitters sp, u64* __restrict__ totals) {
+    __shared__ u32 cnt_s[kMaxRanks];
+    if (threadIdx.x < kMaxRanks) cnt_s[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (u64 base = (u64)blockIdx.x * kPartThreads * kPartItems; base < n; base += (u64)gridDim.x * kPartThreads * kPartItems) {
+#pragma unroll
+        for (int i = 0; i < kPartItems; ++i) {
+            const u64 idx = base + (u64)i * kPartThreads + threadIdx.x;
+            const int d = idx < n ? dest_of(keys[idx], sp) : -1;
+            for (int r = 0; r <= sp.n; ++r) {
+                const u32 b = __ballot_sync(0xffffffffu, d == r);
+                if (lane == 0 && b) atomicAdd(&cnt_s[r], (u32)__popc(b));
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x <= sp.n && cnt_s[threadIdx.x]) atomicAdd(&totals[threadIdx.x], (u64)cnt_s[threadIdx.x]);
+}
+
+// pass 2: scatter into per-destination regions (cursor[r] starts at the region offset); order inside
+// a region is arbitrary -- the receiver sorts
+template <typename K>
+__global__ void __launch_bounds__(kPartThreads) dest_scatter_kernel(const K* __restrict__ keys, u64 n, Splitters sp, u64* __restrict__ cursor,
+                                                                   K* __restrict__ out) {
+    __shared__ u32 cnt_s[kMaxRanks];
+    __shared__ u64 base_s[kMaxRanks];
+    const int lane = threadIdx.x & 31;
+    for (u64 base = (u64)blockIdx.x * kPartThreads * kPartItems; base < n; base += (u64)gridDim.x * kPartThreads * kPartItems) {
+        if (threadIdx.x < kMaxRanks) cnt_s[threadIdx.x] = 0;
+        __syncthreads();
+        K k[kPartItems]; int d[kPartItems]; u32 slot[kPartItems];
+#pragma unroll
+        for (int i = 0; i < kPartItems; ++i) {
+            const u64 idx = base + (u64)i * kPartThreads + threadIdx.x;
+            d[i] = -1; slot[i] = 0;
+            if (idx < n) { k[i] = keys[idx]; d[i] = dest_of(k[i], sp); }
+            for (int r = 0; r <= sp.n; ++r) {
+                const u32 b = __ballot_sync(0xffffffffu, d[i] == r);
+                u32 w = 0;
+                if (lane == 0 && b) w = atomicAdd(&cnt_s[r], (u32)__popc(b));
+                w = __shfl_sync(0xffffffffu, w, 0);
+                if (d[i] == r) slot[i] = w + __popc(b & ((1u << lane) - 1));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x <= sp.n) base_s[threadIdx.x] = cnt_s[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (u64)cnt_s[threadIdx.x]) : 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kPartItems; ++i)
+            if (d[i] >= 0) out[base_s[d[i]] + slot[i]] = k[i];
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 // n_ranks - 1 splitters at equal quantiles of the pooled sample; rank r owns keys in
@@ -212,6 +295,95 @@ void exchange_runs(Exchange* x, Workspace& ws, int key_bytes, int key_bits, Redu
     ReducedRun merged; u64 distinct = 0;
     reduce_sorted(ws, key_bytes, where ? rkeys_alt.p : rkeys.p, where ? rcounts_alt.p : rcounts.p, total, 1, merged, &distinct, nullptr);
     run = std::move(merged);
+}
+
+// Range-partition the raw instance keys by sampled splitters and exchange them (one all-to-all):
+// afterwards `recv` holds every instance, from all ranks, whose key lies in this rank's range.
+void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, u8* parted_buf /* n_keys keys */,
+                        DevBuf<u8>& recv, u64* recv_cap, u64* n_recv, ExchangeTiming* timing) {
+    const int n = x->n;
+    cudaStream_t s = ws.stream;
+    NcclApi& api = nccl();
+    if (n > kMaxRanks) throw StatusError{GSB_EINVAL, "at most 32 ranks are supported"};
+    const u32 S = kExchangeSamplesPerRank;
+    const size_t slot = 2 * (size_t)S + 2;
+    DevBuf<u64> mine(&ws, slot), all(&ws, slot * n);
+    GSB_CUDA_TRY(cudaMemsetAsync(mine.p, 0, slot * 8, s));
+    if (key_bytes == 8) sample_strided_kernel<u64><<<(S + 255) / 256, 256, 0, s>>>((const u64*)keys, n_keys, S, mine.p);
+    else sample_strided_kernel<Key128><<<(S + 255) / 256, 256, 0, s>>>((const Key128*)keys, n_keys, S, mine.p);
+    ++ws.launches;
+    check(api.AllGather(mine.p, all.p, slot, ncclUint64, x->comm, s), "ncclAllGather(samples)");
+    std::vector<u64> h(slot * n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(h.data(), all.p, h.size() * 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    std::vector<u64> samples;
+    for (int r = 0; r < n; ++r) {
+        const u64* p = h.data() + slot * r;
+        if (p[2 * S] == 0) continue;
+        samples.insert(samples.end(), p, p + 2 * (size_t)S);
+    }
+    Splitters sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.n = n - 1;
+    if (!samples.empty()) {
+        std::vector<u64> split(2 * (size_t)(n - 1));
+        plan_splitters(samples.data(), samples.size() / 2, n, split.data());
+        for (int j = 0; j < n - 1; ++j) { sp.lo[j] = split[2 * j]; sp.hi[j] = split[2 * j + 1]; }
+    }
+    // local partition: count, offsets, scatter
+    DevBuf<u64> totals(&ws, 2 * (size_t)kMaxRanks);
+    GSB_CUDA_TRY(cudaMemsetAsync(totals.p, 0, totals.bytes(), s));
+    const u64 tiles = (n_keys + kPartThreads * kPartItems - 1) / (kPartThreads * kPartItems);
+    const int grid = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)ws.sm_count * 8));
+    if (n_keys) {
+        if (key_bytes == 8) dest_count_kernel<u64><<<grid, kPartThreads, 0, s>>>((const u64*)keys, n_keys, sp, totals.p);
+        else dest_count_kernel<Key128><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, n_keys, sp, totals.p);
+        ++ws.launches;
+    }
+    std::vector<u64> send_cnt(kMaxRanks, 0), send_off(n + 1, 0);
+    GSB_CUDA_TRY(cudaMemcpyAsync(send_cnt.data(), totals.p, kMaxRanks * 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    for (int r = 0; r < n; ++r) send_off[r + 1] = send_off[r] + send_cnt[r];
+    GSB_CUDA_TRY(cudaMemcpyAsync(totals.p + kMaxRanks, send_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    struct { u8* p; } parted{parted_buf};
+    if (n_keys) {
+        if (key_bytes == 8) dest_scatter_kernel<u64><<<grid, kPartThreads, 0, s>>>((const u64*)keys, n_keys, sp, totals.p + kMaxRanks, (u64*)parted.p);
+        else dest_scatter_kernel<Key128><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, n_keys, sp, totals.p + kMaxRanks, (Key128*)parted.p);
+        ++ws.launches;
+    }
+    // counts matrix
+    DevBuf<u64> cnt_mine(&ws, n), cnt_all(&ws, (size_t)n * n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(cnt_mine.p, send_cnt.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    check(api.AllGather(cnt_mine.p, cnt_all.p, n, ncclUint64, x->comm, s), "ncclAllGather(counts)");
+    std::vector<u64> cnt((size_t)n * n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(cnt.data(), cnt_all.p, cnt.size() * 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    std::vector<u64> recv_cnt(n), recv_off(n + 1, 0);
+    for (int r = 0; r < n; ++r) { recv_cnt[r] = cnt[(size_t)r * n + x->rank]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
+    const u64 total = recv_off[n];
+    if (total > *recv_cap) {                                      // grow-only: steady-state steps allocate nothing
+        recv.free();
+        *recv_cap = total + total / 16 + 1024;
+        recv.reset(&ws, *recv_cap * key_bytes);
+    }
+    cudaEvent_t e0, e1;
+    GSB_CUDA_TRY(cudaEventCreate(&e0)); GSB_CUDA_TRY(cudaEventCreate(&e1));
+    GSB_CUDA_TRY(cudaEventRecord(e0, s));
+    check(api.GroupStart(), "ncclGroupStart");
+    u64 sent_remote = 0;
+    for (int r = 0; r < n; ++r) {
+        if (send_cnt[r]) check(api.Send(parted.p + send_off[r] * key_bytes, send_cnt[r] * key_bytes, ncclUint8, r, x->comm, s), "ncclSend(instances)");
+        if (recv_cnt[r]) check(api.Recv(recv.p + recv_off[r] * key_bytes, recv_cnt[r] * key_bytes, ncclUint8, r, x->comm, s), "ncclRecv(instances)");
+        if (r != x->rank) sent_remote += send_cnt[r] * key_bytes;
+    }
+    check(api.GroupEnd(), "ncclGroupEnd");
+    GSB_CUDA_TRY(cudaEventRecord(e1, s));
+    GSB_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    GSB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (timing) { timing->ms_all_to_all += ms; timing->bytes_sent_remote += sent_remote; }
+    *n_recv = total;
 }
 
 void exchange_gather(Exchange* x, Workspace& ws, int key_bytes, ReducedRun& run) {

@@ -15,6 +15,11 @@ void exchange_destroy(Exchange* x);
 // Range-partition `run` (sorted distinct keys + counts) by sampled splitters, all-to-all, merge:
 // afterwards rank r holds the r-th contiguous slice of the global order.
 void exchange_runs(Exchange* x, Workspace& ws, int key_bytes, int key_bits, ReducedRun& run);
+struct ExchangeTiming { double ms_all_to_all = 0; u64 bytes_sent_remote = 0; };
+// Range-partition raw instance keys by sampled splitters and exchange them with one all-to-all.
+// `parted_buf` is scratch for n_keys keys; `recv` (capacity *recv_cap keys) grows only when needed.
+void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, u8* parted_buf,
+                        DevBuf<u8>& recv, u64* recv_cap, u64* n_recv, ExchangeTiming* timing);
 // sum of one u64 over all ranks
 u64 exchange_sum(Exchange* x, Workspace& ws, u64 v);
 // concatenate all ranks' runs on rank 0 in rank order (other ranks end up empty)

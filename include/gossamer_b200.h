@@ -91,6 +91,8 @@ typedef struct gsb_stats {
     /* device time per phase, milliseconds, CUDA events on the library's stream */
     double ms_h2d, ms_scan, ms_extract, ms_sort, ms_reduce, ms_merge, ms_emit, ms_d2h, ms_exchange;
     double ms_sort_sweeps;      /* sum of the radix sweep kernels alone (events around each launch) */
+    double ms_all_to_all;       /* the NCCL all-to-all alone (inside ms_exchange) */
+    uint64_t exchange_bytes_sent; /* bytes this rank sent to OTHER ranks in the all-to-all */
     uint64_t bytes_in;          /* raw text bytes pushed */
     uint64_t bytes_out;         /* bytes handed to the sink */
     uint64_t n_symbols;         /* bases + separators in the packed symbol stream */

@@ -1,0 +1,8 @@
+#pragma once
+#include <memory>
+namespace boost {
+using std::shared_ptr;
+using std::make_shared;
+using std::dynamic_pointer_cast;
+using std::static_pointer_cast;
+}

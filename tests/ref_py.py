@@ -1,0 +1,135 @@
+"""ctypes front-end to oracle/_ref/libgossref.so: the REAL reference writers/readers
+(SparseArray / DenseSelect / WordyBitVector / IntegerArray / VariableByteArray / Graph / KmerSet),
+compiled unmodified from /root/reference/src against the Boost shim in oracle/ref/shim.
+Test infrastructure only.  `available()` is False when the library has not been built (it can only
+be built where /root/reference exists; the prebuilt .so travels to the GPU box)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "oracle", "_ref", "libgossref.so")
+_lib = None
+
+
+def available():
+    if os.path.exists(PATH):
+        return True
+    if os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle", "ref")])
+        except Exception:
+            return False
+    return os.path.exists(PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(PATH)
+        L.ref_store_new.restype = C.c_void_p
+        L.ref_store_free.argtypes = [C.c_void_p]
+        L.ref_store_put.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64]
+        L.ref_store_list.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int]
+        L.ref_store_name.argtypes = [C.c_void_p, C.c_int]
+        L.ref_store_name.restype = C.c_char_p
+        L.ref_store_size.argtypes = [C.c_void_p, C.c_int]
+        L.ref_store_size.restype = C.c_uint64
+        L.ref_store_data.argtypes = [C.c_void_p, C.c_int]
+        L.ref_store_data.restype = C.c_void_p
+        L.ref_read_graph.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+LOW_SUFFIXES = ["", ".upr", ".lwr", ".upr.upr", ".upr.lwr", ".lwr.upr", ".lwr.lwr"]
+
+
+def sparse_array_names(base):
+    return [base + ".header", base + ".high-bits", base + "-d0", base + "-d1"] + [base + ".low-bits" + s for s in LOW_SUFFIXES]
+
+
+def graph_names(base):
+    n = [base + ".header", base + "-counts-hist.txt", base + "-counts.ord0", base + "-counts.ord1", base + "-counts.ord2"]
+    n += sparse_array_names(base + "-edges") + sparse_array_names(base + "-counts.ord1p") + sparse_array_names(base + "-counts.ord2p")
+    return n
+
+
+def kmer_set_names(base):
+    return [base + ".header"] + sparse_array_names(base + ".kmers")
+
+
+class Store:
+    def __init__(self):
+        self.h = C.c_void_p(lib().ref_store_new())
+
+    def __del__(self):
+        try:
+            lib().ref_store_free(self.h)
+        except Exception:
+            pass
+
+    def put_all(self, files):
+        for name, data in files.items():
+            data = bytes(data)
+            lib().ref_store_put(self.h, name.encode(), data, len(data))
+
+    def files(self, candidates):
+        arr = (C.c_char_p * len(candidates))(*[c.encode() for c in candidates])
+        n = lib().ref_store_list(self.h, arr, len(candidates))
+        out = {}
+        for i in range(n):
+            sz = lib().ref_store_size(self.h, i)
+            out[lib().ref_store_name(self.h, i).decode()] = C.string_at(lib().ref_store_data(self.h, i), sz) if sz else b""
+        return out
+
+
+def _check(rc, err):
+    if rc < 0:
+        raise RuntimeError("reference: " + err.value.decode())
+    return rc
+
+
+def write_graph(lo, hi, counts, k, m_est=None, base="graph"):
+    lo = np.ascontiguousarray(lo, np.uint64)
+    hi = np.ascontiguousarray(hi if hi is not None else np.zeros_like(lo), np.uint64)
+    counts = np.ascontiguousarray(counts, np.uint64)
+    st, err = Store(), C.create_string_buffer(512)
+    _check(lib().ref_write_graph(st.h, _p(lo), _p(hi), _p(counts), C.c_uint64(lo.size), k,
+                                 C.c_uint64(lo.size if m_est is None else m_est), base.encode(), err, 512), err)
+    return st.files(graph_names(base))
+
+
+def write_kmer_set(lo, hi, k, m_est=None, base="kset"):
+    lo = np.ascontiguousarray(lo, np.uint64)
+    hi = np.ascontiguousarray(hi if hi is not None else np.zeros_like(lo), np.uint64)
+    st, err = Store(), C.create_string_buffer(512)
+    _check(lib().ref_write_kmer_set(st.h, _p(lo), _p(hi), C.c_uint64(lo.size), k, C.c_uint64(lo.size if m_est is None else m_est),
+                                    base.encode(), err, 512), err)
+    return st.files(kmer_set_names(base))
+
+
+def write_sparse_array(lo, hi, universe, m_est, base="sa"):
+    lo = np.ascontiguousarray(lo, np.uint64)
+    hi = np.ascontiguousarray(hi if hi is not None else np.zeros_like(lo), np.uint64)
+    st, err = Store(), C.create_string_buffer(512)
+    _check(lib().ref_write_sparse_array(st.h, _p(lo), _p(hi), C.c_uint64(lo.size), C.c_uint64(universe & (2**64 - 1)),
+                                        C.c_uint64(universe >> 64), C.c_uint64(m_est), base.encode(), err, 512), err)
+    return st.files(sparse_array_names(base))
+
+
+def read_graph(files, base="graph"):
+    """Open a file set with the reference's own Graph::open / select / rank / multiplicity."""
+    st, err = Store(), C.create_string_buffer(512)
+    st.put_all(files)
+    k = C.c_uint64()
+    n = _check(lib().ref_read_graph(st.h, base.encode(), None, None, None, C.c_uint64(0), C.byref(k), err, 512), err)
+    lo, hi, cn = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+    _check(lib().ref_read_graph(st.h, base.encode(), _p(lo), _p(hi), _p(cn), C.c_uint64(n), C.byref(k), err, 512), err)
+    return k.value, lo, hi, cn

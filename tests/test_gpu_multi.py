@@ -31,7 +31,7 @@ def _worker(rank, world, nccl_id, k, min_count, out):
     b.push(_reads(rank), G.FASTQ)
     counts = b.finish()
     lo, hi, cn = b.counts_arrays()
-    slice_info = (int(lo.size), int(lo[0]) if lo.size else None, int(lo[-1]) if lo.size else None)
+    slice_info = (int(lo.size), (int(hi[0]) << 64 | int(lo[0])) if lo.size else None, (int(hi[-1]) << 64 | int(lo[-1])) if lo.size else None)
     b.gather_to_root()
     files = None
     if rank == 0:

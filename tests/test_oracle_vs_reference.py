@@ -1,0 +1,94 @@
+"""Pins the restated oracle against the REAL reference code: the reference's own Graph::Builder,
+KmerSet::Builder and SparseArray::Builder (compiled unmodified from /root/reference/src with a
+Boost shim, oracle/ref/) must write exactly the bytes the oracle writes, and the reference's own
+Graph::open / select / rank / multiplicity must read them back.  Skipped when oracle/_ref is absent."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+import ref_py as R
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libgossref.so not built (needs /root/reference)")
+
+
+def _split(vals):
+    return (np.array([v & (2**64 - 1) for v in vals], np.uint64), np.array([v >> 64 for v in vals], np.uint64))
+
+
+def _diff(a, b):
+    out = []
+    for n in sorted(set(a) | set(b)):
+        if a.get(n) != b.get(n):
+            out.append((n, None if n not in a else len(a[n]), None if n not in b else len(b[n])))
+    return out
+
+
+@pytest.mark.parametrize("bits,m", [(20, 100), (32, 3000), (52, 20000), (52, 8192), (52, 8193), (64, 9000), (72, 500),
+                                    (100, 700), (112, 9000), (126, 300), (56, 2), (30, 0), (40, 1)])
+def test_sparse_array_bytes_equal_reference_writer(bits, m):
+    rng = np.random.default_rng(bits * 1000 + m)
+    vals = sorted({int.from_bytes(rng.bytes(16), "little") & ((1 << bits) - 1) for _ in range(m)})
+    lo, hi = _split(vals)
+    ours = O.write_sparse_array(lo, hi, 1 << bits, len(vals), base="x").files()
+    theirs = R.write_sparse_array(lo, hi, 1 << bits, len(vals), base="x")
+    assert not _diff(ours, theirs)
+
+
+@pytest.mark.parametrize("density", [0.5, 0.02, 0.002, 0.00005])
+def test_select_directories_all_block_classes_equal_reference(density):
+    rng = np.random.default_rng(int(1 / density))
+    n = 60_000
+    gaps = rng.geometric(density, n).astype(np.uint64)
+    gaps[::977] += np.uint64(1 << 26)
+    vals = np.cumsum(gaps)
+    bits = int(vals[-1]).bit_length() + 1
+    ours = O.write_sparse_array(vals, None, 1 << bits, n // 50, base="x").files()
+    theirs = R.write_sparse_array(vals, None, 1 << bits, n // 50, base="x")
+    assert not _diff(ours, theirs)
+
+
+@pytest.mark.parametrize("k", [15, 27, 31, 40, 55, 62])
+def test_graph_bytes_equal_reference_builder(k):
+    rng = np.random.default_rng(k)
+    n = 30_000
+    bits = 2 * (k + 1)
+    vals = sorted({int.from_bytes(rng.bytes(16), "little") & ((1 << bits) - 1) for _ in range(n)})
+    lo, hi = _split(vals)
+    counts = rng.integers(1, 200, len(vals)).astype(np.uint64)
+    counts[rng.integers(0, len(vals), 600)] = rng.integers(256, 65536, 600)
+    counts[rng.integers(0, len(vals), 40)] = rng.integers(65536, 2**32, 40)
+    counts[5] = 2**32 + 9                     # truncated in the array, 64-bit in the hist (src/Graph.hh:101-106)
+    ours = O.write_graph(lo, hi, counts, k).files()
+    theirs = R.write_graph(lo, hi, counts, k)
+    assert not _diff(ours, theirs)
+    # and the reference's own reader opens the oracle's files
+    kk, rlo, rhi, rcn = R.read_graph(ours)
+    assert kk == k and np.array_equal(rlo, lo) and np.array_equal(rhi, hi)
+    assert np.array_equal(rcn, (counts & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+
+
+def test_graph_with_size_estimate_different_from_count():
+    # M_est != M (the spill/merge regime passes the sum of part sizes, src/AsyncMerge.tcc:288-291)
+    rng = np.random.default_rng(3)
+    vals = np.sort(rng.choice(1 << 50, 5000, replace=False)).astype(np.uint64)
+    counts = rng.integers(1, 500, 5000).astype(np.uint64)
+    for m_est in (5000, 7000, 20000, 100):
+        assert not _diff(O.write_graph(vals, None, counts, 24, m_est=m_est).files(), R.write_graph(vals, None, counts, 24, m_est=m_est))
+
+
+@pytest.mark.parametrize("k", [25, 32, 33, 63])
+def test_kmer_set_bytes_equal_reference_builder(k):
+    rng = np.random.default_rng(k)
+    bits = 2 * k
+    vals = sorted({int.from_bytes(rng.bytes(16), "little") & ((1 << bits) - 1) for _ in range(20_000)})
+    lo, hi = _split(vals)
+    assert not _diff(O.write_kmer_set(lo, hi, k).files(), R.write_kmer_set(lo, hi, k))
+
+
+def test_whole_command_output_opens_with_reference_reader():
+    # reference known answers (src/testGossCmdBuildGraph.cc:115-179) through the reference's own Graph::open
+    fs, _ = O.build_graph([(b">\nAAAAAAAAAAAAAAAAAAAAAAAAAAAA\n", O.FASTA)], k=27)
+    k, lo, hi, cn = R.read_graph(fs.files())
+    assert k == 27 and len(lo) == 2 and list(cn) == [1, 1]
+    fs, _ = O.build_graph([(b">\nNACTTTTGATGCAATGTCAAATTCTCCNCGTCATTCGCAACTGAATACAAGNGAATTTGGAAGGAGAATNTGGTA\n", O.FASTA)], k=15)
+    assert len(R.read_graph(fs.files())[1]) == 42
