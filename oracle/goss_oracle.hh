@@ -5,10 +5,12 @@
 // the product (gossamer_b200/, include/).  It exists so that tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference legs have a checker and a CPU timing arm.
 //
-// Parity status: the restatement is pinned against every known-answer value the reference's
-// own tests hold for this path (tests/test_oracle_known_answers.py lists them with
-// file:line), and against the REAL reference writers/readers compiled from /root/reference
-// with a Boost shim where that build is available (oracle/ref/, see oracle/README.md).
+// Parity status: PINNED.  (1) every known-answer value the reference's own tests hold for this
+// path (tests/test_oracle_known_answers.py, with file:line); (2) byte-for-byte against the REAL
+// reference -- its own Graph/KmerSet/SparseArray builders, its own readers, and the whole
+// GossCmdBuildGraph / GossCmdBuildKmerSet / GossCmdTrimGraph commands -- compiled unmodified from
+// /root/reference/src with a std::-only Boost shim (oracle/ref/, tests/test_oracle_vs_reference.py,
+// 56 cases).  See oracle/README.md.
 //
 // Every function cites the reference file:line (relative to /root/reference) it restates.
 // It is written from the reference's *behaviour*; the sequential writer state machines are

@@ -10,8 +10,12 @@
 #include <string>
 #include <vector>
 
+#include "GossCmdBuildGraph.hh"
+#include "GossCmdBuildKmerSet.hh"
+#include "GossCmdTrimGraph.hh"
 #include "Graph.hh"
 #include "KmerSet.hh"
+#include "Logger.hh"
 #include "SparseArray.hh"
 #include "StringFileFactory.hh"
 #include "VariableByteArray.hh"
@@ -39,6 +43,7 @@ std::string describe(const std::exception& e) {
     const boost::exception* be = dynamic_cast<const boost::exception*>(&e);
     if (be) {
         if (const std::string* m = boost::get_error_info<Gossamer::general_error_info>(e)) return *m;
+        if (const std::string* m = boost::get_error_info<Gossamer::parse_error_info>(e)) return *m;
         if (const std::pair<uint64_t, uint64_t>* v = boost::get_error_info<Gossamer::version_mismatch_info>(e))
             return "version mismatch " + std::to_string(v->first) + " vs " + std::to_string(v->second);
     }
@@ -125,6 +130,53 @@ int64_t ref_read_graph(void* sv, const char* base, uint64_t* lo, uint64_t* hi, u
             counts[i] = g.multiplicity(i);
         }
         return (int64_t)n;
+    REF_CATCH
+}
+
+// The whole command, exactly as the reference's own test drives it (src/testGossCmdBuildGraph.cc:120-137):
+// GossCmdBuildGraph(K, S, N, T, out, fastas, fastqs, lines)(GossCmdContext(fac, log, "build-graph", opts)).
+// S = log2 hash slots, N = slots (src/GossCmdBuildGraph.cc:445-447), T = threads.  Input files are put into
+// the StringFileFactory under the given names first.
+int ref_build_graph(void* sv, int k, uint64_t S, uint64_t N, uint64_t T, const char* out,
+                    const char** fastas, int n_fastas, const char** fastqs, int n_fastqs, const char** lines, int n_lines,
+                    char* err, int errcap) {
+    REF_TRY
+        Store* s = (Store*)sv;
+        Logger log("log.txt", s->fac);
+        std::vector<std::string> fa(fastas, fastas + n_fastas), fq(fastqs, fastqs + n_fastqs), ln(lines, lines + n_lines);
+        GossCmdBuildGraph cmd((uint64_t)k, S, N, T, out, fa, fq, ln);
+        boost::program_options::variables_map opts;
+        GossCmdContext cxt(s->fac, log, "build-graph", opts);
+        cmd(cxt);
+        return 0;
+    REF_CATCH
+}
+
+int ref_build_kmer_set(void* sv, int k, uint64_t S, uint64_t N, uint64_t T, const char* out,
+                       const char** fastas, int n_fastas, const char** fastqs, int n_fastqs, const char** lines, int n_lines,
+                       char* err, int errcap) {
+    REF_TRY
+        Store* s = (Store*)sv;
+        Logger log("log.txt", s->fac);
+        std::vector<std::string> fa(fastas, fastas + n_fastas), fq(fastqs, fastqs + n_fastqs), ln(lines, lines + n_lines);
+        GossCmdBuildKmerSet cmd((uint64_t)k, S, N, T, out, fa, fq, ln);
+        boost::program_options::variables_map opts;
+        GossCmdContext cxt(s->fac, log, "build-kmer-set", opts);
+        cmd(cxt);
+        return 0;
+    REF_CATCH
+}
+
+// trim-graph -C c   (src/GossCmdTrimGraph.cc:27-127)
+int ref_trim_graph(void* sv, const char* in, const char* out, uint64_t c, char* err, int errcap) {
+    REF_TRY
+        Store* s = (Store*)sv;
+        Logger log("log.txt", s->fac);
+        GossCmdTrimGraph cmd(in, out, c, false, false, boost::optional<uint64_t>());
+        boost::program_options::variables_map opts;
+        GossCmdContext cxt(s->fac, log, "trim-graph", opts);
+        cmd(cxt);
+        return 0;
     REF_CATCH
 }
 

@@ -1,4 +1,5 @@
 #pragma once
+#include <functional>
 #include <boost/assert.hpp>
 #include <boost/static_assert.hpp>
 #include <memory>

@@ -124,6 +124,50 @@ def write_sparse_array(lo, hi, universe, m_est, base="sa"):
     return st.files(sparse_array_names(base))
 
 
+def _names(lst):
+    arr = (C.c_char_p * max(1, len(lst)))(*[x.encode() for x in lst])
+    return arr, len(lst)
+
+
+def build_graph(inputs, k, threads=2, log_slots=20, base="graph"):
+    """The reference's own GossCmdBuildGraph (parsers, k-merising, BackyardHash, sort, builders) over
+    in-memory files.  inputs: list of (bytes, format) with format 0 fasta / 1 fastq / 2 line."""
+    st, err = Store(), C.create_string_buffer(512)
+    names = {0: [], 1: [], 2: []}
+    for i, (data, fmt) in enumerate(inputs):
+        nm = f"in{i}." + {0: "fa", 1: "fq", 2: "txt"}[fmt]
+        st.put_all({nm: bytes(data)})
+        names[fmt].append(nm)
+    fa, nfa = _names(names[0])
+    fq, nfq = _names(names[1])
+    ln, nln = _names(names[2])
+    _check(lib().ref_build_graph(st.h, k, C.c_uint64(log_slots), C.c_uint64(1 << log_slots), C.c_uint64(threads), base.encode(),
+                                 fa, nfa, fq, nfq, ln, nln, err, 512), err)
+    return st, st.files(graph_names(base))
+
+
+def build_kmer_set(inputs, k, threads=2, log_slots=20, base="kset"):
+    st, err = Store(), C.create_string_buffer(512)
+    names = {0: [], 1: [], 2: []}
+    for i, (data, fmt) in enumerate(inputs):
+        nm = f"in{i}." + {0: "fa", 1: "fq", 2: "txt"}[fmt]
+        st.put_all({nm: bytes(data)})
+        names[fmt].append(nm)
+    fa, nfa = _names(names[0])
+    fq, nfq = _names(names[1])
+    ln, nln = _names(names[2])
+    _check(lib().ref_build_kmer_set(st.h, k, C.c_uint64(log_slots), C.c_uint64(1 << log_slots), C.c_uint64(threads), base.encode(),
+                                    fa, nfa, fq, nfq, ln, nln, err, 512), err)
+    return st, st.files(kmer_set_names(base))
+
+
+def trim_graph(store, src, dst, c):
+    """The reference's own `trim-graph -C c` on a graph already in `store`."""
+    err = C.create_string_buffer(512)
+    _check(lib().ref_trim_graph(store.h, src.encode(), dst.encode(), C.c_uint64(c), err, 512), err)
+    return store.files(graph_names(dst))
+
+
 def read_graph(files, base="graph"):
     """Open a file set with the reference's own Graph::open / select / rank / multiplicity."""
     st, err = Store(), C.create_string_buffer(512)

@@ -323,3 +323,35 @@ def test_config1_full_size_properties():
     # and it is bit-exact with the oracle at this size too (the oracle takes a few seconds here)
     want, _ = O.build_graph([(text, O.FASTQ)], 25, threads=8)
     assert not _diff(sink.as_bytes(), want.files())
+
+
+# ---- straight against the REAL reference (oracle/_ref/libgossref.so, prebuilt; travels with the repo) -------
+import ref_py as R
+
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libgossref.so was not shipped")
+
+
+@needs_ref
+@pytest.mark.parametrize("k,threads", [(25, 1), (31, 4), (55, 2)])
+def test_gpu_files_equal_the_reference_commands_own_output(k, threads):
+    text = _random_reads(31 * k, 40_000, 10_000, 100, err=0.01)
+    store, theirs = R.build_graph([(text, 1)], k, threads=threads, log_slots=22, base="graph")
+    sink, counts, _ = G.build_graph([(text, G.FASTQ)], k)
+    assert not _diff(sink.as_bytes(), theirs)
+    # -m 2 against the reference's build-graph + trim-graph -C 1
+    trimmed = R.trim_graph(store, "graph", "t", 1)
+    sink2, counts2, _ = G.build_graph([(text, G.FASTQ)], k, min_count=2, prefix="t")
+    assert not _diff(sink2.as_bytes(), trimmed)
+    # and the reference's own reader opens the GPU's files
+    kk, lo, hi, cn = R.read_graph(sink2.as_bytes(), base="t")
+    assert kk == k and len(lo) == counts2.n_kept
+
+
+@needs_ref
+@pytest.mark.parametrize("k", [25, 40])
+def test_gpu_kmer_set_equals_the_reference_commands_own_output(k):
+    g = S.genome(50_000, seed=k)
+    fasta = (">g\n" + "\n".join(bytes(g[i:i + 60]).decode() for i in range(0, 50_000, 60)) + "\n").encode()
+    _, theirs = R.build_kmer_set([(fasta, 0)], k, threads=2, log_slots=20)
+    sink, _, _ = G.build_kmer_set([(fasta, G.FASTA)], k)
+    assert not _diff(sink.as_bytes(), theirs)

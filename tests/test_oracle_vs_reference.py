@@ -92,3 +92,82 @@ def test_whole_command_output_opens_with_reference_reader():
     assert k == 27 and len(lo) == 2 and list(cn) == [1, 1]
     fs, _ = O.build_graph([(b">\nNACTTTTGATGCAATGTCAAATTCTCCNCGTCATTCGCAACTGAATACAAGNGAATTTGGAAGGAGAATNTGGTA\n", O.FASTA)], k=15)
     assert len(R.read_graph(fs.files())[1]) == 42
+
+
+# ---- whole commands: the reference's own GossCmdBuildGraph / GossCmdBuildKmerSet / GossCmdTrimGraph ---------
+import simreads_py as S
+
+FA, FQ, LN = 0, 1, 2
+
+
+def _noisy_reads(seed, glen, n, rlen, err):
+    g = S.genome(glen, seed)
+    arr = bytearray(bytes(S.reads_fastq(g, rlen, n, err=err, seed=seed + 1)))
+    rng = np.random.default_rng(seed)
+    for p in rng.integers(0, len(arr), 200):
+        if arr[p] in b"ACGT":
+            arr[p] = ord("N") if p % 3 == 0 else arr[p] | 0x20
+    return bytes(arr)
+
+
+SMALL_INPUTS = [
+    ([(b">\nAAAAAAAAAAAAAAAAAAAAAAAAAAAA\n", FA)], 27),
+    ([(b">\nNACTTTTGATGCAATGTCAAATTCTCCNCGTCATTCGCAACTGAATACAAGNGAATTTGGAAGGAGAATNTGGTA\n", FA)], 15),
+    ([(b">1\nTTTT\n>2\nTTTTATGTACTATTATCTTATTTCTAAATATTAACTATAGTATCCCCTGGCGTTAATACAGCTCTAGAAATC\n", FA)], 14),
+    ([(b">r\r\nACGTACGTACGTAAACCCGGGTTT\r\nACGTACGTTTTTGGGGCCCCAAAA\r\n", FA)], 7),
+    ([(b">a\nACGTAC\nGTACGT\n\nAAACCCGGGTTT\n>b\n>c\nacgtnACGTAGGATCCAGGATTACCA", FA)], 5),
+    ([(b"@r1\nACGTAC\nGTAGGCT\n+\nIIIIII\nIIIIIII\n@r2\nGGCCAATTGGCCAA\n+\nJJJJJJJJJJJJJJ\n", FQ)], 5),
+    ([(b"@r1\nACGTACGTAGGCT\n+\n@IIIIIIIIIII+\n@r2\nGGCCAATTGGCCAA\n+\n+JJJJJJJJJJJJJ", FQ)], 5),
+    ([(b"@r\r\nACGTACGTAGGCT\r\n+\r\nIIIIIIIIIIIII\r\n", FQ)], 5),
+    ([(b"ACGTACGTAGGCTAGGA\n\nGGNNACGTAGGCTAGACCA\nAC", LN)], 5),
+    ([(b"@r1\nACGTACGTAGGCT\n+\nIIIIIIIIIIIII\n", FQ), (b">x\nGGGGACGTACGTAGGCTTTT\n", FA), (b"ACGTACGTAGGCTAGGA\n", LN)], 6),
+]
+
+
+@pytest.mark.parametrize("case", range(len(SMALL_INPUTS)))
+def test_build_graph_small_inputs_equal_reference_command(case):
+    inputs, k = SMALL_INPUTS[case]
+    _, theirs = R.build_graph(inputs, k, threads=1, log_slots=12)
+    ours, _ = O.build_graph(inputs, k)
+    assert not _diff(ours.files(), theirs)
+
+
+@pytest.mark.parametrize("k,threads", [(15, 1), (25, 1), (31, 4), (32, 1), (55, 2), (62, 1)])
+def test_build_graph_random_reads_equal_reference_command(k, threads):
+    text = _noisy_reads(10 + k, 30_000, 6000, 100, err=0.01)
+    _, theirs = R.build_graph([(text, FQ)], k, threads=threads, log_slots=22)
+    ours, st = O.build_graph([(text, O.FASTQ)], k)
+    assert st.n_distinct > 100_000
+    assert not _diff(ours.files(), theirs)
+
+
+def test_min_count_equals_reference_build_then_trim():
+    # -m 2  ==  build-graph, then trim-graph -C 1 (src/GossCmdTrimGraph.cc:97-124)
+    text = _noisy_reads(77, 20_000, 8000, 100, err=0.01)
+    store, _ = R.build_graph([(text, FQ)], 31, threads=1, log_slots=22, base="g")
+    for m in (2, 3, 5):
+        theirs = R.trim_graph(store, "g", f"t{m}", m - 1)
+        ours, st = O.build_graph([(text, O.FASTQ)], 31, min_count=m, base=f"t{m}")
+        assert 0 < st.n_kept < st.n_distinct
+        assert not _diff(ours.files(), theirs)
+
+
+@pytest.mark.parametrize("k", [25, 32, 40, 63])
+def test_build_kmer_set_equals_reference_command(k):
+    g = S.genome(40_000, seed=k)
+    fasta = (">g1\n" + "\n".join(bytes(g[i:i + 60]).decode() for i in range(0, 20_000, 60)) + "\n>g2 desc\n" +
+             "\n".join(bytes(g[i:i + 71]).decode() for i in range(20_000, 40_000, 71)) + "\n").encode()
+    _, theirs = R.build_kmer_set([(fasta, FA)], k, threads=1, log_slots=20)
+    ours, _ = O.build_kmer_set([(fasta, O.FASTA)], k)
+    assert not _diff(ours.files(), theirs)
+
+
+@pytest.mark.parametrize("text,fmt", [
+    (b"r1\nACGT\n+\nIIII\n", FQ), (b"@r1\nACGT\n", FQ), (b"@r1\nACGT\n@r2\n", FQ), (b"@r1\nACGT\n+r2\nIIII\n", FQ),
+    (b"@r1\nACGT\n+\nIII\n", FQ), (b"ACGT\n", FA)])
+def test_parse_errors_match_reference_command(text, fmt):
+    with pytest.raises(RuntimeError) as re_:
+        R.build_graph([(text, fmt)], 3, threads=1, log_slots=10)
+    with pytest.raises(O.OracleParseError) as oe:
+        O.build_graph([(text, fmt)], 3)
+    assert str(oe.value) in str(re_.value)
