@@ -61,10 +61,14 @@ template <typename T> struct LookbackWord;
 template <> struct LookbackWord<u32> { static const int kShift = 30; static const u32 kMask = 0x3FFFFFFFu; };
 template <> struct LookbackWord<u64> { static const int kShift = 62; static const u64 kMask = 0x3FFFFFFFFFFFFFFFull; };
 
-template <typename T>
-__device__ __forceinline__ T ld_volatile(const T* p) { return *(const volatile T*)p; }
-template <typename T>
-__device__ __forceinline__ void st_volatile(T* p, T v) { *(volatile T*)p = v; }
+// Look-back state is read and written with relaxed GPU-scope accesses (status and value live in
+// ONE word, so no ordering against other data is needed).  `volatile` compiles to
+// LDG/STG.E.STRONG.SYS -- system scope -- which ncu showed as the dominant stall of the
+// run-length kernel; .gpu scope stops at the L2.
+__device__ __forceinline__ u32 ld_volatile(const u32* p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ u64 ld_volatile(const u64* p) { u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_volatile(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_volatile(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 
 // Called by ONE thread per (tile, bin).  `states` is indexed [tile * stride + bin]; tiles must be
 // numbered by an atomic ticket so that every lower tile is already running.
@@ -87,6 +91,38 @@ __device__ __forceinline__ T lookback_exclusive(T* states, u32 stride, u32 tile,
         if ((s >> S) == 2) break;
     }
     st_volatile(mine, (T)(((T)2 << S) | (excl + aggregate)));
+    return excl;
+}
+
+// Warp-wide variant for one scalar per tile (stride 1): called by ALL 32 lanes of one warp; 32
+// predecessor states are examined per round trip.  Returns the exclusive prefix in every lane.
+template <typename T>
+__device__ __forceinline__ T lookback_exclusive_warp(T* states, u32 tile, T aggregate) {
+    const int S = LookbackWord<T>::kShift;
+    const T M = LookbackWord<T>::kMask;
+    const int lane = threadIdx.x & 31;
+    T* mine = states + tile;
+    if (lane == 0) st_volatile(mine, (T)(((T)(tile == 0 ? 2 : 1) << S) | aggregate));
+    if (tile == 0) return 0;
+    T excl = 0;
+    long long t = (long long)tile - 1;
+    for (;;) {
+        const long long idx = t - lane;
+        const T sv = idx >= 0 ? ld_volatile(states + idx) : (T)((T)2 << S);
+        const u32 status = (u32)(sv >> S);
+        const u32 zero_mask = __ballot_sync(0xffffffffu, status == 0);
+        const u32 pref_mask = __ballot_sync(0xffffffffu, status == 2);
+        const int first_zero = zero_mask ? __ffs(zero_mask) - 1 : 32;
+        const int first_pref = pref_mask ? __ffs(pref_mask) - 1 : 32;
+        const int take = first_pref < first_zero ? first_pref + 1 : first_zero;   // lanes [0, take) contribute
+        T v = lane < take ? (sv & M) : (T)0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (first_pref < first_zero) break;
+        t -= take;                                              // re-poll from the first unpublished tile (or go 32 further back)
+    }
+    if (lane == 0) st_volatile(mine, (T)(((T)2 << S) | (excl + aggregate)));
     return excl;
 }
 

@@ -478,7 +478,7 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                     DevBuf<u8> fk(&c->ws, c->acc.m * c->key_bytes);
                     DevBuf<u64> fc(&c->ws, c->acc.m), total(&c->ws, 1);
                     DevBuf<u8> lb(&c->ws, rle_lookback_bytes(c->acc.m));
-                    sort_filter(c->key_bytes, c->acc.keys.p, c->acc.counts.p, c->acc.m, min_count, fk.p, fc.p, lb.p, total.p, c->ws.stream, &c->ws.launches);
+                    sort_filter(c->key_bytes, c->acc.keys.p, c->acc.counts.p, nullptr, c->acc.m, min_count, fk.p, fc.p, lb.p, total.p, c->ws.stream, &c->ws.launches);
                     u64 kept = 0;
                     GSB_CUDA_TRY(cudaMemcpyAsync(&kept, total.p, 8, cudaMemcpyDeviceToHost, c->ws.stream));
                     c->ws.sync();

@@ -332,7 +332,17 @@ template <> struct WindowOps<Key128> {
 
 static const int kExThreads = 256;
 
-template <typename K, int MODE>
+// reverse the four bases of a byte and complement them: digit j of rc(x) = revcomp_byte(digit P-1-j of x)
+// whenever the key is a whole number of bytes (window % 4 == 0)
+__device__ __forceinline__ u32 revcomp_byte(u32 v) {
+    v = ~v & 0xFFu;
+    return ((v & 0x03u) << 6) | ((v & 0x0Cu) << 2) | ((v & 0x30u) >> 2) | ((v & 0xC0u) >> 6);
+}
+
+// SYM: graph mode with window % 4 == 0 -- the digit histograms of the reverse complements are a
+// permutation of those of the forward keys, so only the forward keys are histogrammed (half the
+// shared-memory atomics, which bound this kernel) and the mirror image is added at flush time.
+template <typename K, int MODE, bool SYM>
 __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restrict__ codes, const u32* __restrict__ valid,
                                                              u64 p_begin, u64 p_end, int w, int passes,
                                                              K* __restrict__ out, u64* __restrict__ cursor, u64 capacity,
@@ -388,7 +398,7 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
             }
             for (int d = 0; d < passes; ++d) {
                 atomicAdd(&hist_s[d * 256 + KO::digit(x, 8 * d)], 1u);
-                if (MODE == GSB_KIND_GRAPH) atomicAdd(&hist_s[d * 256 + KO::digit(y, 8 * d)], 1u);
+                if (MODE == GSB_KIND_GRAPH && !SYM) atomicAdd(&hist_s[d * 256 + KO::digit(y, 8 * d)], 1u);
             }
         }
         __syncthreads();
@@ -396,7 +406,10 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
     __syncthreads();
     for (int i = threadIdx.x; i < passes * 256; i += kExThreads) {
         u32 c = hist_s[i];
-        if (c) atomicAdd(&digit_hist[i], (u64)c);
+        if (c) {
+            atomicAdd(&digit_hist[i], (u64)c);
+            if (SYM) atomicAdd(&digit_hist[(passes - 1 - (i >> 8)) * 256 + revcomp_byte(i & 255)], (u64)c);
+        }
     }
 }
 
@@ -482,10 +495,12 @@ static void launch_extract(int kind, const u64* codes, const u32* valid, u64 p_b
     u64 tiles = (p_end - p_begin + kExThreads - 1) / kExThreads;
     int grid = (int)(tiles < (u64)sm_count * 8 ? tiles : (u64)sm_count * 8);
     size_t smem = (size_t)passes * 256 * sizeof(u32);
-    if (kind == GSB_KIND_GRAPH)
-        extract_kernel<K, GSB_KIND_GRAPH><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+    if (kind == GSB_KIND_GRAPH && (w % 4) == 0)
+        extract_kernel<K, GSB_KIND_GRAPH, true><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+    else if (kind == GSB_KIND_GRAPH)
+        extract_kernel<K, GSB_KIND_GRAPH, false><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
     else
-        extract_kernel<K, GSB_KIND_KMERSET><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+        extract_kernel<K, GSB_KIND_KMERSET, false><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
 }
 
 void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,

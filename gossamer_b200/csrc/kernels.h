@@ -81,9 +81,11 @@ void sort_digit_base(const u64* hist, u64* base, int passes, cudaStream_t s, u64
 void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vout, u64 n, int pass, const u64* digit_base_all,
                void* lookback, cudaStream_t s, u64* launches, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr);
 u64 rle_lookback_bytes(u64 n);
-void sort_rle(int key_bytes, const void* keys, u64 n, void* out_keys, u64* out_pos, void* lookback, u64* total_dev, cudaStream_t s, u64* launches);
-void sort_counts_from_pos(const u64* pos, const u64* csum, u64 m, u64* counts, cudaStream_t s, u64* launches);
-void sort_filter(int key_bytes, const void* keys, const u64* counts, u64 m, u64 min_count, void* out_keys, u64* out_counts,
+u64 rle_tiles(u64 n);
+void sort_rle_count(int key_bytes, const void* keys, u64 n, u64 min_count, u32* tile_kept, u64* total_heads, cudaStream_t s, u64* launches);
+void sort_rle_emit(int key_bytes, const void* keys, const u64* csum, u64 n, u64 min_count, const u64* tile_off, void* out_keys, u64* out_counts,
+                   cudaStream_t s, u64* launches);
+void sort_filter(int key_bytes, const void* keys, const u64* counts, const u64* pos, u64 m, u64 min_count, void* out_keys, u64* out_counts,
                  void* lookback, u64* total_dev, cudaStream_t s, u64* launches);
 void sort_scan_weights(const u64* w, u64* csum, u64 n, u64* tmp, cudaStream_t s, u64* launches);
 u64 sort_scan_tmp_elems(u64 n);

@@ -76,7 +76,7 @@ __device__ __forceinline__ LB lookback_window(const LB* __restrict__ bin_states 
 //   MODE 0  count digits first (shared atomics) -> publish the tile aggregate -> rank -> look back -> write
 //   MODE 1  rank and count in one go (ballots + plain LDS/STS on the warp's counters, no atomics)
 //           -> publish -> scatter -> look back -> write
-template <typename K, typename LB, int THREADS, int ITEMS, bool HAS_VALUES, int MINB, int MODE>
+template <typename K, typename LB, int THREADS, int ITEMS, bool HAS_VALUES, int MINB, int MODE, int LBW = 4>
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __restrict__ in, K* __restrict__ out,
                                                                  const u64* __restrict__ vin, u64* __restrict__ vout,
                                                                  u64 n, int shift, const u64* __restrict__ digit_base,
@@ -94,16 +94,17 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     __shared__ u32 scan_s[THREADS / 32 + 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
+    if (threadIdx.x == 0) tile_s = (ablate & 8) ? blockIdx.x : atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < WARPS * 256; i += THREADS) warp_ofs[i] = 0;
     __syncthreads();
     const u32 tile = tile_s;
     const u64 base = (u64)tile * TILE;
     const u32 tile_n = (u32)((n - base) < (u64)TILE ? (n - base) : (u64)TILE);
     const u32 lt_mask = (1u << lane) - 1;
+    if (ablate & 16) in += (u64)(tile & 63) * TILE - base;      // profiling only: every load hits the L2
 
     K key[ITEMS];
-    u16 rank[MODE == 1 ? ITEMS : 1];
+    u16 rank[MODE != 0 ? ITEMS : 1];
     const u32 wbase = warp * 32 * ITEMS + lane;
     u32* my_ofs = warp_ofs + warp * 256;
 #pragma unroll
@@ -112,23 +113,44 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
         key[i] = idx < tile_n ? in[base + idx] : KO::make(0, 0);
     }
 
-    // peer set of this lane for item i: lanes (with a key) whose digit equals mine, from 8 ballots
+    // peer set of this lane for item i: lanes (with a key) whose digit equals mine, from 8 ballots.
+    // Hand-scheduled: per bit one predicate test, one vote, one select, one LOP3 that accumulates the
+    // lanes that DIFFER from me in that bit (the compiler's version of the obvious loop spent 36 % of
+    // all executed instructions here, ncu source view).
     auto peer_set = [&](u32 d, bool ok) -> u32 {
-        u32 peers = __ballot_sync(0xffffffffu, ok);
+        const u32 okmask = __ballot_sync(0xffffffffu, ok);
         if (ablate & 2) return ok ? (1u << lane) : 0u;          // profiling only: wrong ranks, no ballots
+        u32 differ = 0;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const u32 bal = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? bal : ~bal;
+            u32 bal, mine;
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                         "and.b32 t, %2, %3;\n\t"
+                         "setp.ne.b32 p, t, 0;\n\t"
+                         "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                         "selp.b32 %1, 0xffffffff, 0, p;\n\t}"
+                         : "=r"(bal), "=r"(mine) : "r"(d), "r"(1u << b));
+            differ |= bal ^ mine;                               // my bit set: lanes with it clear differ; clear: lanes with it set
         }
-        return peers;
+        return ~differ & okmask;
     };
 
     if (MODE == 0) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
             if (wbase + i * 32 < tile_n) atomicAdd(&my_ofs[KO::digit(key[i], shift)], 1u);
+    } else if (MODE == 2) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const bool ok = wbase + i * 32 < tile_n;
+            const u32 d = KO::digit(key[i], shift);
+            const u32 peers = peer_set(d, ok);
+            const int leader = __ffs(peers) - 1;
+            u32 before = 0;
+            if (ok && lane == leader) before = atomicAdd(&my_ofs[d], (u32)__popc(peers));
+            before = __shfl_sync(0xffffffffu, before, leader < 0 ? lane : leader);
+            rank[i] = (u16)(before + __popc(peers & lt_mask));
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     if (threadIdx.x < 256) {
         LB excl = 0;
         if (tile != 0 && !(ablate & 1)) {
-            excl = lookback_window<LB, 4>(lookback + threadIdx.x, tile);
+            excl = lookback_window<LB, LBW>(lookback + threadIdx.x, tile);
             st_volatile(my_state, (LB)(((LB)2 << S) | (excl + (LB)count)));
         }
         gofs[threadIdx.x] = digit_base[threadIdx.x] + (u64)excl - (u64)bstart;
@@ -207,22 +229,26 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
 
     // coalesced write-out, one contiguous run per digit
     if (ablate & 4) return;
-    for (u32 j = threadIdx.x; j < tile_n; j += THREADS) {
-        const K k = keys_s[j];
-        const u64 dst = (ablate & 1) ? (base + j) : gofs[KO::digit(k, shift)] + j;
-        out[dst] = k;
-        if (HAS_VALUES) vout[dst] = vin[base + vpos_s[j]];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const u32 j = i * THREADS + threadIdx.x;
+        if (j < tile_n) {
+            const K k = keys_s[j];
+            const u64 dst = (ablate & 1) ? (base + j) : gofs[KO::digit(k, shift)] + j;
+            out[dst] = k;
+            if (HAS_VALUES) vout[dst] = vin[base + vpos_s[j]];
+        }
     }
 }
 
 extern int g_sort_ablate_fwd;
-template <typename K, typename LB, int THREADS, int ITEMS, bool HAS_VALUES, int MINB, int MODE>
+template <typename K, typename LB, int THREADS, int ITEMS, bool HAS_VALUES, int MINB, int MODE, int LBW = 4>
 static void launch_onesweep(const void* in, void* out, const u64* vin, u64* vout, u64 n, int shift, const u64* digit_base,
                             void* lookback, u32* ticket, cudaStream_t s) {
     constexpr int TILE = THREADS * ITEMS;
     const size_t smem = (size_t)TILE * sizeof(K) + (size_t)(THREADS / 32) * 256 * 4 + 256 * 8 + (HAS_VALUES ? (size_t)TILE * 4 : 0);
     static bool configured = false;
-    auto kern = onesweep_kernel<K, LB, THREADS, ITEMS, HAS_VALUES, MINB, MODE>;
+    auto kern = onesweep_kernel<K, LB, THREADS, ITEMS, HAS_VALUES, MINB, MODE, LBW>;
     if (!configured) {
         GSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -239,7 +265,7 @@ static int g_sort_tuning = 0;
 int g_sort_ablate_fwd = 0;
 #define g_sort_ablate g_sort_ablate_fwd
 // profiling only (gsb_debug_set_tuning(id | ablate << 8)): results are wrong when non-zero
-static const SortShape kShapes64[] = {{256, 16}, {256, 16}, {256, 16}, {384, 16}, {512, 8}, {256, 12}, {512, 12}, {256, 12}};
+static const SortShape kShapes64[] = {{256, 16}, {256, 16}, {256, 16}, {256, 16}, {256, 16}, {1024, 8}, {384, 16}, {256, 20}};
 static const int kNumShapes64 = (int)(sizeof(kShapes64) / sizeof(kShapes64[0]));
 static const SortShape kShape128 = {256, 8};
 
@@ -298,13 +324,16 @@ void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vo
     if (key_bytes == 8) {
         switch (g_sort_tuning) {
             default: GSB_LAUNCH(u64, 256, 16, 4, 0); break;
-            case 1: GSB_LAUNCH(u64, 256, 16, 3, 1); break;
-            case 2: GSB_LAUNCH(u64, 256, 16, 4, 1); break;
-            case 3: GSB_LAUNCH(u64, 384, 16, 2, 1); break;
-            case 4: GSB_LAUNCH(u64, 512, 8, 2, 1); break;
-            case 5: GSB_LAUNCH(u64, 256, 12, 4, 1); break;
-            case 6: GSB_LAUNCH(u64, 512, 12, 2, 0); break;
-            case 7: GSB_LAUNCH(u64, 256, 12, 4, 0); break;
+            case 1: if (small && !hv) { launch_onesweep<u64, u32, 256, 16, false, 4, 0, 8>(in, out, vin, vout, n, shift, db, lookback, ticket, s); break; }
+                    GSB_LAUNCH(u64, 256, 16, 4, 0); break;
+            case 2: if (small && !hv) { launch_onesweep<u64, u32, 256, 16, false, 4, 0, 16>(in, out, vin, vout, n, shift, db, lookback, ticket, s); break; }
+                    GSB_LAUNCH(u64, 256, 16, 4, 0); break;
+            case 3: if (small && !hv) { launch_onesweep<u64, u32, 256, 16, false, 4, 0, 32>(in, out, vin, vout, n, shift, db, lookback, ticket, s); break; }
+                    GSB_LAUNCH(u64, 256, 16, 4, 0); break;
+            case 4: GSB_LAUNCH(u64, 256, 16, 4, 2); break;
+            case 5: GSB_LAUNCH(u64, 1024, 8, 1, 0); break;
+            case 6: GSB_LAUNCH(u64, 384, 16, 2, 0); break;
+            case 7: GSB_LAUNCH(u64, 256, 20, 3, 0); break;
         }
     } else {
         GSB_LAUNCH(Key128, 256, 8, 3, 0);
@@ -320,130 +349,212 @@ void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vo
 static const int kRleThreads = 256;
 static const int kRleItems = 8;
 
+// Run-length reduce WITHOUT a cross-tile dependency chain.  ncu showed the single-pass look-back
+// version latency bound (58 % of stall samples at the barrier that waits for the look-back, 2.8 ms
+// for 5 GB): a tile must hold its keys while it waits, and the register file bounds the bytes in
+// flight.  Two streaming passes over the sorted keys instead:
+//   pass 1  count, per tile, the run heads that survive the min-count filter (+ all heads, for the stats)
+//   scan    tile counts -> tile offsets
+//   pass 2  recompute the heads, write (key, count) of the survivors at their final place
+// A head at i survives iff keys[i + m - 1] == keys[i] (the keys are sorted), and its count is the
+// distance to the end of its run, found by a galloping search that almost always stays inside the
+// cache lines the tile has just read.  The second read of the keys comes mostly from the L2.
 template <typename K>
-__global__ void __launch_bounds__(kRleThreads) rle_kernel(const K* __restrict__ keys, u64 n, K* __restrict__ out_keys, u64* __restrict__ out_pos,
-                                                          u64* lookback, u32* ticket, u64* __restrict__ total_out) {
-    typedef KeyOps<K> KO;
-    __shared__ u32 tile_s;
-    __shared__ u64 prefix_s;
-    __shared__ u32 scan_s[kRleThreads / 32 + 1];
-    if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const u32 tile = tile_s;
-    const u64 base = (u64)tile * (kRleThreads * kRleItems) + (u64)threadIdx.x * kRleItems;
-    K k[kRleItems];
-    bool head[kRleItems];
-    u32 cnt = 0;
-    K prev = KO::make(0, 0);
-    if (base > 0 && base < n) prev = keys[base - 1];
+struct RleTile {
+    // head / survivor ballots of one warp-striped tile; returns the warp's survivor count
+    __device__ static __forceinline__ u32 scan(const K* __restrict__ keys, u64 n, u64 wbase, int lane, u64 min_count,
+                                               K (&k)[kRleItems], u32 (&kept)[kRleItems], u32 (&headb)[kRleItems], u32& heads) {
+        typedef KeyOps<K> KO;
+        K carry = KO::make(0, 0);
+        if (wbase > 0 && wbase < n) carry = keys[wbase - 1];
 #pragma unroll
-    for (int i = 0; i < kRleItems; ++i) {
-        const u64 idx = base + i;
-        head[i] = false;
-        if (idx < n) {
-            k[i] = keys[idx];
-            head[i] = idx == 0 || !KO::eq(k[i], prev);
-            prev = k[i];
-            cnt += head[i];
+        for (int i = 0; i < kRleItems; ++i) {
+            const u64 idx = wbase + (u64)i * 32 + lane;
+            k[i] = idx < n ? keys[idx] : KO::make(0, 0);
         }
+        u32 wcount = 0;
+        heads = 0;
+#pragma unroll
+        for (int i = 0; i < kRleItems; ++i) {
+            const u64 idx = wbase + (u64)i * 32 + lane;
+            const bool ok = idx < n;
+            const K& last_src = i ? k[i ? i - 1 : 0] : carry;
+            u64 up_lo = __shfl_up_sync(0xffffffffu, KO::lo(k[i]), 1), up_hi = 0;
+            u64 last_lo = __shfl_sync(0xffffffffu, KO::lo(last_src), i ? 31 : 0), last_hi = 0;
+            if (sizeof(K) == 16) {
+                up_hi = __shfl_up_sync(0xffffffffu, KO::hi(k[i]), 1);
+                last_hi = __shfl_sync(0xffffffffu, KO::hi(last_src), i ? 31 : 0);
+            }
+            const K prev = KO::make(lane ? up_lo : last_lo, lane ? up_hi : last_hi);
+            const bool head = ok && (idx == 0 || !KO::eq(k[i], prev));
+            bool keep = head;
+            if (head && min_count > 1) keep = idx + min_count - 1 < n && KO::eq(keys[idx + min_count - 1], k[i]);
+            headb[i] = __ballot_sync(0xffffffffu, head);
+            heads += __popc(headb[i]);
+            kept[i] = __ballot_sync(0xffffffffu, keep);
+            wcount += __popc(kept[i]);
+        }
+        return wcount;
     }
-    u32 tile_total;
-    u32 ex = block_exclusive_scan<u32, kRleThreads>(cnt, &tile_total, scan_s);
+};
+
+template <typename K>
+__global__ void __launch_bounds__(kRleThreads, 4) rle_count_kernel(const K* __restrict__ keys, u64 n, u64 min_count,
+                                                                   u32* __restrict__ tile_kept, u64* __restrict__ total_heads) {
+    __shared__ u32 warp_tot[kRleThreads / 32], warp_heads[kRleThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 wbase = (u64)blockIdx.x * (kRleThreads * kRleItems) + (u64)warp * 32 * kRleItems;
+    K k[kRleItems]; u32 kept[kRleItems], headb[kRleItems]; u32 heads;
+    const u32 wcount = RleTile<K>::scan(keys, n, wbase, lane, min_count, k, kept, headb, heads);
+    if (lane == 0) { warp_tot[warp] = wcount; warp_heads[warp] = heads; }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        u64 p = lookback_exclusive<u64>(lookback, 1u, tile, 0u, (u64)tile_total);
-        prefix_s = p;
-        if ((u64)(tile + 1) * (kRleThreads * kRleItems) >= n) {           // last tile
-            *total_out = p + tile_total;
-            out_pos[p + tile_total] = n;                                     // sentinel: count_j = pos[j+1] - pos[j]
-        }
-    }
-    __syncthreads();
-    u64 j = prefix_s + ex;
+        u32 t = 0, h = 0;
 #pragma unroll
-    for (int i = 0; i < kRleItems; ++i)
-        if (head[i]) { out_keys[j] = k[i]; out_pos[j] = base + i; ++j; }
+        for (int w = 0; w < kRleThreads / 32; ++w) { t += warp_tot[w]; h += warp_heads[w]; }
+        tile_kept[blockIdx.x] = t;
+        if (h) atomicAdd(total_heads, (u64)h);
+    }
 }
 
-u64 rle_lookback_bytes(u64 n) { return ((n + kRleThreads * kRleItems - 1) / (kRleThreads * kRleItems)) * 8 + 256; }
+// count of the run that starts at idx: distance to the first different key (gallop, then bisect)
+template <typename K>
+__device__ __forceinline__ u64 run_end(const K* __restrict__ keys, u64 n, u64 known_equal, const K& key) {
+    typedef KeyOps<K> KO;
+    u64 a = known_equal, step = 1;                              // keys[a] == key
+    while (a + step < n && KO::eq(keys[a + step], key)) { a += step; step <<= 1; }
+    u64 lo = a + 1, hi = a + step < n ? a + step : n;           // keys[hi] != key or hi == n
+    while (lo < hi) { const u64 mid = lo + ((hi - lo) >> 1); if (KO::eq(keys[mid], key)) lo = mid + 1; else hi = mid; }
+    return lo;
+}
 
-void sort_rle(int key_bytes, const void* keys, u64 n, void* out_keys, u64* out_pos, void* lookback, u64* total_dev, cudaStream_t s, u64* launches) {
-    if (!n) {
-        GSB_CUDA_TRY(cudaMemsetAsync(total_dev, 0, 8, s));
-        GSB_CUDA_TRY(cudaMemsetAsync(out_pos, 0, 8, s));
-        return;
+template <typename K>
+__global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __restrict__ keys, const u64* __restrict__ csum, u64 n, u64 min_count,
+                                                                  const u64* __restrict__ tile_off, K* __restrict__ out_keys,
+                                                                  u64* __restrict__ out_counts) {
+    constexpr int WORDS = kRleThreads * kRleItems / 32;          // the tile's run-head bit vector (warp-striped layout
+    __shared__ u32 warp_tot[kRleThreads / 32];                  // makes word w*ITEMS+i hold keys [32(w*ITEMS+i), +32))
+    __shared__ u32 head_bits[WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 tbase = (u64)blockIdx.x * (kRleThreads * kRleItems);
+    const u64 wbase = tbase + (u64)warp * 32 * kRleItems;
+    K k[kRleItems]; u32 kept[kRleItems], headb[kRleItems]; u32 heads;
+    const u32 wcount = RleTile<K>::scan(keys, n, wbase, lane, min_count, k, kept, headb, heads);
+    if (lane == 0) {
+        warp_tot[warp] = wcount;
+#pragma unroll
+        for (int i = 0; i < kRleItems; ++i) head_bits[warp * kRleItems + i] = headb[i];
     }
-    const u64 lb = rle_lookback_bytes(n);
-    GSB_CUDA_TRY(cudaMemsetAsync(lookback, 0, lb, s));
-    u32* ticket = (u32*)((char*)lookback + lb - 256);
-    const u64 tiles = (n + kRleThreads * kRleItems - 1) / (kRleThreads * kRleItems);
-    if (key_bytes == 8) rle_kernel<u64><<<(unsigned)tiles, kRleThreads, 0, s>>>((const u64*)keys, n, (u64*)out_keys, out_pos, (u64*)lookback, ticket, total_dev);
-    else rle_kernel<Key128><<<(unsigned)tiles, kRleThreads, 0, s>>>((const Key128*)keys, n, (Key128*)out_keys, out_pos, (u64*)lookback, ticket, total_dev);
+    __syncthreads();
+    u64 j = tile_off[blockIdx.x];
+    for (int w = 0; w < warp; ++w) j += warp_tot[w];
+    const u32 lt = (1u << lane) - 1;
+    const u64 tile_end = tbase + kRleThreads * kRleItems < n ? tbase + kRleThreads * kRleItems : n;
+#pragma unroll
+    for (int i = 0; i < kRleItems; ++i) {
+        if ((kept[i] >> lane) & 1u) {
+            const u64 idx = wbase + (u64)i * 32 + lane;
+            // end of the run = next run head: first from the tile's bit vector, else gallop past the tile
+            int w = warp * kRleItems + i;
+            u32 m = lane == 31 ? 0u : (head_bits[w] & ~((2u << lane) - 1));
+            while (!m && ++w < WORDS) m = head_bits[w];
+            const u64 end = m ? tbase + (u64)w * 32 + (__ffs(m) - 1)
+                              : (tile_end < n ? run_end<K>(keys, n, tile_end - 1, k[i]) : n);
+            const u64 o = j + __popc(kept[i] & lt);
+            out_keys[o] = k[i];
+            out_counts[o] = csum ? (csum[end] - csum[idx]) : (end - idx);
+        }
+        j += __popc(kept[i]);
+    }
+}
+
+u64 rle_tiles(u64 n) { return (n + kRleThreads * kRleItems - 1) / (kRleThreads * kRleItems); }
+u64 rle_lookback_bytes(u64 n) { return rle_tiles(n) * 8 + 256; }
+
+void sort_rle_count(int key_bytes, const void* keys, u64 n, u64 min_count, u32* tile_kept, u64* total_heads, cudaStream_t s, u64* launches) {
+    if (!n) return;
+    const unsigned tiles = (unsigned)rle_tiles(n);
+    if (key_bytes == 8) rle_count_kernel<u64><<<tiles, kRleThreads, 0, s>>>((const u64*)keys, n, min_count, tile_kept, total_heads);
+    else rle_count_kernel<Key128><<<tiles, kRleThreads, 0, s>>>((const Key128*)keys, n, min_count, tile_kept, total_heads);
     ++*launches;
 }
 
-// counts[j] = pos[j+1] - pos[j]              (fresh instances: every instance weighs 1)
-// counts[j] = csum[pos[j+1]] - csum[pos[j]]  (merging reduced runs: csum = exclusive scan of the weights, n+1 entries)
-__global__ void counts_from_pos_kernel(const u64* __restrict__ pos, const u64* __restrict__ csum, u64 m, u64* __restrict__ counts) {
-    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (u64)gridDim.x * blockDim.x) {
-        u64 a = pos[j], b = pos[j + 1];
-        counts[j] = csum ? (csum[b] - csum[a]) : (b - a);
-    }
-}
-
-void sort_counts_from_pos(const u64* pos, const u64* csum, u64 m, u64* counts, cudaStream_t s, u64* launches) {
-    if (!m) return;
-    u64 blocks = (m + 255) / 256;
-    counts_from_pos_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>(pos, csum, m, counts);
+void sort_rle_emit(int key_bytes, const void* keys, const u64* csum, u64 n, u64 min_count, const u64* tile_off, void* out_keys, u64* out_counts,
+                   cudaStream_t s, u64* launches) {
+    if (!n) return;
+    const unsigned tiles = (unsigned)rle_tiles(n);
+    if (key_bytes == 8) rle_emit_kernel<u64><<<tiles, kRleThreads, 0, s>>>((const u64*)keys, csum, n, min_count, tile_off, (u64*)out_keys, out_counts);
+    else rle_emit_kernel<Key128><<<tiles, kRleThreads, 0, s>>>((const Key128*)keys, csum, n, min_count, tile_off, (Key128*)out_keys, out_counts);
     ++*launches;
 }
 
 // ------------------------------------------------------------------------------------------
 // min-count filter: keep (key,count) with count >= min_count, order preserved
 // ------------------------------------------------------------------------------------------
+// Order-preserving compaction of (key, count >= min_count).  Counts come either from a counts
+// array or directly from the run-head positions (count_j = pos[j+1] - pos[j]), which saves writing
+// and re-reading the full counts array when a min-count filter follows the run-length reduce.
 template <typename K>
-__global__ void __launch_bounds__(kRleThreads) filter_kernel(const K* __restrict__ keys, const u64* __restrict__ counts, u64 m, u64 min_count,
-                                                             K* __restrict__ out_keys, u64* __restrict__ out_counts,
+__global__ void __launch_bounds__(kRleThreads, 4) filter_kernel(const K* __restrict__ keys, const u64* __restrict__ counts, const u64* __restrict__ pos,
+                                                             u64 m, u64 min_count, K* __restrict__ out_keys, u64* __restrict__ out_counts,
                                                              u64* lookback, u32* ticket, u64* __restrict__ total_out) {
+    constexpr int WARPS = kRleThreads / 32;
     __shared__ u32 tile_s;
     __shared__ u64 prefix_s;
-    __shared__ u32 scan_s[kRleThreads / 32 + 1];
+    __shared__ u32 warp_tot[WARPS];
     if (threadIdx.x == 0) tile_s = atomicAdd(ticket, 1u);
     __syncthreads();
     const u32 tile = tile_s;
-    const u64 base = (u64)tile * (kRleThreads * kRleItems) + (u64)threadIdx.x * kRleItems;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 wbase = (u64)tile * (kRleThreads * kRleItems) + (u64)warp * 32 * kRleItems;
     u64 c[kRleItems];
-    u32 cnt = 0;
+    u32 ballots[kRleItems];
+    u32 wcount = 0;
 #pragma unroll
     for (int i = 0; i < kRleItems; ++i) {
-        const u64 idx = base + i;
-        c[i] = idx < m ? counts[idx] : 0;
-        if (idx < m && c[i] >= min_count) ++cnt;
+        const u64 idx = wbase + (u64)i * 32 + lane;
+        c[i] = 0;
+        if (idx < m) c[i] = counts ? counts[idx] : (pos[idx + 1] - pos[idx]);
+        ballots[i] = __ballot_sync(0xffffffffu, idx < m && c[i] >= min_count);
+        wcount += __popc(ballots[i]);
     }
-    u32 tile_total;
-    u32 ex = block_exclusive_scan<u32, kRleThreads>(cnt, &tile_total, scan_s);
-    if (threadIdx.x == 0) {
-        u64 p = lookback_exclusive<u64>(lookback, 1u, tile, 0u, (u64)tile_total);
-        prefix_s = p;
-        if ((u64)(tile + 1) * (kRleThreads * kRleItems) >= m) *total_out = p + tile_total;
+    if (lane == 0) warp_tot[warp] = wcount;
+    __syncthreads();
+    if (warp == 0) {
+        u32 mine = lane < WARPS ? warp_tot[lane] : 0u, inc = mine;
+#pragma unroll
+        for (int o = 1; o < WARPS; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        const u32 run = __shfl_sync(0xffffffffu, inc, WARPS - 1);
+        if (lane < WARPS) warp_tot[lane] = inc - mine;
+        const u64 p = lookback_exclusive_warp<u64>(lookback, tile, (u64)run);
+        if (lane == 0) {
+            prefix_s = p;
+            if ((u64)(tile + 1) * (kRleThreads * kRleItems) >= m) *total_out = p + run;
+        }
     }
     __syncthreads();
-    u64 j = prefix_s + ex;
+    u64 j = prefix_s + warp_tot[warp];
+    const u32 lt = (1u << lane) - 1;
 #pragma unroll
     for (int i = 0; i < kRleItems; ++i) {
-        const u64 idx = base + i;
-        if (idx < m && c[i] >= min_count) { out_keys[j] = keys[idx]; out_counts[j] = c[i]; ++j; }
+        if ((ballots[i] >> lane) & 1u) {
+            const u64 o = j + __popc(ballots[i] & lt);
+            out_keys[o] = keys[wbase + (u64)i * 32 + lane];
+            out_counts[o] = c[i];
+        }
+        j += __popc(ballots[i]);
     }
 }
 
-void sort_filter(int key_bytes, const void* keys, const u64* counts, u64 m, u64 min_count, void* out_keys, u64* out_counts,
+void sort_filter(int key_bytes, const void* keys, const u64* counts, const u64* pos, u64 m, u64 min_count, void* out_keys, u64* out_counts,
                  void* lookback, u64* total_dev, cudaStream_t s, u64* launches) {
     if (!m) { GSB_CUDA_TRY(cudaMemsetAsync(total_dev, 0, 8, s)); return; }
     const u64 lb = rle_lookback_bytes(m);
     GSB_CUDA_TRY(cudaMemsetAsync(lookback, 0, lb, s));
     u32* ticket = (u32*)((char*)lookback + lb - 256);
     const u64 tiles = (m + kRleThreads * kRleItems - 1) / (kRleThreads * kRleItems);
-    if (key_bytes == 8) filter_kernel<u64><<<(unsigned)tiles, kRleThreads, 0, s>>>((const u64*)keys, counts, m, min_count, (u64*)out_keys, out_counts, (u64*)lookback, ticket, total_dev);
-    else filter_kernel<Key128><<<(unsigned)tiles, kRleThreads, 0, s>>>((const Key128*)keys, counts, m, min_count, (Key128*)out_keys, out_counts, (u64*)lookback, ticket, total_dev);
+    if (key_bytes == 8) filter_kernel<u64><<<(unsigned)tiles, kRleThreads, 0, s>>>((const u64*)keys, counts, pos, m, min_count, (u64*)out_keys, out_counts, (u64*)lookback, ticket, total_dev);
+    else filter_kernel<Key128><<<(unsigned)tiles, kRleThreads, 0, s>>>((const Key128*)keys, counts, pos, m, min_count, (Key128*)out_keys, out_counts, (u64*)lookback, ticket, total_dev);
     ++*launches;
 }
 
@@ -521,54 +632,47 @@ int sort_keys(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64*
 }
 
 void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* weights, u64 n, u64 min_count,
-                   ReducedRun& out, u64* m_distinct, void* dkeys_scratch) {
+                   ReducedRun& out, u64* m_distinct, void* /*dkeys_scratch*/) {
     cudaStream_t s = ws.stream;
     out.m = 0;
     if (m_distinct) *m_distinct = 0;
     if (n == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return; }
-    DevBuf<u8> dkeys_own;
-    if (!dkeys_scratch) dkeys_own.reset(&ws, (size_t)n * key_bytes);
-    u8* const dkeys_p = dkeys_scratch ? (u8*)dkeys_scratch : dkeys_own.p;
-    DevBuf<u64> pos(&ws, (size_t)n + 1);
-    DevBuf<u64> total(&ws, 1);
-    u64 m = 0;
-    {
-        DevBuf<u8> lookback(&ws, rle_lookback_bytes(n));
-        sort_rle(key_bytes, sorted, n, dkeys_p, pos.p, lookback.p, total.p, s, &ws.launches);
-        GSB_CUDA_TRY(cudaMemcpyAsync(&m, total.p, 8, cudaMemcpyDeviceToHost, s));
-        ws.sync();
-    }
-    if (m_distinct) *m_distinct = m;
-    DevBuf<u64> counts(&ws, (size_t)m);
+    if (min_count < 1) min_count = 1;
+    // With weights (merging reduced runs) the filter applies to summed weights, not run lengths: emit
+    // every run here and let the caller filter.
+    const u64 local_min = weights ? 1 : min_count;
+    const u64 tiles = rle_tiles(n);
+    DevBuf<u32> tile_kept(&ws, tiles);
+    DevBuf<u64> tile_off(&ws, tiles), tmp(&ws, scan_tmp_elems(tiles)), scalars(&ws, 2);
+    GSB_CUDA_TRY(cudaMemsetAsync(scalars.p, 0, 16, s));
+    sort_rle_count(key_bytes, sorted, n, local_min, tile_kept.p, scalars.p, s, &ws.launches);
+    exclusive_scan<u32, u64>(tile_kept.p, tile_off.p, tiles, 0ull, scalars.p + 1, tmp.p, s, &ws.launches);
+    u64 host[2] = {0, 0};
+    GSB_CUDA_TRY(cudaMemcpyAsync(host, scalars.p, 16, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    const u64 heads = host[0], kept = host[1];
+    if (m_distinct) *m_distinct = heads;
+    DevBuf<u64> csum;
     if (weights) {
-        DevBuf<u64> csum(&ws, (size_t)n + 1);
-        DevBuf<u64> tmp(&ws, sort_scan_tmp_elems(n));
-        sort_scan_weights(weights, csum.p, n, tmp.p, s, &ws.launches);
-        sort_counts_from_pos(pos.p, csum.p, m, counts.p, s, &ws.launches);
-        ws.sync();
-    } else {
-        sort_counts_from_pos(pos.p, nullptr, m, counts.p, s, &ws.launches);
+        csum.reset(&ws, (size_t)n + 1);
+        DevBuf<u64> tmp2(&ws, sort_scan_tmp_elems(n));
+        sort_scan_weights(weights, csum.p, n, tmp2.p, s, &ws.launches);
     }
-    pos.free();
-    if (min_count > 1) {
-        DevBuf<u8> fkeys(&ws, (size_t)m * key_bytes);
-        DevBuf<u64> fcounts(&ws, (size_t)m);
-        DevBuf<u8> lookback(&ws, rle_lookback_bytes(m));
-        sort_filter(key_bytes, dkeys_p, counts.p, m, min_count, fkeys.p, fcounts.p, lookback.p, total.p, s, &ws.launches);
-        u64 kept = 0;
-        GSB_CUDA_TRY(cudaMemcpyAsync(&kept, total.p, 8, cudaMemcpyDeviceToHost, s));
+    out.keys.reset(&ws, (size_t)kept * key_bytes);
+    out.counts.reset(&ws, (size_t)kept);
+    sort_rle_emit(key_bytes, sorted, weights ? csum.p : nullptr, n, local_min, tile_off.p, out.keys.p, out.counts.p, s, &ws.launches);
+    out.m = kept;
+    if (weights && min_count > 1 && kept) {
+        DevBuf<u8> fkeys(&ws, (size_t)kept * key_bytes);
+        DevBuf<u64> fcounts(&ws, (size_t)kept), total(&ws, 1);
+        DevBuf<u8> lookback(&ws, rle_lookback_bytes(kept));
+        sort_filter(key_bytes, out.keys.p, out.counts.p, nullptr, kept, min_count, fkeys.p, fcounts.p, lookback.p, total.p, s, &ws.launches);
+        u64 k2 = 0;
+        GSB_CUDA_TRY(cudaMemcpyAsync(&k2, total.p, 8, cudaMemcpyDeviceToHost, s));
         ws.sync();
-        out.keys = std::move(fkeys);
-        out.counts = std::move(fcounts);
-        out.m = kept;
-    } else {
-        DevBuf<u8> fkeys(&ws, (size_t)m * key_bytes);
-        GSB_CUDA_TRY(cudaMemcpyAsync(fkeys.p, dkeys_p, (size_t)m * key_bytes, cudaMemcpyDeviceToDevice, s));
-        out.keys = std::move(fkeys);
-        out.counts = std::move(counts);
-        out.m = m;
-        ws.sync();
+        out.keys = std::move(fkeys); out.counts = std::move(fcounts); out.m = k2;
     }
+    ws.sync();
 }
 
 }  // namespace gsb
