@@ -266,7 +266,7 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     const u64 n_words = (n_sym_total + 31) / 32;
     DevBuf<u64> codes(&ws, n_words);
     DevBuf<u32> valid(&ws, n_words);
-    ingest_pack(text, line_start.p, kind.p, sym_off.p, n_lines, c->carry.p, n_carry, n_sym_total, codes.p, valid.p, n_words, s, &ws.launches);
+    ingest_pack(text, n, line_start.p, kind.p, sym_off.p, n_lines, c->carry.p, n_carry, n_sym_total, codes.p, valid.p, n_words, s, &ws.launches);
     line_start.free(); nsym.free(); sym_off.free(); kind.free();
     c->stats.n_symbols += block_syms;
 

@@ -234,7 +234,33 @@ __device__ __forceinline__ u32 base_code(u8 c) {
     }
 }
 
-__global__ void __launch_bounds__(256) pack_symbols_kernel(const u8* __restrict__ text, const u32* __restrict__ line_start,
+// 32 sequence bytes starting at text + off (any alignment) -> packed codes + valid bits, four bytes per
+// step with SIMD-in-a-word arithmetic: upper-case, code = t ^ (t >> 1) with t = (c >> 1) & 3
+// (A 0, C 1, G 2, T 3), valid = byte is one of A C G T; a multiply gathers the four 2-bit codes
+// (or the four valid bits) of a word into one byte (nibble).
+__device__ __forceinline__ void pack32_fast(const u8* __restrict__ text, u64 off, u64& cw, u32& vw) {
+    const u32* base = reinterpret_cast<const u32*>(text + (off & ~3ull));
+    const u32 sh = (u32)(off & 3) * 8;
+    u32 w[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = base[i];
+    cw = 0; vw = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const u32 x = __funnelshift_r(w[i], w[i + 1], sh);      // bytes off+4i .. off+4i+3, first byte lowest
+        const u32 u = x & 0xDFDFDFDFu;
+        const u32 t = (u >> 1) & 0x03030303u;
+        const u32 c = t ^ ((t >> 1) & 0x01010101u);
+        const u32 ok = (__vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u)) & 0x01010101u;
+        const u32 cm = c & (ok * 3u);                           // invalid symbols carry code 0
+        const u32 c8 = (cm * 0x40100401u) >> 24;                // c0<<6 | c1<<4 | c2<<2 | c3
+        const u32 v4 = ((ok * 0x08040201u) >> 24) & 0xFu;       // v0<<3 | v1<<2 | v2<<1 | v3
+        cw |= (u64)c8 << (56 - 8 * i);
+        vw |= v4 << (28 - 4 * i);
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_symbols_kernel(const u8* __restrict__ text, u64 text_bytes, const u32* __restrict__ line_start,
                                                            const u8* __restrict__ kind, const u32* __restrict__ sym_off /* n_lines+1 */,
                                                            u32 n_lines, const u8* __restrict__ carry, u32 n_carry, u64 n_sym_total,
                                                            u64* __restrict__ codes, u32* __restrict__ valid, u64 n_words) {
@@ -251,7 +277,37 @@ __global__ void __launch_bounds__(256) pack_symbols_kernel(const u8* __restrict_
         L = (long long)lo - 1;
         line_lo = sym_off[L]; line_hi = sym_off[L + 1]; src = line_start[L]; lk = kind[L];
     };
-#pragma unroll 4
+    // Words made only of this block's symbols: walk the (one to three, typically) line segments that
+    // overlap the word and convert each with the vectorised routine, masked to the segment and shifted
+    // into place.  (A per-symbol loop here cost 105 warp instructions per symbol, ncu.)
+    if (s0 >= first_block_sym && s0 + 32 <= n_sym_total) {
+        u32 x = (u32)(s0 - first_block_sym);
+        seek(x);
+        int j = 0;
+        while (j < 32) {
+            while (x >= line_hi) { ++L; line_lo = line_hi; line_hi = sym_off[L + 1]; src = line_start[L]; lk = kind[L]; }
+            const u32 r = x - line_lo;
+            u32 seg = line_hi - x;
+            if (seg > (u32)(32 - j)) seg = 32 - j;
+            if (lk == LK_SEP || (lk == LK_LINE && r == 0)) { ++j; ++x; continue; }   // one invalid symbol
+            const u64 off = (u64)src + (lk == LK_LINE ? r - 1 : r);
+            u64 c = 0; u32 v = 0;
+            if (off + 36 <= text_bytes) {
+                pack32_fast(text, off, c, v);
+            } else {
+                for (u32 i = 0; i < seg; ++i) {
+                    const u32 code = base_code(text[off + i]);
+                    if (code < 4) { c |= (u64)code << (2 * (31 - i)); v |= 1u << (31 - i); }
+                }
+            }
+            if (seg < 32) { c &= ~0ull << (2 * (32 - seg)); v &= ~0u << (32 - seg); }
+            cw |= c >> (2 * j); vw |= v >> j;
+            j += seg; x += seg;
+        }
+        codes[w] = cw; valid[w] = vw;
+        return;
+    }
+    // the few words that touch the pad, the carried symbols or the end of the stream: symbol by symbol
     for (int j = 0; j < 32; ++j) {
         const u64 s = s0 + j;
         u32 code = 4;
@@ -260,13 +316,10 @@ __global__ void __launch_bounds__(256) pack_symbols_kernel(const u8* __restrict_
         else {
             const u32 x = (u32)(s - first_block_sym);
             if (L < 0) seek(x);
-            while (x >= line_hi) {                             // advance over (possibly empty) lines
-                ++L; line_lo = line_hi; line_hi = sym_off[L + 1]; src = line_start[L]; lk = kind[L];
-            }
+            while (x >= line_hi) { ++L; line_lo = line_hi; line_hi = sym_off[L + 1]; src = line_start[L]; lk = kind[L]; }
             const u32 r = x - line_lo;
             if (lk == LK_SEQ) code = base_code(text[src + r]);
             else if (lk == LK_LINE) code = r == 0 ? 4 : base_code(text[src + r - 1]);
-            else code = 4;                                     // LK_SEP
         }
         if (code < 4) { cw |= (u64)code << (2 * (31 - j)); vw |= 1u << (31 - j); }
     }
@@ -342,13 +395,17 @@ __device__ __forceinline__ u32 revcomp_byte(u32 v) {
 // SYM: graph mode with window % 4 == 0 -- the digit histograms of the reverse complements are a
 // permutation of those of the forward keys, so only the forward keys are histogrammed (half the
 // shared-memory atomics, which bound this kernel) and the mirror image is added at flush time.
-template <typename K, int MODE, bool SYM>
+static const int kExItems = 4;                                  // stream positions per thread per iteration
+
+// PASSES > 0 unrolls the histogram update (7 = k 25, 8 = k 31, 14 = k 55); 0 = run-time count.
+template <typename K, int MODE, bool SYM, int PASSES>
 __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restrict__ codes, const u32* __restrict__ valid,
-                                                             u64 p_begin, u64 p_end, int w, int passes,
+                                                             u64 p_begin, u64 p_end, int w, int passes_rt,
                                                              K* __restrict__ out, u64* __restrict__ cursor, u64 capacity,
                                                              u64* __restrict__ digit_hist /* [passes][256] */, IngestStatus* st) {
     typedef KeyOps<K> KO;
     typedef WindowOps<K> WO;
+    const int passes = PASSES ? PASSES : passes_rt;
     extern __shared__ u32 hist_s[];                            // [passes][256]
     __shared__ u32 warp_cnt[kExThreads / 32];
     __shared__ u64 base_s;
@@ -357,29 +414,37 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 wmask = w >= 64 ? ~0ull : ((1ull << w) - 1);
     const int per = MODE == GSB_KIND_GRAPH ? 2 : 1;
+    const u32 lt = (1u << lane) - 1;
+    constexpr u64 kSpan = (u64)kExThreads * kExItems;
 
-    for (u64 tile = p_begin + (u64)blockIdx.x * kExThreads; tile < p_end; tile += (u64)gridDim.x * kExThreads) {
-        const u64 p = tile + threadIdx.x;
-        bool ok = false;
-        K x = KO::make(0, 0), y = KO::make(0, 0);
-        if (p < p_end) {
-            const u64 b = p >> 5; const int j = (int)(p & 31);
-            const int vs = 31 - j;
-            u64 v = ((u64)valid[b] >> vs) | ((u64)valid[b - 1] << (32 - vs));
-            if (vs) v |= (u64)valid[b - 2] << (64 - vs);
-            ok = (v & wmask) == wmask;
-            if (ok) {
-                x = WO::load(codes, b, 2 * vs, w);
-                if (MODE == GSB_KIND_GRAPH) y = WO::rc(x, w);
-                else {                                         // position_type::normalize, src/RankSelect.hh:126-140
-                    K r = WO::rc(x, w);
-                    u64 h0 = WO::hash(x), h1 = WO::hash(r);
-                    if (h0 > h1 || (h0 == h1 && KO::lt(r, x))) x = r;
+    for (u64 tile = p_begin + (u64)blockIdx.x * kSpan; tile < p_end; tile += (u64)gridDim.x * kSpan) {
+        K x[kExItems];
+        u32 ballot[kExItems];
+        u32 wtot = 0;
+#pragma unroll
+        for (int it = 0; it < kExItems; ++it) {
+            const u64 p = tile + (u64)it * kExThreads + threadIdx.x;
+            bool ok = false;
+            x[it] = KO::make(0, 0);
+            if (p < p_end) {
+                const u64 b = p >> 5; const int j = (int)(p & 31);
+                const int vs = 31 - j;
+                u64 v = ((u64)valid[b] >> vs) | ((u64)valid[b - 1] << (32 - vs));
+                if (vs) v |= (u64)valid[b - 2] << (64 - vs);
+                ok = (v & wmask) == wmask;
+                if (ok) {
+                    x[it] = WO::load(codes, b, 2 * vs, w);
+                    if (MODE != GSB_KIND_GRAPH) {               // position_type::normalize, src/RankSelect.hh:126-140
+                        const K r = WO::rc(x[it], w);
+                        const u64 h0 = WO::hash(x[it]), h1 = WO::hash(r);
+                        if (h0 > h1 || (h0 == h1 && KO::lt(r, x[it]))) x[it] = r;
+                    }
                 }
             }
+            ballot[it] = __ballot_sync(0xffffffffu, ok);
+            wtot += __popc(ballot[it]);
         }
-        const u32 ballot = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) warp_cnt[warp] = __popc(ballot);
+        if (lane == 0) warp_cnt[warp] = wtot;
         __syncthreads();
         if (threadIdx.x == 0) {
             u32 tot = 0;
@@ -388,18 +453,34 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
             base_s = tot ? atomicAdd(cursor, (u64)tot * per) : 0;
         }
         __syncthreads();
-        if (ok) {
-            const u64 idx = base_s + (u64)(warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1))) * per;
-            if (idx + per <= capacity) {
-                out[idx] = x;
-                if (MODE == GSB_KIND_GRAPH) out[idx + 1] = y;
-            } else {
-                st->error = GSB_PE_KEY_OVERFLOW;
+        u32 slot = warp_cnt[warp];
+#pragma unroll
+        for (int it = 0; it < kExItems; ++it) {
+            if ((ballot[it] >> lane) & 1u) {
+                const u64 idx = base_s + (u64)(slot + __popc(ballot[it] & lt)) * per;
+                if (idx + per <= capacity) {
+                    out[idx] = x[it];
+                    if (MODE == GSB_KIND_GRAPH) out[idx + 1] = WO::rc(x[it], w);
+                } else {
+                    st->error = GSB_PE_KEY_OVERFLOW;
+                }
+                if (PASSES) {
+#pragma unroll
+                    for (int d = 0; d < (PASSES ? PASSES : 1); ++d) atomicAdd(&hist_s[d * 256 + KO::digit(x[it], 8 * d)], 1u);
+                    if (MODE == GSB_KIND_GRAPH && !SYM) {
+                        const K y = WO::rc(x[it], w);
+#pragma unroll
+                        for (int d = 0; d < (PASSES ? PASSES : 1); ++d) atomicAdd(&hist_s[d * 256 + KO::digit(y, 8 * d)], 1u);
+                    }
+                } else {
+                    for (int d = 0; d < passes; ++d) atomicAdd(&hist_s[d * 256 + KO::digit(x[it], 8 * d)], 1u);
+                    if (MODE == GSB_KIND_GRAPH && !SYM) {
+                        const K y = WO::rc(x[it], w);
+                        for (int d = 0; d < passes; ++d) atomicAdd(&hist_s[d * 256 + KO::digit(y, 8 * d)], 1u);
+                    }
+                }
             }
-            for (int d = 0; d < passes; ++d) {
-                atomicAdd(&hist_s[d * 256 + KO::digit(x, 8 * d)], 1u);
-                if (MODE == GSB_KIND_GRAPH && !SYM) atomicAdd(&hist_s[d * 256 + KO::digit(y, 8 * d)], 1u);
-            }
+            slot += __popc(ballot[it]);
         }
         __syncthreads();
     }
@@ -475,10 +556,10 @@ void ingest_symbol_offsets(const u32* nsym, u32* sym_off, u32 n_lines, u32* tota
     exclusive_scan<u32, u32>(nsym, sym_off, n_lines, 0u, total_dev, tmp, s, launches);
 }
 
-void ingest_pack(const u8* text, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
+void ingest_pack(const u8* text, u64 text_bytes, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
                  const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, cudaStream_t s, u64* launches) {
     if (!n_words) return;
-    pack_symbols_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, s>>>(text, line_start, kind, sym_off, n_lines, carry, n_carry,
+    pack_symbols_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, s>>>(text, text_bytes, line_start, kind, sym_off, n_lines, carry, n_carry,
                                                                         n_sym_total, codes, valid, n_words);
     ++*launches;
 }
@@ -489,18 +570,30 @@ void ingest_save_carry(const u64* codes, const u32* valid, u64 n_sym_total, u32 
     ++*launches;
 }
 
-template <typename K>
-static void launch_extract(int kind, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
-                           K* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s) {
-    u64 tiles = (p_end - p_begin + kExThreads - 1) / kExThreads;
+template <typename K, int PASSES>
+static void launch_extract_p(int kind, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
+                             K* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s) {
+    const u64 span = (u64)kExThreads * kExItems;
+    u64 tiles = (p_end - p_begin + span - 1) / span;
     int grid = (int)(tiles < (u64)sm_count * 8 ? tiles : (u64)sm_count * 8);
     size_t smem = (size_t)passes * 256 * sizeof(u32);
     if (kind == GSB_KIND_GRAPH && (w % 4) == 0)
-        extract_kernel<K, GSB_KIND_GRAPH, true><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+        extract_kernel<K, GSB_KIND_GRAPH, true, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
     else if (kind == GSB_KIND_GRAPH)
-        extract_kernel<K, GSB_KIND_GRAPH, false><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+        extract_kernel<K, GSB_KIND_GRAPH, false, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
     else
-        extract_kernel<K, GSB_KIND_KMERSET, false><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+        extract_kernel<K, GSB_KIND_KMERSET, false, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+}
+
+template <typename K>
+static void launch_extract(int kind, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
+                           K* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s) {
+    switch (passes) {
+        case 7: launch_extract_p<K, 7>(kind, codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st, sm_count, s); break;
+        case 8: launch_extract_p<K, 8>(kind, codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st, sm_count, s); break;
+        case 14: launch_extract_p<K, 14>(kind, codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st, sm_count, s); break;
+        default: launch_extract_p<K, 0>(kind, codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st, sm_count, s); break;
+    }
 }
 
 void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,

@@ -65,7 +65,7 @@ void ingest_fill_line_starts(const u8* text, u64 n, const u32* tile_offsets, u32
 void ingest_classify(const u8* text, const u32* line_start, u32 n_lines, int format, int file_start, u64 line_base,
                      u8* kind, u32* nsym, IngestStatus* st_dev, cudaStream_t s, u64* launches);
 void ingest_symbol_offsets(const u32* nsym, u32* sym_off, u32 n_lines, u32* total_dev, u32* tmp, cudaStream_t s, u64* launches);
-void ingest_pack(const u8* text, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
+void ingest_pack(const u8* text, u64 text_bytes, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
                  const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, cudaStream_t s, u64* launches);
 void ingest_save_carry(const u64* codes, const u32* valid, u64 n_sym_total, u32 want, u8* carry_out, cudaStream_t s, u64* launches);
 void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
