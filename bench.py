@@ -99,9 +99,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_reads(wl, rank, out=None):
+def make_reads(wl, rank, world, out=None):
+    """Weak scaling: per-GPU work is fixed, so the genome grows with the number of GPUs at constant
+    coverage (N x 5 Mbp at 50x for c2, like BASELINE configs[4]'s large genome spread over 8 GPUs);
+    every rank draws its reads from the whole genome."""
     import simreads_py as S
-    g = S.genome(wl["genome"], 42)
+    g = S.genome(wl["genome"] * world, 42)
     return S.reads_fastq(g, wl["read_len"], wl["n_reads"], err=wl["err"], seed=43 + rank, out=out)
 
 
@@ -210,7 +213,7 @@ def main():
     import simreads_py as S
     nbytes = S.fastq_bytes(wl["n_reads"], wl["read_len"])
     host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    text = make_reads(wl, rank, out=host.numpy())
+    text = make_reads(wl, rank, world, out=host.numpy())
     assert text.size == nbytes
     dev = host.to(f"cuda:{local_rank}", non_blocking=False)
     torch.cuda.synchronize()
@@ -334,7 +337,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if key_bytes == 8 else "u128",
         "data": "synthetic",
         "config": {"workload": wl["desc"], "k": wl["k"], "min_count": wl["min_count"], "n_reads_per_gpu": wl["n_reads"],
-                   "read_len": wl["read_len"], "genome": wl["genome"], "err": wl["err"], "seeds": [42, 43],
+                   "read_len": wl["read_len"], "genome": wl["genome"] * world, "err": wl["err"], "seeds": [42, 43],
                    "fastq_bytes_per_gpu": int(nbytes), "n_instances": int(n_inst_total), "n_distinct": int(m_distinct),
                    "n_edges_kept": int(m_kept), "parallelism": f"range-partition x{world}" if world > 1 else "single GPU",
                    "l2_note": "inputs (FASTQ text and key buffers) are larger than the 126 MB L2; no flush needed"},
@@ -352,6 +355,8 @@ def main():
         "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
         "exchange": None if world == 1 else {
             "what": "one all-to-all of raw instance keys routed to the rank owning their key range (rank 0's view)",
+            "path": "fused partition+transfer kernel storing into peer windows over NVLink (CUDA IPC)" if b.stats().exchange_peer_memory
+                    else "staged partition + grouped ncclSend/ncclRecv",
             "bytes_sent_per_gpu_per_step": a2a_bytes / args.steps, "all_to_all_ms": a2a_ms / args.steps,
             "gb_per_s_per_gpu": (a2a_bytes / max(a2a_ms, 1e-9)) / 1e6,
             "frac_of_nvlink_770": (a2a_bytes / max(a2a_ms, 1e-9)) / 1e6 / 770.0},

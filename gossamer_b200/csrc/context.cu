@@ -91,6 +91,7 @@ struct gsb_ctx {
     Exchange* comm = nullptr;
     bool exchanged_instances = false;
     u64 instances_before_exchange = 0;
+    u8* batch_src = nullptr;       // where the current batch's instances are when not in `keys` (receive window)
 
     void log(int sev, const std::string& m) { if (cfg.log) cfg.log(cfg.log_user, sev, m.c_str()); }
 };
@@ -176,9 +177,11 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     const int kb = c->key_bytes;
     ensure_alt(c, c->n_keys);
     DevBuf<u8>& alt = c->alt;
+    u8* const src = c->batch_src ? c->batch_src : c->keys.p;
+    c->batch_src = nullptr;
     int passes_run = 0;
     c->timer.start();
-    int where = sort_keys(ws, kb, c->key_bits, c->keys.p, alt.p, nullptr, nullptr, c->n_keys, c->hist.p, &passes_run, &c->stats.ms_sort_sweeps);
+    int where = sort_keys(ws, kb, c->key_bits, src, alt.p, nullptr, nullptr, c->n_keys, c->hist.p, &passes_run, &c->stats.ms_sort_sweeps);
     c->timer.stop(c->stats.ms_sort);
     c->stats.sort_passes += passes_run;
     c->stats.sort_passes_model += c->passes;
@@ -186,7 +189,7 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     ReducedRun run; u64 distinct = 0;
     const u64 min_count = (final_and_only && c->cfg.kind == GSB_KIND_GRAPH && (!c->comm || c->exchanged_instances)) ? std::max<u64>(1, c->cfg.min_count) : 1;
     c->timer.start();
-    reduce_sorted(ws, kb, where ? alt.p : c->keys.p, nullptr, c->n_keys, min_count, run, &distinct, where ? c->keys.p : alt.p);
+    reduce_sorted(ws, kb, where ? alt.p : src, nullptr, c->n_keys, min_count, run, &distinct, nullptr);
     c->timer.stop(c->stats.ms_reduce);
     c->counts.n_instances += c->n_keys;
     if (final_and_only) c->counts.n_distinct = distinct;
@@ -448,14 +451,15 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                 u64 n_recv = 0;
                 ExchangeTiming et;
                 ensure_alt(c, c->n_keys);
-                exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &n_recv, &et);
+                u8* recv_ptr = nullptr;
+                exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &recv_ptr, &n_recv, &et);
                 c->stats.ms_all_to_all += et.ms_all_to_all;
                 c->stats.exchange_bytes_sent += et.bytes_sent_remote;
-                std::swap(c->keys, c->third);                    // the received instances become the batch to sort
-                std::swap(c->keys_cap, c->third_cap);
+                c->stats.exchange_peer_memory = et.used_peer_memory ? 1 : 0;
+                c->batch_src = recv_ptr;                           // the received instances are the batch to sort
                 c->n_keys = n_recv;
                 GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), c->ws.stream));
-                sort_digit_hist(c->key_bytes, c->keys.p, c->n_keys, c->passes, c->hist.p, c->ws.sm_count, c->ws.stream, &c->ws.launches);
+                sort_digit_hist(c->key_bytes, recv_ptr, c->n_keys, c->passes, c->hist.p, c->ws.sm_count, c->ws.stream, &c->ws.launches);
                 c->timer.stop(c->stats.ms_exchange);
                 exchanged_instances = true;
                 c->instances_before_exchange = local_instances;

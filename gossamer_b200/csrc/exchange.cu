@@ -14,6 +14,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 
 #include "exchange.h"
 
@@ -113,22 +116,36 @@ __global__ void sample_strided_kernel(const K* __restrict__ keys, u64 n, u32 S, 
 static const int kPartThreads = 256;
 static const int kPartItems = 8;
 
-// pass 1: how many keys go to each destination
+// lanes (among those with ok) whose small value d equals mine, from `bits` ballots
+__device__ __forceinline__ u32 same_dest_lanes(int d, int bits, bool ok) {
+    u32 peers = __ballot_sync(0xffffffffu, ok);
+    for (int b = 0; b < bits; ++b) {
+        const bool bit = (d >> b) & 1;
+        const u32 bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
+// pass 1: how many keys go to each destination (warp-aggregated: one shared atomic per distinct
+// destination per warp instruction -- consecutive instances are not sorted, so a warp typically
+// sees every destination; the match is on a value < 32, done with a short ballot loop over ranks
+// only when there are few ranks, else by per-lane shared atomics)
 template <typename K>
 __global__ void __launch_bounds__(kPartThreads) dest_count_kernel(const K* __restrict__ keys, u64 n, Splitters sp, u64* __restrict__ totals) {
     __shared__ u32 cnt_s[kMaxRanks];
     if (threadIdx.x < kMaxRanks) cnt_s[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    int bits = 0; while ((1 << bits) <= sp.n) ++bits;
     for (u64 base = (u64)blockIdx.x * kPartThreads * kPartItems; base < n; base += (u64)gridDim.x * kPartThreads * kPartItems) {
 #pragma unroll
         for (int i = 0; i < kPartItems; ++i) {
             const u64 idx = base + (u64)i * kPartThreads + threadIdx.x;
-            const int d = idx < n ? dest_of(keys[idx], sp) : -1;
-            for (int r = 0; r <= sp.n; ++r) {
-                const u32 b = __ballot_sync(0xffffffffu, d == r);
-                if (lane == 0 && b) atomicAdd(&cnt_s[r], (u32)__popc(b));
-            }
+            const bool ok = idx < n;
+            const int d = ok ? dest_of(keys[idx], sp) : 0;
+            const u32 peers = same_dest_lanes(d, bits, ok);
+            if (ok && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&cnt_s[d], (u32)__popc(peers));
         }
     }
     __syncthreads();
@@ -136,14 +153,19 @@ __global__ void __launch_bounds__(kPartThreads) dest_count_kernel(const K* __res
 }
 
 // pass 2: scatter into per-destination regions (cursor[r] starts at the region offset); order inside
-// a region is arbitrary -- the receiver sorts
+// a region is arbitrary -- the receiver sorts.  Keys are staged through shared memory grouped by
+// destination so that the global (or peer) writes of one destination are contiguous.
 template <typename K>
 __global__ void __launch_bounds__(kPartThreads) dest_scatter_kernel(const K* __restrict__ keys, u64 n, Splitters sp, u64* __restrict__ cursor,
                                                                    K* __restrict__ out) {
-    __shared__ u32 cnt_s[kMaxRanks];
+    constexpr int TILE = kPartThreads * kPartItems;
+    __shared__ u32 cnt_s[kMaxRanks], start_s[kMaxRanks + 1];
     __shared__ u64 base_s[kMaxRanks];
+    __shared__ K stage[TILE];
+    __shared__ u8 stage_dest[TILE];
     const int lane = threadIdx.x & 31;
-    for (u64 base = (u64)blockIdx.x * kPartThreads * kPartItems; base < n; base += (u64)gridDim.x * kPartThreads * kPartItems) {
+    int bits = 0; while ((1 << bits) <= sp.n) ++bits;
+    for (u64 base = (u64)blockIdx.x * TILE; base < n; base += (u64)gridDim.x * TILE) {
         if (threadIdx.x < kMaxRanks) cnt_s[threadIdx.x] = 0;
         __syncthreads();
         K k[kPartItems]; int d[kPartItems]; u32 slot[kPartItems];
@@ -151,21 +173,85 @@ __global__ void __launch_bounds__(kPartThreads) dest_scatter_kernel(const K* __r
         for (int i = 0; i < kPartItems; ++i) {
             const u64 idx = base + (u64)i * kPartThreads + threadIdx.x;
             d[i] = -1; slot[i] = 0;
-            if (idx < n) { k[i] = keys[idx]; d[i] = dest_of(k[i], sp); }
-            for (int r = 0; r <= sp.n; ++r) {
-                const u32 b = __ballot_sync(0xffffffffu, d[i] == r);
-                u32 w = 0;
-                if (lane == 0 && b) w = atomicAdd(&cnt_s[r], (u32)__popc(b));
-                w = __shfl_sync(0xffffffffu, w, 0);
-                if (d[i] == r) slot[i] = w + __popc(b & ((1u << lane) - 1));
-            }
+            const bool ok = idx < n;
+            if (ok) { k[i] = keys[idx]; d[i] = dest_of(k[i], sp); }
+            const u32 peers = same_dest_lanes(ok ? d[i] : 0, bits, ok);
+            const int leader = __ffs(peers) - 1;
+            u32 before = 0;
+            if (ok && lane == leader) before = atomicAdd(&cnt_s[d[i]], (u32)__popc(peers));
+            before = __shfl_sync(0xffffffffu, before, leader < 0 ? lane : leader);
+            slot[i] = before + __popc(peers & ((1u << lane) - 1));
         }
         __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (int r = 0; r <= sp.n; ++r) { start_s[r] = run; run += cnt_s[r]; }
+            start_s[sp.n + 1] = run;
+        }
         if (threadIdx.x <= sp.n) base_s[threadIdx.x] = cnt_s[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (u64)cnt_s[threadIdx.x]) : 0;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < kPartItems; ++i)
-            if (d[i] >= 0) out[base_s[d[i]] + slot[i]] = k[i];
+            if (d[i] >= 0) { const u32 p = start_s[d[i]] + slot[i]; stage[p] = k[i]; stage_dest[p] = (u8)d[i]; }
+        __syncthreads();
+        const u32 total = start_s[sp.n + 1];
+        for (u32 j = threadIdx.x; j < total; j += kPartThreads) {
+            const int r = stage_dest[j];
+            out[base_s[r] + (j - start_s[r])] = stage[j];
+        }
+        __syncthreads();
+    }
+}
+
+// Fused partition + transfer: the same tile-local grouping by destination, but each destination's
+// run is stored straight into that rank's receive window over NVLink (peer-mapped memory), at the
+// offset reserved for this source rank.  No staging copy, no collective on the data path.
+struct PeerWindows { void* base[kMaxRanks]; };   // window of rank r, already offset to this source's region
+
+template <typename K>
+__global__ void __launch_bounds__(kPartThreads) dest_scatter_p2p_kernel(const K* __restrict__ keys, u64 n, Splitters sp, u64* __restrict__ cursor,
+                                                                       PeerWindows win) {
+    constexpr int TILE = kPartThreads * kPartItems;
+    __shared__ u32 cnt_s[kMaxRanks], start_s[kMaxRanks + 1];
+    __shared__ u64 base_s[kMaxRanks];
+    __shared__ K stage[TILE];
+    __shared__ u8 stage_dest[TILE];
+    const int lane = threadIdx.x & 31;
+    int bits = 0; while ((1 << bits) <= sp.n) ++bits;
+    for (u64 base = (u64)blockIdx.x * TILE; base < n; base += (u64)gridDim.x * TILE) {
+        if (threadIdx.x < kMaxRanks) cnt_s[threadIdx.x] = 0;
+        __syncthreads();
+        K k[kPartItems]; int d[kPartItems]; u32 slot[kPartItems];
+#pragma unroll
+        for (int i = 0; i < kPartItems; ++i) {
+            const u64 idx = base + (u64)i * kPartThreads + threadIdx.x;
+            d[i] = -1; slot[i] = 0;
+            const bool ok = idx < n;
+            if (ok) { k[i] = keys[idx]; d[i] = dest_of(k[i], sp); }
+            const u32 peers = same_dest_lanes(ok ? d[i] : 0, bits, ok);
+            const int leader = __ffs(peers) - 1;
+            u32 before = 0;
+            if (ok && lane == leader) before = atomicAdd(&cnt_s[d[i]], (u32)__popc(peers));
+            before = __shfl_sync(0xffffffffu, before, leader < 0 ? lane : leader);
+            slot[i] = before + __popc(peers & ((1u << lane) - 1));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (int r = 0; r <= sp.n; ++r) { start_s[r] = run; run += cnt_s[r]; }
+            start_s[sp.n + 1] = run;
+        }
+        if (threadIdx.x <= sp.n) base_s[threadIdx.x] = cnt_s[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (u64)cnt_s[threadIdx.x]) : 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kPartItems; ++i)
+            if (d[i] >= 0) { const u32 p = start_s[d[i]] + slot[i]; stage[p] = k[i]; stage_dest[p] = (u8)d[i]; }
+        __syncthreads();
+        const u32 total = start_s[sp.n + 1];
+        for (u32 j = threadIdx.x; j < total; j += kPartThreads) {
+            const int r = stage_dest[j];
+            static_cast<K*>(win.base[r])[base_s[r] + (j - start_s[r])] = stage[j];
+        }
         __syncthreads();
     }
 }
@@ -188,6 +274,14 @@ void plan_splitters(const u64* samples /* (lo,hi) pairs */, u64 n_samples, int n
 struct Exchange {
     ncclComm_t comm = nullptr;
     int n = 1, rank = 0;
+    // Peer-memory receive window (the fused partition + transfer path): a plain cudaMalloc allocation,
+    // exported with CUDA IPC, mapped by every peer; grows only.
+    u8* recv_buf = nullptr;
+    u64 recv_cap_bytes = 0;
+    std::vector<u8*> peer_ptr;                     // [rank] mapped base of that rank's window (own = recv_buf)
+    std::vector<cudaIpcMemHandle_t> peer_handle;   // handle currently mapped for each peer
+    std::vector<char> peer_open;
+    bool p2p_usable = true;                        // cleared if IPC mapping fails: NCCL send/recv is used instead
 };
 
 void exchange_make_id(void* id_out) {
@@ -210,6 +304,9 @@ Exchange* exchange_create(const void* id_bytes, int n_ranks, int rank, Workspace
 
 void exchange_destroy(Exchange* x) {
     if (!x) return;
+    for (size_t r = 0; r < x->peer_ptr.size(); ++r)
+        if ((int)r != x->rank && x->peer_open[r]) cudaIpcCloseMemHandle(x->peer_ptr[r]);
+    if (x->recv_buf) cudaFree(x->recv_buf);
     if (x->comm) nccl().CommDestroy(x->comm);
     delete x;
 }
@@ -299,8 +396,22 @@ void exchange_runs(Exchange* x, Workspace& ws, int key_bytes, int key_bits, Redu
 
 // Range-partition the raw instance keys by sampled splitters and exchange them (one all-to-all):
 // afterwards `recv` holds every instance, from all ranks, whose key lies in this rank's range.
+static double host_now_ms() {
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, u8* parted_buf /* n_keys keys */,
-                        DevBuf<u8>& recv, u64* recv_cap, u64* n_recv, ExchangeTiming* timing) {
+                        DevBuf<u8>& recv, u64* recv_cap, u8** recv_ptr_out, u64* n_recv, ExchangeTiming* timing) {
+    const bool trace = getenv("GSB_TRACE_EXCHANGE") != nullptr;
+    double t_prev = host_now_ms();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        ws.sync();
+        double t = host_now_ms();
+        fprintf(stderr, "[exchange rank %d] %-28s %8.3f ms\n", x->rank, what, t - t_prev);
+        t_prev = t;
+    };
     const int n = x->n;
     cudaStream_t s = ws.stream;
     NcclApi& api = nccl();
@@ -330,6 +441,7 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
         plan_splitters(samples.data(), samples.size() / 2, n, split.data());
         for (int j = 0; j < n - 1; ++j) { sp.lo[j] = split[2 * j]; sp.hi[j] = split[2 * j + 1]; }
     }
+    lap("sample + splitters");
     // local partition: count, offsets, scatter
     DevBuf<u64> totals(&ws, 2 * (size_t)kMaxRanks);
     GSB_CUDA_TRY(cudaMemsetAsync(totals.p, 0, totals.bytes(), s));
@@ -345,13 +457,8 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
     ws.sync();
     for (int r = 0; r < n; ++r) send_off[r + 1] = send_off[r] + send_cnt[r];
     GSB_CUDA_TRY(cudaMemcpyAsync(totals.p + kMaxRanks, send_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    struct { u8* p; } parted{parted_buf};
-    if (n_keys) {
-        if (key_bytes == 8) dest_scatter_kernel<u64><<<grid, kPartThreads, 0, s>>>((const u64*)keys, n_keys, sp, totals.p + kMaxRanks, (u64*)parted.p);
-        else dest_scatter_kernel<Key128><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, n_keys, sp, totals.p + kMaxRanks, (Key128*)parted.p);
-        ++ws.launches;
-    }
-    // counts matrix
+    lap("count per destination");
+    // counts matrix: cnt[src][dst]
     DevBuf<u64> cnt_mine(&ws, n), cnt_all(&ws, (size_t)n * n);
     GSB_CUDA_TRY(cudaMemcpyAsync(cnt_mine.p, send_cnt.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
     check(api.AllGather(cnt_mine.p, cnt_all.p, n, ncclUint64, x->comm, s), "ncclAllGather(counts)");
@@ -361,28 +468,108 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
     std::vector<u64> recv_cnt(n), recv_off(n + 1, 0);
     for (int r = 0; r < n; ++r) { recv_cnt[r] = cnt[(size_t)r * n + x->rank]; recv_off[r + 1] = recv_off[r] + recv_cnt[r]; }
     const u64 total = recv_off[n];
-    if (total > *recv_cap) {                                      // grow-only: steady-state steps allocate nothing
-        recv.free();
-        *recv_cap = total + total / 16 + 1024;
-        recv.reset(&ws, *recv_cap * key_bytes);
-    }
+    u64 sent_remote = 0;
+    for (int r = 0; r < n; ++r) if (r != x->rank) sent_remote += send_cnt[r] * key_bytes;
+
+    lap("counts matrix allgather");
     cudaEvent_t e0, e1;
     GSB_CUDA_TRY(cudaEventCreate(&e0)); GSB_CUDA_TRY(cudaEventCreate(&e1));
-    GSB_CUDA_TRY(cudaEventRecord(e0, s));
-    check(api.GroupStart(), "ncclGroupStart");
-    u64 sent_remote = 0;
-    for (int r = 0; r < n; ++r) {
-        if (send_cnt[r]) check(api.Send(parted.p + send_off[r] * key_bytes, send_cnt[r] * key_bytes, ncclUint8, r, x->comm, s), "ncclSend(instances)");
-        if (recv_cnt[r]) check(api.Recv(recv.p + recv_off[r] * key_bytes, recv_cnt[r] * key_bytes, ncclUint8, r, x->comm, s), "ncclRecv(instances)");
-        if (r != x->rank) sent_remote += send_cnt[r] * key_bytes;
+    bool done = false;
+    if (x->p2p_usable) {
+        // ---- peer-memory path: make sure every rank's window is big enough and mapped everywhere ----
+        if (total * key_bytes > x->recv_cap_bytes) {
+            ws.sync();
+            if (x->recv_buf) GSB_CUDA_TRY(cudaFree(x->recv_buf));
+            x->recv_cap_bytes = (total + total / 8 + 4096) * key_bytes;
+            GSB_CUDA_TRY(cudaMalloc((void**)&x->recv_buf, x->recv_cap_bytes));
+        }
+        lap("window (re)allocation");
+        struct Slot { cudaIpcMemHandle_t h; u64 cap; u64 ok; };
+        Slot mine_h;
+        memset(&mine_h, 0, sizeof(mine_h));
+        mine_h.ok = cudaIpcGetMemHandle(&mine_h.h, x->recv_buf) == cudaSuccess ? 1 : 0;
+        if (!mine_h.ok) cudaGetLastError();
+        mine_h.cap = x->recv_cap_bytes;
+        DevBuf<u8> h_mine(&ws, sizeof(Slot)), h_all(&ws, sizeof(Slot) * n);
+        GSB_CUDA_TRY(cudaMemcpyAsync(h_mine.p, &mine_h, sizeof(Slot), cudaMemcpyHostToDevice, s));
+        check(api.AllGather(h_mine.p, h_all.p, sizeof(Slot), ncclUint8, x->comm, s), "ncclAllGather(ipc handles)");
+        std::vector<Slot> slots(n);
+        GSB_CUDA_TRY(cudaMemcpyAsync(slots.data(), h_all.p, sizeof(Slot) * n, cudaMemcpyDeviceToHost, s));
+        ws.sync();
+        bool all_ok = true;
+        for (int r = 0; r < n; ++r) all_ok = all_ok && slots[r].ok;
+        if (x->peer_ptr.empty()) { x->peer_ptr.assign(n, nullptr); x->peer_handle.resize(n); x->peer_open.assign(n, 0); }
+        u64 local_ok = all_ok ? 1 : 0;
+        if (all_ok) {
+            for (int r = 0; r < n && local_ok; ++r) {
+                if (r == x->rank) { x->peer_ptr[r] = x->recv_buf; continue; }
+                if (x->peer_open[r] && memcmp(&x->peer_handle[r], &slots[r].h, sizeof(cudaIpcMemHandle_t)) == 0) continue;
+                if (x->peer_open[r]) { cudaIpcCloseMemHandle(x->peer_ptr[r]); x->peer_open[r] = 0; }
+                void* p = nullptr;
+                if (cudaIpcOpenMemHandle(&p, slots[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); local_ok = 0; break; }
+                x->peer_ptr[r] = (u8*)p; x->peer_handle[r] = slots[r].h; x->peer_open[r] = 1;
+            }
+        }
+        lap("ipc handles exchange + map");
+        // every rank must take the same path
+        const u64 n_ok = exchange_sum(x, ws, local_ok);
+        lap("agree on path");
+        if (n_ok == (u64)n) {
+            PeerWindows win;
+            memset(&win, 0, sizeof(win));
+            for (int r = 0; r < n; ++r) {
+                u64 before_me = 0;                                  // keys that lower-ranked sources send to r
+                for (int src = 0; src < x->rank; ++src) before_me += cnt[(size_t)src * n + r];
+                win.base[r] = x->peer_ptr[r] + before_me * key_bytes;
+            }
+            GSB_CUDA_TRY(cudaMemsetAsync(totals.p + kMaxRanks, 0, kMaxRanks * 8, s));
+            GSB_CUDA_TRY(cudaEventRecord(e0, s));
+            if (n_keys) {
+                if (key_bytes == 8) dest_scatter_p2p_kernel<u64><<<grid, kPartThreads, 0, s>>>((const u64*)keys, n_keys, sp, totals.p + kMaxRanks, win);
+                else dest_scatter_p2p_kernel<Key128><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, n_keys, sp, totals.p + kMaxRanks, win);
+                ++ws.launches;
+            }
+            // barrier: when this all-reduce completes here, every rank's scatter kernel has finished
+            DevBuf<u64> flag(&ws, 2);
+            GSB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, 16, s));
+            check(api.AllReduce(flag.p, flag.p + 1, 1, ncclUint64, ncclSum, x->comm, s), "ncclAllReduce(barrier)");
+            GSB_CUDA_TRY(cudaEventRecord(e1, s));
+            GSB_CUDA_TRY(cudaEventSynchronize(e1));
+            *recv_ptr_out = x->recv_buf;
+            done = true;
+            lap("fused scatter + barrier");
+        } else {
+            x->p2p_usable = false;                                  // e.g. IPC not permitted in this container
+        }
     }
-    check(api.GroupEnd(), "ncclGroupEnd");
-    GSB_CUDA_TRY(cudaEventRecord(e1, s));
-    GSB_CUDA_TRY(cudaEventSynchronize(e1));
+    if (!done) {
+        // ---- NCCL path: partition into a staging buffer, then grouped send/recv ----
+        GSB_CUDA_TRY(cudaMemcpyAsync(totals.p + kMaxRanks, send_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        if (n_keys) {
+            if (key_bytes == 8) dest_scatter_kernel<u64><<<grid, kPartThreads, 0, s>>>((const u64*)keys, n_keys, sp, totals.p + kMaxRanks, (u64*)parted_buf);
+            else dest_scatter_kernel<Key128><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, n_keys, sp, totals.p + kMaxRanks, (Key128*)parted_buf);
+            ++ws.launches;
+        }
+        if (total > *recv_cap) {                                      // grow-only: steady-state steps allocate nothing
+            recv.free();
+            *recv_cap = total + total / 16 + 1024;
+            recv.reset(&ws, *recv_cap * key_bytes);
+        }
+        GSB_CUDA_TRY(cudaEventRecord(e0, s));
+        check(api.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < n; ++r) {
+            if (send_cnt[r]) check(api.Send(parted_buf + send_off[r] * key_bytes, send_cnt[r] * key_bytes, ncclUint8, r, x->comm, s), "ncclSend(instances)");
+            if (recv_cnt[r]) check(api.Recv(recv.p + recv_off[r] * key_bytes, recv_cnt[r] * key_bytes, ncclUint8, r, x->comm, s), "ncclRecv(instances)");
+        }
+        check(api.GroupEnd(), "ncclGroupEnd");
+        GSB_CUDA_TRY(cudaEventRecord(e1, s));
+        GSB_CUDA_TRY(cudaEventSynchronize(e1));
+        *recv_ptr_out = recv.p;
+    }
     float ms = 0;
     GSB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (timing) { timing->ms_all_to_all += ms; timing->bytes_sent_remote += sent_remote; }
+    if (timing) { timing->ms_all_to_all += ms; timing->bytes_sent_remote += sent_remote; timing->used_peer_memory = done; }
     *n_recv = total;
 }
 

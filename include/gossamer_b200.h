@@ -93,6 +93,7 @@ typedef struct gsb_stats {
     double ms_sort_sweeps;      /* sum of the radix sweep kernels alone (events around each launch) */
     double ms_all_to_all;       /* the NCCL all-to-all alone (inside ms_exchange) */
     uint64_t exchange_bytes_sent; /* bytes this rank sent to OTHER ranks in the all-to-all */
+    uint64_t exchange_peer_memory; /* 1 = fused partition+transfer into peer windows over NVLink, 0 = NCCL send/recv */
     uint64_t bytes_in;          /* raw text bytes pushed */
     uint64_t bytes_out;         /* bytes handed to the sink */
     uint64_t n_symbols;         /* bases + separators in the packed symbol stream */

@@ -118,3 +118,21 @@ def test_config4_scaled_128bit_keys():
     assert c1.n_instances == n_reads * 95 * 2 and st1.sort_key_bytes == 16
     c2, st2, s2 = _build(G.GRAPH, 55, g, 150, n_reads, 0.01, 1_000_000, max_batch_keys=300_000_000)
     assert st2.n_batches >= 3 and s1.digest() == s2.digest()
+
+
+@pytest.mark.skipif(os.environ.get("GSB_BIG_FULL") != "1", reason="set GSB_BIG_FULL=1 as well: 20 GB of reads, several minutes")
+def test_config3_full_size_kmer_set():
+    """BASELINE configs[2] in full: build-kmer-set k=25 on 10 Gbases (100 M x 100 bp reads, 100 Mbp genome, e=1 %):
+    7.6 G instances = 61 GB of keys, more than one batch on a 180 GB GPU."""
+    g = S.genome(100_000_000, 42)
+    n_reads = 100_000_000
+    c, st, s = _build(G.KMERSET, 25, g, 100, n_reads, 0.01, 4_000_000)
+    assert c.n_instances == n_reads * 76 == 7_600_000_000
+    assert st.n_batches >= 2 and 0 < c.n_kept < c.n_instances
+    d = s.digest()
+    assert struct.unpack("<3Q", bytes(s.small["out.header"])) == (2011101701, 25, c.n_kept)
+    ver, D, qD = struct.unpack("<3Q", bytes(s.small["out.kmers.header"])[:24])
+    assert ver == 2012030501 and struct.unpack("<Q", bytes(s.small["out.kmers.header"])[56:64])[0] == c.n_kept
+    low = sum(sz for n, (sz, _) in d.items() if n.startswith("out.kmers.low-bits"))
+    assert low == c.n_kept * qD // 8
+    print("c3 full:", c.n_instances, "instances,", c.n_kept, "k-mers,", st.n_batches, "batches;", st.as_dict())
