@@ -13,21 +13,56 @@ namespace gsb {
 // ------------------------------------------------------------------------------------------
 // Workspace
 // ------------------------------------------------------------------------------------------
+static size_t round_block(size_t bytes) {
+    if (bytes < 512) return 512;
+    if (bytes < (1u << 20)) return (bytes + 511) & ~(size_t)511;
+    return (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);          // 2 MiB granules for large buffers
+}
+
 void* Workspace::alloc(size_t bytes) {
+    const size_t want = round_block(bytes);
     void* p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        throw StatusError{GSB_ENOMEM, std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e)};
+    auto it = free_.lower_bound(want);
+    if (it != free_.end() && it->first <= want + want / 4 + (1u << 20)) {   // close enough in size: reuse
+        p = it->second;
+        free_.erase(it);
+    } else {
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {                                            // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            GSB_CUDA_TRY(cudaStreamSynchronize(stream));
+            trim();
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw StatusError{GSB_ENOMEM, std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e)};
+        }
+        size_of_[p] = want;
+        reserved_bytes += want;
     }
-    live_bytes += bytes;
+    live_bytes += size_of_[p];
     peak_bytes = std::max(peak_bytes, live_bytes);
     return p;
 }
-void Workspace::release(void* p, size_t bytes) {
-    cudaFreeAsync(p, stream);
-    live_bytes -= bytes;
+
+void Workspace::release(void* p, size_t) {
+    auto it = size_of_.find(p);
+    if (it == size_of_.end()) return;
+    live_bytes -= it->second;
+    free_.insert({it->second, p});
 }
+
+void Workspace::trim() {
+    for (auto& kv : free_) { cudaFree(kv.second); reserved_bytes -= kv.first; size_of_.erase(kv.second); }
+    free_.clear();
+}
+
+Workspace::~Workspace() {
+    if (stream) cudaStreamSynchronize(stream);
+    trim();
+}
+
 void Workspace::sync() { GSB_CUDA_TRY(cudaStreamSynchronize(stream)); }
 
 struct PhaseTimer {
@@ -338,10 +373,6 @@ void init_ctx(gsb_ctx* c) {
     if (prop.major < 10) throw StatusError{GSB_ECUDA, std::string("device ") + prop.name + " is not sm_100-class; this build targets B200 only"};
     c->ws.sm_count = prop.multiProcessorCount;
     GSB_CUDA_TRY(cudaStreamCreateWithFlags(&c->ws.stream, cudaStreamNonBlocking));
-    cudaMemPool_t pool;
-    GSB_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, cfg.device));
-    u64 threshold = ~0ull;
-    GSB_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     c->timer.init(c->ws.stream);
     GSB_CUDA_TRY(cudaEventCreate(&c->user_e0));
     GSB_CUDA_TRY(cudaEventCreate(&c->user_e1));
@@ -397,7 +428,7 @@ void gsb_destroy(gsb_ctx* c) {
     if (c->user_e0) cudaEventDestroy(c->user_e0);
     if (c->user_e1) cudaEventDestroy(c->user_e1);
     if (c->pinned) cudaFreeHost(c->pinned);
-    if (c->ws.stream) { cudaStreamSynchronize(c->ws.stream); cudaStreamDestroy(c->ws.stream); }
+    if (c->ws.stream) { cudaStreamSynchronize(c->ws.stream); c->ws.trim(); cudaStreamDestroy(c->ws.stream); c->ws.stream = nullptr; }
     delete c;
 }
 
@@ -661,7 +692,7 @@ struct DebugDevice {
         GSB_CUDA_TRY(cudaMallocHost((void**)&pinned, 16 << 20));
     }
     ~DebugDevice() {
-        if (ws.stream) { cudaStreamSynchronize(ws.stream); cudaStreamDestroy(ws.stream); }
+        if (ws.stream) { cudaStreamSynchronize(ws.stream); ws.trim(); cudaStreamDestroy(ws.stream); ws.stream = nullptr; }
         if (pinned) cudaFreeHost(pinned);
     }
 };

@@ -1,7 +1,9 @@
 // kernels.h -- internal interface between the CUDA modules (ingest / sort / emit) and the
 // context that owns memory and orchestrates them.  Not part of the public ABI.
 #pragma once
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/gossamer_b200.h"
@@ -28,16 +30,28 @@ struct IngestStatus {
     u64 n_reads;
 };
 
-// stream-ordered device allocator with a high-water mark (cudaMallocAsync pool underneath)
+// Device memory for one stream: a caching allocator.  Freed blocks are kept in size-ordered free
+// lists and handed out again to later requests of a similar size, so a steady-state step performs
+// no driver allocation at all.  (The first version used cudaMallocAsync; with the multi-GB buffers
+// of this path the pool kept re-mapping memory and emission time varied between 6 and 44 ms.)
+// Reuse is safe without events because every user of a Workspace enqueues on its single stream.
 struct Workspace {
     cudaStream_t stream = nullptr;
     int device = 0;
     int sm_count = 148;
     u64 launches = 0;
-    u64 live_bytes = 0, peak_bytes = 0;
+    u64 live_bytes = 0, peak_bytes = 0, reserved_bytes = 0;
     void* alloc(size_t bytes);
     void release(void* p, size_t bytes);
     void sync();
+    void trim();                 // give every cached block back to the driver
+    ~Workspace();
+    Workspace() {}
+    Workspace(const Workspace&) = delete;
+    Workspace& operator=(const Workspace&) = delete;
+private:
+    std::multimap<size_t, void*> free_;
+    std::unordered_map<void*, size_t> size_of_;
 };
 
 template <typename T>
