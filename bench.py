@@ -278,6 +278,8 @@ def main():
         a2a_bytes += st.exchange_bytes_sent
         for key in ("ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_merge", "ms_exchange", "ms_emit"):
             phase[key] = phase.get(key, 0.0) + getattr(st, key)
+        if os.environ.get("GSB_BENCH_TRACE"):
+            print(f"[bench rank {rank}] step phases:", {k: round(getattr(st, k), 2) for k in ("ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_exchange", "ms_emit")}, file=sys.stderr, flush=True)
     ms_dev = b.timer_end()
     barrier()
     clocks = sampler.stop()

@@ -7,6 +7,10 @@
 // (src/GossCmdTrimGraph.cc:119).  A cuckoo hash is a random-access structure; on a GPU with
 // 8 TB/s of streaming bandwidth the same multiset is counted faster by sorting the instances
 // and measuring run lengths, and the sorted order is what the succinct writers need anyway.
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+
 #include "kernels.h"
 #include "scan.cuh"
 
@@ -638,6 +642,15 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
     if (m_distinct) *m_distinct = 0;
     if (n == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return; }
     if (min_count < 1) min_count = 1;
+    const bool trace = getenv("GSB_TRACE_REDUCE") != nullptr;
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[reduce] %-22s %8.3f ms (reserved %.2f GB)\n", what, (t.tv_sec - ts0.tv_sec) * 1e3 + (t.tv_nsec - ts0.tv_nsec) * 1e-6, ws.reserved_bytes / 1e9);
+        ts0 = t;
+    };
     // With weights (merging reduced runs) the filter applies to summed weights, not run lengths: emit
     // every run here and let the caller filter.
     const u64 local_min = weights ? 1 : min_count;
@@ -645,7 +658,9 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
     DevBuf<u32> tile_kept(&ws, tiles);
     DevBuf<u64> tile_off(&ws, tiles), tmp(&ws, scan_tmp_elems(tiles)), scalars(&ws, 2);
     GSB_CUDA_TRY(cudaMemsetAsync(scalars.p, 0, 16, s));
+    lap("alloc small");
     sort_rle_count(key_bytes, sorted, n, local_min, tile_kept.p, scalars.p, s, &ws.launches);
+    lap("rle_count");
     exclusive_scan<u32, u64>(tile_kept.p, tile_off.p, tiles, 0ull, scalars.p + 1, tmp.p, s, &ws.launches);
     u64 host[2] = {0, 0};
     GSB_CUDA_TRY(cudaMemcpyAsync(host, scalars.p, 16, cudaMemcpyDeviceToHost, s));
@@ -658,10 +673,13 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
         DevBuf<u64> tmp2(&ws, sort_scan_tmp_elems(n));
         sort_scan_weights(weights, csum.p, n, tmp2.p, s, &ws.launches);
     }
+    lap("scan + readback");
     out.keys.reset(&ws, (size_t)kept * key_bytes);
     out.counts.reset(&ws, (size_t)kept);
+    lap("alloc outputs");
     sort_rle_emit(key_bytes, sorted, weights ? csum.p : nullptr, n, local_min, tile_off.p, out.keys.p, out.counts.p, s, &ws.launches);
     out.m = kept;
+    lap("rle_emit");
     if (weights && min_count > 1 && kept) {
         DevBuf<u8> fkeys(&ws, (size_t)kept * key_bytes);
         DevBuf<u64> fcounts(&ws, (size_t)kept), total(&ws, 1);
