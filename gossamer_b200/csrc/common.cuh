@@ -55,6 +55,18 @@ __device__ __forceinline__ u64 rev_base4(u64 x) {
     return ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);
 }
 
+// Reverse complement of a key of w symbols (BigInteger<2>::reverseComplement, src/BigInteger.hh:204-217:
+// complement, base-4 reverse each word and swap the words, shift right by the unused bits).
+__device__ __forceinline__ u64 key_rc(u64 x, int w) { return rev_base4(~x) >> (64 - 2 * w); }       // 1 <= w <= 32
+__device__ __forceinline__ Key128 key_rc(const Key128& x, int w) {                                  // 32 < w <= 63
+    const u64 hi = rev_base4(~x.lo), lo = rev_base4(~x.hi);
+    const int sh = 128 - 2 * w;                                 // 2 <= sh < 64
+    Key128 r;
+    r.lo = (lo >> sh) | (hi << (64 - sh));
+    r.hi = hi >> sh;
+    return r;
+}
+
 // ---- decoupled look-back over tiles ---------------------------------------------------------
 // state word = status (top 2 bits: 0 empty, 1 tile aggregate, 2 inclusive prefix) | value.
 template <typename T> struct LookbackWord;

@@ -97,6 +97,7 @@ struct gsb_ctx {
     Workspace ws;
     std::string err;
     int key_bytes = 8, key_bits = 0, window = 0, passes = 0;
+    int fold_w = 0;                // graph mode: instances are strand-folded windows of this many symbols (fold.cu); 0 = kmer set
 
     // instance keys of the current batch
     DevBuf<u8> keys;
@@ -199,7 +200,7 @@ void merge_runs(gsb_ctx* c, ReducedRun& into, ReducedRun& other) {
     into.keys.free(); into.counts.free(); other.keys.free(); other.counts.free();
     int where = sort_keys(ws, kb, c->key_bits, ka.p, kbuf.p, va.p, vb.p, n, nullptr, nullptr);
     ReducedRun merged; u64 distinct = 0;
-    reduce_sorted(ws, kb, where ? kbuf.p : ka.p, where ? vb.p : va.p, n, 1, merged, &distinct, nullptr);
+    reduce_sorted(ws, kb, where ? kbuf.p : ka.p, where ? vb.p : va.p, n, 1, merged, &distinct);
     into = std::move(merged);
     other.m = 0;
 }
@@ -227,13 +228,18 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     c->stats.sort_passes += passes_run;
     c->stats.sort_passes_model += c->passes;
     c->stats.n_batches += 1;
-    ReducedRun run; u64 distinct = 0;
-    const u64 min_count = (final_and_only && c->cfg.kind == GSB_KIND_GRAPH && (!c->comm || c->exchanged_instances)) ? std::max<u64>(1, c->cfg.min_count) : 1;
+    ReducedRun run; u64 distinct = 0, n_self_rc = 0;
+    // The only batch of a build (on this rank, after any instance exchange): doubling of the
+    // self-complementary keys and the min-count filter are fused into the run-length reduce.
+    // Otherwise the run stays folded with raw occurrence counts until every batch has been merged.
+    const bool fused_final = final_and_only && (!c->comm || c->exchanged_instances);
+    const u64 min_count = (fused_final && c->cfg.kind == GSB_KIND_GRAPH) ? std::max<u64>(1, c->cfg.min_count) : 1;
     c->timer.start();
-    reduce_sorted(ws, kb, where ? alt.p : src, nullptr, c->n_keys, min_count, run, &distinct, nullptr);
+    reduce_sorted(ws, kb, where ? alt.p : src, nullptr, c->n_keys, min_count, run, &distinct, fused_final ? c->fold_w : 0, &n_self_rc);
     c->timer.stop(c->stats.ms_reduce);
-    c->counts.n_instances += c->n_keys;
-    if (final_and_only) c->counts.n_distinct = distinct;
+    c->counts.n_instances += c->n_keys * (c->fold_w ? 2 : 1);  // the reference counts both strands (src/ReverseComplementAdapter.hh:34-55)
+    c->stats.n_sorted_keys += c->n_keys;
+    if (fused_final) c->counts.n_distinct = c->fold_w ? 2 * distinct - n_self_rc : distinct;
     if (c->have_acc) {
         c->timer.start();
         merge_runs(c, c->acc, run);
@@ -300,8 +306,7 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     if (st.error) throw StatusError{GSB_EPARSE, parse_message(st.error, st.error_line)};
     c->counts.n_reads += st.n_reads;
 
-    const u64 per = c->cfg.kind == GSB_KIND_GRAPH ? 2 : 1;
-    ensure_key_capacity(c, (u64)block_syms * per);     // may sort+reduce the current batch first
+    ensure_key_capacity(c, (u64)block_syms);           // one (folded) key per window at most; may sort+reduce the current batch first
 
     // K2: packed symbol stream = [64 pad][carry][block]
     c->timer.start();
@@ -384,6 +389,7 @@ void init_ctx(gsb_ctx* c) {
     GSB_CUDA_TRY(cudaEventCreate(&c->user_e1));
 
     c->window = cfg.kind == GSB_KIND_GRAPH ? cfg.k + 1 : cfg.k;
+    c->fold_w = cfg.kind == GSB_KIND_GRAPH ? c->window : 0;
     c->key_bits = 2 * c->window;
     c->key_bytes = c->key_bits <= 64 ? 8 : 16;
     c->passes = (c->key_bits + 7) / 8;
@@ -513,7 +519,14 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
             const bool filtered_already = single && (!c->comm || exchanged_instances);
             if (exchanged_instances) c->counts.n_distinct = exchange_sum(c->comm, c->ws, c->counts.n_distinct);
             if (!filtered_already) {
+                // merged batches (and/or exchanged reduced runs): still folded, raw occurrence counts
                 u64 local_distinct = c->acc.m;
+                if (c->fold_w && c->acc.m) {
+                    c->timer.start();
+                    const u64 n_self = fold_double_self_rc(c->ws, c->key_bytes, c->fold_w, c->acc.keys.p, c->acc.counts.p, c->acc.m);
+                    c->timer.stop(c->stats.ms_unfold);
+                    local_distinct = 2 * c->acc.m - n_self;
+                }
                 if (min_count > 1 && c->acc.m) {
                     c->timer.start();
                     DevBuf<u8> fk(&c->ws, c->acc.m * c->key_bytes);
@@ -527,6 +540,18 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                     c->timer.stop(c->stats.ms_reduce);
                 }
                 c->counts.n_distinct = c->comm ? exchange_sum(c->comm, c->ws, local_distinct) : local_distinct;
+            }
+            if (c->fold_w) {
+                // restore both strands: acc := sorted(acc U rc(acc))
+                c->timer.start();
+                unfold_run(c->ws, c->key_bytes, c->key_bits, c->fold_w, c->acc);
+                c->timer.stop(c->stats.ms_unfold);
+                if (c->comm) {
+                    // a rank's reverse complements fall into other ranks' key ranges: partition the full runs again
+                    c->timer.start();
+                    exchange_runs(c->comm, c->ws, c->key_bytes, c->key_bits, c->acc);
+                    c->timer.stop(c->stats.ms_exchange);
+                }
             }
             c->counts.n_kept = c->comm ? exchange_sum(c->comm, c->ws, c->acc.m) : c->acc.m;
             if (c->comm) c->counts.n_instances = exchange_sum(c->comm, c->ws, c->counts.n_instances);

@@ -390,7 +390,7 @@ void exchange_runs(Exchange* x, Workspace& ws, int key_bytes, int key_bits, Redu
     // 5. merge the n sorted runs that arrived: sort by key carrying counts, sum equal keys
     int where = sort_keys(ws, key_bytes, key_bits, rkeys.p, rkeys_alt.p, rcounts.p, rcounts_alt.p, total, nullptr, nullptr);
     ReducedRun merged; u64 distinct = 0;
-    reduce_sorted(ws, key_bytes, where ? rkeys_alt.p : rkeys.p, where ? rcounts_alt.p : rcounts.p, total, 1, merged, &distinct, nullptr);
+    reduce_sorted(ws, key_bytes, where ? rkeys_alt.p : rkeys.p, where ? rcounts_alt.p : rcounts.p, total, 1, merged, &distinct);
     run = std::move(merged);
 }
 

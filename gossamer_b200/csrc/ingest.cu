@@ -357,7 +357,7 @@ template <> struct WindowOps<u64> {
         if (sh) x |= codes[b - 1] << (64 - sh);
         return w >= 32 ? x : (x & ((1ull << (2 * w)) - 1));
     }
-    __device__ static __forceinline__ u64 rc(u64 x, int w) { return rev_base4(~x) >> (64 - 2 * w); }
+    __device__ static __forceinline__ u64 rc(u64 x, int w) { return key_rc(x, w); }
     __device__ static __forceinline__ u64 hash(u64 x) { return fnv16(x, 0); }
 };
 
@@ -371,34 +371,21 @@ template <> struct WindowOps<Key128> {
         if (hb < 64) k.hi &= (1ull << hb) - 1;
         return k;
     }
-    __device__ static __forceinline__ Key128 rc(const Key128& x, int w) {
-        // complement, base-4 reverse each word and swap them, shift right by 128 - 2w (src/BigInteger.hh:204-217)
-        u64 hi = rev_base4(~x.lo), lo = rev_base4(~x.hi);
-        int sh = 128 - 2 * w;                                  // 2 <= sh < 64 for 32 < w <= 63
-        Key128 r;
-        r.lo = (lo >> sh) | (hi << (64 - sh));
-        r.hi = hi >> sh;
-        return r;
-    }
+    __device__ static __forceinline__ Key128 rc(const Key128& x, int w) { return key_rc(x, w); }
     __device__ static __forceinline__ u64 hash(const Key128& x) { return fnv16(x.lo, x.hi); }
 };
 
 static const int kExThreads = 256;
 
-// reverse the four bases of a byte and complement them: digit j of rc(x) = revcomp_byte(digit P-1-j of x)
-// whenever the key is a whole number of bytes (window % 4 == 0)
-__device__ __forceinline__ u32 revcomp_byte(u32 v) {
-    v = ~v & 0xFFu;
-    return ((v & 0x03u) << 6) | ((v & 0x0Cu) << 2) | ((v & 0x30u) >> 2) | ((v & 0xC0u) >> 6);
-}
-
-// SYM: graph mode with window % 4 == 0 -- the digit histograms of the reverse complements are a
-// permutation of those of the forward keys, so only the forward keys are histogrammed (half the
-// shared-memory atomics, which bound this kernel) and the mirror image is added at flush time.
+// Graph mode emits ONE key per window: the smaller of the window and its reverse complement
+// ("strand folding").  The reference pushes x and rc(x) (src/ReverseComplementAdapter.hh:34-55), so
+// in its multiset count(y) == count(rc y) == #windows whose canonical key is min(y, rc y), doubled
+// when y is its own reverse complement.  Counting the folded keys halves every later pass over the
+// instances; fold.cu restores both strands after the run-length reduce.
 static const int kExItems = 4;                                  // stream positions per thread per iteration
 
 // PASSES > 0 unrolls the histogram update (7 = k 25, 8 = k 31, 14 = k 55); 0 = run-time count.
-template <typename K, int MODE, bool SYM, int PASSES>
+template <typename K, int MODE, int PASSES>
 __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restrict__ codes, const u32* __restrict__ valid,
                                                              u64 p_begin, u64 p_end, int w, int passes_rt,
                                                              K* __restrict__ out, u64* __restrict__ cursor, u64 capacity,
@@ -413,7 +400,6 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 wmask = w >= 64 ? ~0ull : ((1ull << w) - 1);
-    const int per = MODE == GSB_KIND_GRAPH ? 2 : 1;
     const u32 lt = (1u << lane) - 1;
     constexpr u64 kSpan = (u64)kExThreads * kExItems;
 
@@ -434,8 +420,10 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
                 ok = (v & wmask) == wmask;
                 if (ok) {
                     x[it] = WO::load(codes, b, 2 * vs, w);
-                    if (MODE != GSB_KIND_GRAPH) {               // position_type::normalize, src/RankSelect.hh:126-140
-                        const K r = WO::rc(x[it], w);
+                    const K r = WO::rc(x[it], w);
+                    if (MODE == GSB_KIND_GRAPH) {               // fold the two strands
+                        if (KO::lt(r, x[it])) x[it] = r;
+                    } else {                                    // position_type::normalize, src/RankSelect.hh:126-140
                         const u64 h0 = WO::hash(x[it]), h1 = WO::hash(r);
                         if (h0 > h1 || (h0 == h1 && KO::lt(r, x[it]))) x[it] = r;
                     }
@@ -450,34 +438,21 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
             u32 tot = 0;
 #pragma unroll
             for (int i = 0; i < kExThreads / 32; ++i) { u32 c = warp_cnt[i]; warp_cnt[i] = tot; tot += c; }
-            base_s = tot ? atomicAdd(cursor, (u64)tot * per) : 0;
+            base_s = tot ? atomicAdd(cursor, (u64)tot) : 0;
         }
         __syncthreads();
         u32 slot = warp_cnt[warp];
 #pragma unroll
         for (int it = 0; it < kExItems; ++it) {
             if ((ballot[it] >> lane) & 1u) {
-                const u64 idx = base_s + (u64)(slot + __popc(ballot[it] & lt)) * per;
-                if (idx + per <= capacity) {
-                    out[idx] = x[it];
-                    if (MODE == GSB_KIND_GRAPH) out[idx + 1] = WO::rc(x[it], w);
-                } else {
-                    st->error = GSB_PE_KEY_OVERFLOW;
-                }
+                const u64 idx = base_s + (u64)(slot + __popc(ballot[it] & lt));
+                if (idx < capacity) out[idx] = x[it];
+                else st->error = GSB_PE_KEY_OVERFLOW;
                 if (PASSES) {
 #pragma unroll
                     for (int d = 0; d < (PASSES ? PASSES : 1); ++d) atomicAdd(&hist_s[d * 256 + KO::digit(x[it], 8 * d)], 1u);
-                    if (MODE == GSB_KIND_GRAPH && !SYM) {
-                        const K y = WO::rc(x[it], w);
-#pragma unroll
-                        for (int d = 0; d < (PASSES ? PASSES : 1); ++d) atomicAdd(&hist_s[d * 256 + KO::digit(y, 8 * d)], 1u);
-                    }
                 } else {
                     for (int d = 0; d < passes; ++d) atomicAdd(&hist_s[d * 256 + KO::digit(x[it], 8 * d)], 1u);
-                    if (MODE == GSB_KIND_GRAPH && !SYM) {
-                        const K y = WO::rc(x[it], w);
-                        for (int d = 0; d < passes; ++d) atomicAdd(&hist_s[d * 256 + KO::digit(y, 8 * d)], 1u);
-                    }
                 }
             }
             slot += __popc(ballot[it]);
@@ -487,10 +462,7 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
     __syncthreads();
     for (int i = threadIdx.x; i < passes * 256; i += kExThreads) {
         u32 c = hist_s[i];
-        if (c) {
-            atomicAdd(&digit_hist[i], (u64)c);
-            if (SYM) atomicAdd(&digit_hist[(passes - 1 - (i >> 8)) * 256 + revcomp_byte(i & 255)], (u64)c);
-        }
+        if (c) atomicAdd(&digit_hist[i], (u64)c);
     }
 }
 
@@ -577,12 +549,10 @@ static void launch_extract_p(int kind, const u64* codes, const u32* valid, u64 p
     u64 tiles = (p_end - p_begin + span - 1) / span;
     int grid = (int)(tiles < (u64)sm_count * 8 ? tiles : (u64)sm_count * 8);
     size_t smem = (size_t)passes * 256 * sizeof(u32);
-    if (kind == GSB_KIND_GRAPH && (w % 4) == 0)
-        extract_kernel<K, GSB_KIND_GRAPH, true, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
-    else if (kind == GSB_KIND_GRAPH)
-        extract_kernel<K, GSB_KIND_GRAPH, false, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+    if (kind == GSB_KIND_GRAPH)
+        extract_kernel<K, GSB_KIND_GRAPH, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
     else
-        extract_kernel<K, GSB_KIND_KMERSET, false, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+        extract_kernel<K, GSB_KIND_KMERSET, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
 }
 
 template <typename K>

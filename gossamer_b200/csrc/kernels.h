@@ -96,8 +96,8 @@ void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vo
                void* lookback, cudaStream_t s, u64* launches, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr);
 u64 rle_lookback_bytes(u64 n);
 u64 rle_tiles(u64 n);
-void sort_rle_count(int key_bytes, const void* keys, u64 n, u64 min_count, u32* tile_kept, u64* total_heads, cudaStream_t s, u64* launches);
-void sort_rle_emit(int key_bytes, const void* keys, const u64* csum, u64 n, u64 min_count, const u64* tile_off, void* out_keys, u64* out_counts,
+void sort_rle_count(int key_bytes, const void* keys, u64 n, u64 min_count, int fold_w, u32* tile_kept, u64* total_heads /* u64[4] */, cudaStream_t s, u64* launches);
+void sort_rle_emit(int key_bytes, const void* keys, const u64* csum, u64 n, u64 min_count, int fold_w, const u64* tile_off, void* out_keys, u64* out_counts,
                    cudaStream_t s, u64* launches);
 void sort_filter(int key_bytes, const void* keys, const u64* counts, const u64* pos, u64 m, u64 min_count, void* out_keys, u64* out_counts,
                  void* lookback, u64* total_dev, cudaStream_t s, u64* launches);
@@ -117,9 +117,22 @@ struct ReducedRun {
     DevBuf<u64> counts;     // m
     u64 m = 0;
 };
-// `dkeys_scratch` (optional) is a buffer of n keys that may be clobbered (the idle sort buffer).
+// fold_w > 0 (only without weights): the keys are strand-folded windows of fold_w symbols -- the counts of
+// self-complementary keys are doubled and the filter applies to the doubled count; *n_self_rc gets the
+// number of distinct self-complementary keys (before the filter).
 void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* weights, u64 n, u64 min_count,
-                   ReducedRun& out, u64* m_distinct, void* dkeys_scratch = nullptr);
+                   ReducedRun& out, u64* m_distinct, int fold_w = 0, u64* n_self_rc = nullptr);
+
+// ---- fold.cu ---------------------------------------------------------------------------------
+// Strand folding (graph mode): instances are counted as min(x, rc x); these restore both strands.
+// merged, still folded run with raw occurrence counts -> doubled counts for self-complementary keys;
+// returns how many of the m keys are self-complementary
+u64 fold_double_self_rc(Workspace& ws, int key_bytes, int w, const void* keys, u64* counts, u64 m);
+// folded, filtered run (final counts) -> the full sorted run: every key y plus rc(y) with the same count
+void unfold_run(Workspace& ws, int key_bytes, int key_bits, int w, ReducedRun& run);
+// two sorted runs with disjoint key sets -> one sorted run (merge path)
+void merge_disjoint_runs(Workspace& ws, int key_bytes, const void* ka, const u64* ca, u64 na, const void* kb, const u64* cb, u64 nb,
+                         void* out_keys, u64* out_counts);
 
 // ---- emit.cu ---------------------------------------------------------------------------------
 struct Emitter {

@@ -366,8 +366,10 @@ static const int kRleItems = 8;
 template <typename K>
 struct RleTile {
     // head / survivor ballots of one warp-striped tile; returns the warp's survivor count
-    __device__ static __forceinline__ u32 scan(const K* __restrict__ keys, u64 n, u64 wbase, int lane, u64 min_count,
-                                               K (&k)[kRleItems], u32 (&kept)[kRleItems], u32 (&headb)[kRleItems], u32& heads) {
+    // fold_w > 0: the keys are strand-folded (w symbols each).  A key that is its own reverse complement
+    // stands for two instances per occurrence, so it needs only ceil(min_count / 2) occurrences to survive.
+    __device__ static __forceinline__ u32 scan(const K* __restrict__ keys, u64 n, u64 wbase, int lane, u64 min_count, int fold_w,
+                                               K (&k)[kRleItems], u32 (&kept)[kRleItems], u32 (&headb)[kRleItems], u32& heads, u32& pals) {
         typedef KeyOps<K> KO;
         K carry = KO::make(0, 0);
         if (wbase > 0 && wbase < n) carry = keys[wbase - 1];
@@ -377,7 +379,7 @@ struct RleTile {
             k[i] = idx < n ? keys[idx] : KO::make(0, 0);
         }
         u32 wcount = 0;
-        heads = 0;
+        heads = 0; pals = 0;
 #pragma unroll
         for (int i = 0; i < kRleItems; ++i) {
             const u64 idx = wbase + (u64)i * 32 + lane;
@@ -392,7 +394,13 @@ struct RleTile {
             const K prev = KO::make(lane ? up_lo : last_lo, lane ? up_hi : last_hi);
             const bool head = ok && (idx == 0 || !KO::eq(k[i], prev));
             bool keep = head;
-            if (head && min_count > 1) keep = idx + min_count - 1 < n && KO::eq(keys[idx + min_count - 1], k[i]);
+            u64 need = min_count;
+            if (fold_w) {
+                const bool pal = head && KO::eq(key_rc(k[i], fold_w), k[i]);
+                if (pal) need = (min_count + 1) >> 1;
+                pals += __popc(__ballot_sync(0xffffffffu, pal));
+            }
+            if (head && need > 1) keep = idx + need - 1 < n && KO::eq(keys[idx + need - 1], k[i]);
             headb[i] = __ballot_sync(0xffffffffu, head);
             heads += __popc(headb[i]);
             kept[i] = __ballot_sync(0xffffffffu, keep);
@@ -403,21 +411,22 @@ struct RleTile {
 };
 
 template <typename K>
-__global__ void __launch_bounds__(kRleThreads, 4) rle_count_kernel(const K* __restrict__ keys, u64 n, u64 min_count,
-                                                                   u32* __restrict__ tile_kept, u64* __restrict__ total_heads) {
-    __shared__ u32 warp_tot[kRleThreads / 32], warp_heads[kRleThreads / 32];
+__global__ void __launch_bounds__(kRleThreads, 4) rle_count_kernel(const K* __restrict__ keys, u64 n, u64 min_count, int fold_w,
+                                                                   u32* __restrict__ tile_kept, u64* __restrict__ total_heads /* [0] heads, [2] self-complementary heads */) {
+    __shared__ u32 warp_tot[kRleThreads / 32], warp_heads[kRleThreads / 32], warp_pals[kRleThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 wbase = (u64)blockIdx.x * (kRleThreads * kRleItems) + (u64)warp * 32 * kRleItems;
-    K k[kRleItems]; u32 kept[kRleItems], headb[kRleItems]; u32 heads;
-    const u32 wcount = RleTile<K>::scan(keys, n, wbase, lane, min_count, k, kept, headb, heads);
-    if (lane == 0) { warp_tot[warp] = wcount; warp_heads[warp] = heads; }
+    K k[kRleItems]; u32 kept[kRleItems], headb[kRleItems]; u32 heads, pals;
+    const u32 wcount = RleTile<K>::scan(keys, n, wbase, lane, min_count, fold_w, k, kept, headb, heads, pals);
+    if (lane == 0) { warp_tot[warp] = wcount; warp_heads[warp] = heads; warp_pals[warp] = pals; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        u32 t = 0, h = 0;
+        u32 t = 0, h = 0, p = 0;
 #pragma unroll
-        for (int w = 0; w < kRleThreads / 32; ++w) { t += warp_tot[w]; h += warp_heads[w]; }
+        for (int w = 0; w < kRleThreads / 32; ++w) { t += warp_tot[w]; h += warp_heads[w]; p += warp_pals[w]; }
         tile_kept[blockIdx.x] = t;
         if (h) atomicAdd(total_heads, (u64)h);
+        if (p) atomicAdd(total_heads + 2, (u64)p);
     }
 }
 
@@ -433,7 +442,7 @@ __device__ __forceinline__ u64 run_end(const K* __restrict__ keys, u64 n, u64 kn
 }
 
 template <typename K>
-__global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __restrict__ keys, const u64* __restrict__ csum, u64 n, u64 min_count,
+__global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __restrict__ keys, const u64* __restrict__ csum, u64 n, u64 min_count, int fold_w,
                                                                   const u64* __restrict__ tile_off, K* __restrict__ out_keys,
                                                                   u64* __restrict__ out_counts) {
     constexpr int WORDS = kRleThreads * kRleItems / 32;          // the tile's run-head bit vector (warp-striped layout
@@ -442,8 +451,8 @@ __global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __res
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 tbase = (u64)blockIdx.x * (kRleThreads * kRleItems);
     const u64 wbase = tbase + (u64)warp * 32 * kRleItems;
-    K k[kRleItems]; u32 kept[kRleItems], headb[kRleItems]; u32 heads;
-    const u32 wcount = RleTile<K>::scan(keys, n, wbase, lane, min_count, k, kept, headb, heads);
+    K k[kRleItems]; u32 kept[kRleItems], headb[kRleItems]; u32 heads, pals;
+    const u32 wcount = RleTile<K>::scan(keys, n, wbase, lane, min_count, fold_w, k, kept, headb, heads, pals);
     if (lane == 0) {
         warp_tot[warp] = wcount;
 #pragma unroll
@@ -466,7 +475,9 @@ __global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __res
                               : (tile_end < n ? run_end<K>(keys, n, tile_end - 1, k[i]) : n);
             const u64 o = j + __popc(kept[i] & lt);
             out_keys[o] = k[i];
-            out_counts[o] = csum ? (csum[end] - csum[idx]) : (end - idx);
+            u64 cnt = csum ? (csum[end] - csum[idx]) : (end - idx);
+            if (fold_w && KeyOps<K>::eq(key_rc(k[i], fold_w), k[i])) cnt <<= 1;   // both strands of a self-complementary key are this key
+            out_counts[o] = cnt;
         }
         j += __popc(kept[i]);
     }
@@ -475,20 +486,20 @@ __global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __res
 u64 rle_tiles(u64 n) { return (n + kRleThreads * kRleItems - 1) / (kRleThreads * kRleItems); }
 u64 rle_lookback_bytes(u64 n) { return rle_tiles(n) * 8 + 256; }
 
-void sort_rle_count(int key_bytes, const void* keys, u64 n, u64 min_count, u32* tile_kept, u64* total_heads, cudaStream_t s, u64* launches) {
+void sort_rle_count(int key_bytes, const void* keys, u64 n, u64 min_count, int fold_w, u32* tile_kept, u64* total_heads, cudaStream_t s, u64* launches) {
     if (!n) return;
     const unsigned tiles = (unsigned)rle_tiles(n);
-    if (key_bytes == 8) rle_count_kernel<u64><<<tiles, kRleThreads, 0, s>>>((const u64*)keys, n, min_count, tile_kept, total_heads);
-    else rle_count_kernel<Key128><<<tiles, kRleThreads, 0, s>>>((const Key128*)keys, n, min_count, tile_kept, total_heads);
+    if (key_bytes == 8) rle_count_kernel<u64><<<tiles, kRleThreads, 0, s>>>((const u64*)keys, n, min_count, fold_w, tile_kept, total_heads);
+    else rle_count_kernel<Key128><<<tiles, kRleThreads, 0, s>>>((const Key128*)keys, n, min_count, fold_w, tile_kept, total_heads);
     ++*launches;
 }
 
-void sort_rle_emit(int key_bytes, const void* keys, const u64* csum, u64 n, u64 min_count, const u64* tile_off, void* out_keys, u64* out_counts,
+void sort_rle_emit(int key_bytes, const void* keys, const u64* csum, u64 n, u64 min_count, int fold_w, const u64* tile_off, void* out_keys, u64* out_counts,
                    cudaStream_t s, u64* launches) {
     if (!n) return;
     const unsigned tiles = (unsigned)rle_tiles(n);
-    if (key_bytes == 8) rle_emit_kernel<u64><<<tiles, kRleThreads, 0, s>>>((const u64*)keys, csum, n, min_count, tile_off, (u64*)out_keys, out_counts);
-    else rle_emit_kernel<Key128><<<tiles, kRleThreads, 0, s>>>((const Key128*)keys, csum, n, min_count, tile_off, (Key128*)out_keys, out_counts);
+    if (key_bytes == 8) rle_emit_kernel<u64><<<tiles, kRleThreads, 0, s>>>((const u64*)keys, csum, n, min_count, fold_w, tile_off, (u64*)out_keys, out_counts);
+    else rle_emit_kernel<Key128><<<tiles, kRleThreads, 0, s>>>((const Key128*)keys, csum, n, min_count, fold_w, tile_off, (Key128*)out_keys, out_counts);
     ++*launches;
 }
 
@@ -636,10 +647,12 @@ int sort_keys(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64*
 }
 
 void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* weights, u64 n, u64 min_count,
-                   ReducedRun& out, u64* m_distinct, void* /*dkeys_scratch*/) {
+                   ReducedRun& out, u64* m_distinct, int fold_w, u64* n_self_rc) {
     cudaStream_t s = ws.stream;
     out.m = 0;
     if (m_distinct) *m_distinct = 0;
+    if (n_self_rc) *n_self_rc = 0;
+    if (weights && fold_w) throw StatusError{GSB_EINVAL, "internal: strand folding is finished by fold_finalize for merged runs"};
     if (n == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return; }
     if (min_count < 1) min_count = 1;
     const bool trace = getenv("GSB_TRACE_REDUCE") != nullptr;
@@ -656,17 +669,18 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
     const u64 local_min = weights ? 1 : min_count;
     const u64 tiles = rle_tiles(n);
     DevBuf<u32> tile_kept(&ws, tiles);
-    DevBuf<u64> tile_off(&ws, tiles), tmp(&ws, scan_tmp_elems(tiles)), scalars(&ws, 2);
-    GSB_CUDA_TRY(cudaMemsetAsync(scalars.p, 0, 16, s));
+    DevBuf<u64> tile_off(&ws, tiles), tmp(&ws, scan_tmp_elems(tiles)), scalars(&ws, 4);
+    GSB_CUDA_TRY(cudaMemsetAsync(scalars.p, 0, 32, s));
     lap("alloc small");
-    sort_rle_count(key_bytes, sorted, n, local_min, tile_kept.p, scalars.p, s, &ws.launches);
+    sort_rle_count(key_bytes, sorted, n, local_min, fold_w, tile_kept.p, scalars.p, s, &ws.launches);
     lap("rle_count");
     exclusive_scan<u32, u64>(tile_kept.p, tile_off.p, tiles, 0ull, scalars.p + 1, tmp.p, s, &ws.launches);
-    u64 host[2] = {0, 0};
-    GSB_CUDA_TRY(cudaMemcpyAsync(host, scalars.p, 16, cudaMemcpyDeviceToHost, s));
+    u64 host[4] = {0, 0, 0, 0};
+    GSB_CUDA_TRY(cudaMemcpyAsync(host, scalars.p, 32, cudaMemcpyDeviceToHost, s));
     ws.sync();
     const u64 heads = host[0], kept = host[1];
     if (m_distinct) *m_distinct = heads;
+    if (n_self_rc) *n_self_rc = host[2];
     DevBuf<u64> csum;
     if (weights) {
         csum.reset(&ws, (size_t)n + 1);
@@ -677,7 +691,7 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
     out.keys.reset(&ws, (size_t)kept * key_bytes);
     out.counts.reset(&ws, (size_t)kept);
     lap("alloc outputs");
-    sort_rle_emit(key_bytes, sorted, weights ? csum.p : nullptr, n, local_min, tile_off.p, out.keys.p, out.counts.p, s, &ws.launches);
+    sort_rle_emit(key_bytes, sorted, weights ? csum.p : nullptr, n, local_min, fold_w, tile_off.p, out.keys.p, out.counts.p, s, &ws.launches);
     out.m = kept;
     lap("rle_emit");
     if (weights && min_count > 1 && kept) {

@@ -72,7 +72,7 @@ typedef struct gsb_config {
 
 typedef struct gsb_counts {
     uint64_t n_reads;      /* records framed */
-    uint64_t n_instances;  /* keys fed to counting (both strands for graphs) */
+    uint64_t n_instances;  /* keys the reference feeds to counting (both strands for graphs) */
     uint64_t n_distinct;   /* distinct keys (all ranks when a communicator is attached) */
     uint64_t n_kept;       /* after the min-count filter == number of edges / k-mers emitted */
 } gsb_counts;
@@ -92,6 +92,7 @@ typedef struct gsb_stats {
     double ms_h2d, ms_scan, ms_extract, ms_sort, ms_reduce, ms_merge, ms_emit, ms_d2h, ms_exchange;
     double ms_sort_sweeps;      /* sum of the radix sweep kernels alone (events around each launch) */
     double ms_all_to_all;       /* the NCCL all-to-all alone (inside ms_exchange) */
+    double ms_unfold;           /* graph mode: reverse complements of the folded, filtered run + sort + merge */
     uint64_t exchange_bytes_sent; /* bytes this rank sent to OTHER ranks in the all-to-all */
     uint64_t exchange_peer_memory; /* 1 = fused partition+transfer into peer windows over NVLink, 0 = NCCL send/recv */
     uint64_t bytes_in;          /* raw text bytes pushed */
@@ -103,6 +104,8 @@ typedef struct gsb_stats {
     uint64_t n_batches;         /* sort+reduce rounds */
     uint64_t kernel_launches;   /* launches of this library's kernels so far */
     uint64_t hbm_peak_bytes;    /* high-water mark of device allocations */
+    uint64_t n_sorted_keys;     /* keys that went through the instance sort (graph mode: one per window,
+                                   = n_instances / 2, because the two strands are folded) */
 } gsb_stats;
 
 /* Replaces: GossCmdFactoryBuildGraph::create parameter checks (src/GossCmdBuildGraph.cc:428-477)
