@@ -115,24 +115,31 @@ class MemorySink:
     def __init__(self, keep_data=True):
         self.files = {}
         self.sizes = {}
+        self.segments = {}          # name -> [(offset, length)]: the pieces this process wrote (multi-GPU emission)
         self.keep_data = keep_data
         self._handles = {}
         self._next = 1
 
         def _open(user, name, size_hint, out):
+            # size_hint is the size of the whole file; a file may be opened again for a further piece, and
+            # bytes that nobody writes are zero
             h = self._next
             self._next += 1
             nm = name.decode()
             self._handles[h] = nm
-            self.sizes[nm] = 0
+            self.sizes[nm] = max(self.sizes.get(nm, 0), size_hint)
+            self.segments.setdefault(nm, [])
             if self.keep_data:
-                self.files[nm] = bytearray()
+                buf = self.files.setdefault(nm, bytearray())
+                if len(buf) < size_hint:
+                    buf.extend(b"\0" * (size_hint - len(buf)))
             out[0] = h
             return 0
 
         def _pwrite(user, handle, offset, data, length):
             nm = self._handles[handle]
             self.sizes[nm] = max(self.sizes[nm], offset + length)
+            self.segments[nm].append((offset, length))
             if self.keep_data:
                 buf = self.files[nm]
                 if len(buf) < offset + length:
@@ -159,9 +166,12 @@ class DirectorySink:
         self._next = 1
 
         def _open(user, name, size_hint, out):
+            # no truncation: with several GPUs every rank opens the same file and writes its own pieces
             h = self._next
             self._next += 1
-            self._handles[h] = open(name.decode(), "wb")
+            fd = os.open(name.decode(), os.O_CREAT | os.O_RDWR, 0o644)
+            os.ftruncate(fd, size_hint)
+            self._handles[h] = os.fdopen(fd, "r+b")
             out[0] = h
             return 0
 

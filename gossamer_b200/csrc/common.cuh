@@ -67,6 +67,16 @@ __device__ __forceinline__ Key128 key_rc(const Key128& x, int w) {              
     return r;
 }
 
+// Bijective bit mixing of a key, used when instances are only GROUPED (counting from a partial sort,
+// sort.cu): the low bits of the mixed key depend on every base of the window, so keys that differ by one
+// substitution anywhere -- a true k-mer and its sequencing-error variants share most of their bases --
+// fall into different groups.  x ^ (x >> 32) is its own inverse on 64 bits; the high word of a 128-bit key
+// is folded into the low word first and left unchanged itself.
+__host__ __device__ __forceinline__ u64 key_mix(u64 x) { return x ^ (x >> 32); }
+__host__ __device__ __forceinline__ u64 key_unmix(u64 x) { return x ^ (x >> 32); }
+__host__ __device__ __forceinline__ Key128 key_mix(const Key128& x) { Key128 r; const u64 t = x.lo ^ x.hi; r.lo = t ^ (t >> 32); r.hi = x.hi; return r; }
+__host__ __device__ __forceinline__ Key128 key_unmix(const Key128& x) { Key128 r; const u64 t = x.lo ^ (x.lo >> 32); r.lo = t ^ x.hi; r.hi = x.hi; return r; }
+
 // ---- decoupled look-back over tiles ---------------------------------------------------------
 // state word = status (top 2 bits: 0 empty, 1 tile aggregate, 2 inclusive prefix) | value.
 template <typename T> struct LookbackWord;

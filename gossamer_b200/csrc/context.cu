@@ -1,6 +1,7 @@
 // context.cu -- the C ABI of include/gossamer_b200.h: context, memory, per-block pipeline,
 // batching/merging, emission of the Graph / KmerSet file sets.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -97,6 +98,10 @@ struct gsb_ctx {
     Workspace ws;
     std::string err;
     int key_bytes = 8, key_bits = 0, window = 0, passes = 0;
+    u64 self_rc_windows = 0;       // windows seen so far that equal their own reverse complement
+    bool any_self_rc = true;       // (all ranks) whether any exist: if not, doubling / the special filter threshold are skipped
+    bool mix = false;              // graph mode with a min-count filter: instances are stored bit-mixed (key_mix) for the
+                                   // partial-sort counting of sort.cu; any other use of a batch un-mixes it first
     int fold_w = 0;                // graph mode: instances are strand-folded windows of this many symbols (fold.cu); 0 = kmer set
 
     // instance keys of the current batch
@@ -134,6 +139,10 @@ struct gsb_ctx {
     bool exchanged_instances = false;
     u64 instances_before_exchange = 0;
     u8* batch_src = nullptr;       // where the current batch's instances are when not in `keys` (receive window)
+    DistRun dist;                  // multi-GPU: the final run as published in the ranks' peer-mapped windows
+    bool dist_ready = false;       // ... is valid: gsb_emit writes this rank's byte ranges of every file
+    bool acc_unsorted = false;     // acc came out of reduce_groups: folded, filtered, final counts, arbitrary order
+    bool gathered = false;         // gsb_gather_to_root was called: rank 0 holds and emits everything
 
     void log(int sev, const std::string& m) { if (cfg.log) cfg.log(cfg.log_user, sev, m.c_str()); }
 };
@@ -222,21 +231,57 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     u8* const src = c->batch_src ? c->batch_src : c->keys.p;
     c->batch_src = nullptr;
     int passes_run = 0;
-    c->timer.start();
-    int where = sort_keys(ws, kb, c->key_bits, src, alt.p, nullptr, nullptr, c->n_keys, c->hist.p, &passes_run, &c->stats.ms_sort_sweeps);
-    c->timer.stop(c->stats.ms_sort);
-    c->stats.sort_passes += passes_run;
-    c->stats.sort_passes_model += c->passes;
-    c->stats.n_batches += 1;
+    // digit histograms: fused into the extraction on one GPU, taken from the received instances after an
+    // instance exchange; a batch flushed BEFORE the exchange (multi-batch input with a communicator) has none yet
+    const u64* hist = (c->comm && !c->exchanged_instances) ? nullptr : c->hist.p;
     ReducedRun run; u64 distinct = 0, n_self_rc = 0;
     // The only batch of a build (on this rank, after any instance exchange): doubling of the
     // self-complementary keys and the min-count filter are fused into the run-length reduce.
     // Otherwise the run stays folded with raw occurrence counts until every batch has been merged.
     const bool fused_final = final_and_only && (!c->comm || c->exchanged_instances);
     const u64 min_count = (fused_final && c->cfg.kind == GSB_KIND_GRAPH) ? std::max<u64>(1, c->cfg.min_count) : 1;
-    c->timer.start();
-    reduce_sorted(ws, kb, where ? alt.p : src, nullptr, c->n_keys, min_count, run, &distinct, fused_final ? c->fold_w : 0, &n_self_rc);
-    c->timer.stop(c->stats.ms_reduce);
+    const int fold_w = (fused_final && c->any_self_rc) ? c->fold_w : 0;
+    // With a min-count filter the survivors are few: count from a PARTIAL sort (low digits of the bit-mixed key only,
+    // enough of them that a group of equal low bits is almost surely one key) and sort just the survivors by the full
+    // key afterwards (sort.cu "counting from a partial sort", fold.cu).
+    int where = 0;
+    bool reduced = false;
+    if (c->mix && fused_final) {
+        int lg = 0; while ((1ull << lg) < c->n_keys) ++lg;
+        int group_digits = std::max(1, std::min(c->passes, (lg + 12 + 7) / 8));
+        if (const char* e = getenv("GSB_GROUP_DIGITS")) group_digits = std::max(1, std::min(c->passes, atoi(e)));   // test / profiling knob
+        c->timer.start();
+        where = sort_keys(ws, kb, c->key_bits, src, alt.p, nullptr, nullptr, c->n_keys, hist, &passes_run, &c->stats.ms_sort_sweeps, 0, group_digits);
+        c->timer.stop(c->stats.ms_sort);
+        c->stats.sort_passes += passes_run;
+        c->timer.start();
+        reduced = reduce_groups(ws, kb, c->key_bits, where ? alt.p : src, c->n_keys, std::min(8 * group_digits, c->key_bits), min_count, fold_w,
+                                where ? src : alt.p, run, &distinct, &n_self_rc);
+        c->timer.stop(c->stats.ms_reduce);
+        if (reduced) c->acc_unsorted = true;
+        else c->log(0, "partial-sort counting declined (many survivors or colliding groups): sorting by the full key instead");
+    }
+    if (!reduced) {
+        u8* const from = where ? alt.p : src;
+        u8* const other = where ? src : alt.p;
+        c->timer.start();
+        if (c->mix) {                                              // real keys again; the fused histograms described the mixed ones
+            sort_unmix_inplace(kb, from, c->n_keys, ws.sm_count, ws.stream, &ws.launches);
+            hist = nullptr;
+        }
+        passes_run = 0;
+        const int where2 = sort_keys(ws, kb, c->key_bits, from, other, nullptr, nullptr, c->n_keys, hist, &passes_run, &c->stats.ms_sort_sweeps);
+        where ^= where2;
+        c->timer.stop(c->stats.ms_sort);
+        c->stats.sort_passes += passes_run;
+    }
+    c->stats.sort_passes_model += c->passes;
+    c->stats.n_batches += 1;
+    if (!reduced) {
+        c->timer.start();
+        reduce_sorted(ws, kb, where ? alt.p : src, nullptr, c->n_keys, min_count, run, &distinct, fold_w, &n_self_rc);
+        c->timer.stop(c->stats.ms_reduce);
+    }
     c->counts.n_instances += c->n_keys * (c->fold_w ? 2 : 1);  // the reference counts both strands (src/ReverseComplementAdapter.hh:34-55)
     c->stats.n_sorted_keys += c->n_keys;
     if (fused_final) c->counts.n_distinct = c->fold_w ? 2 * distinct - n_self_rc : distinct;
@@ -320,7 +365,9 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     c->stats.n_symbols += block_syms;
 
     // K3: windows -> keys (+ fused digit histograms)
-    ingest_extract(c->cfg.kind, c->key_bytes, codes.p, valid.p, 64 + n_carry, n_sym_total, c->window, c->passes,
+    // (with a communicator attached the instances are exchanged before the sort and the digit histograms are taken from
+    // what arrives, so the fused histograms -- the dominant cost of the kernel -- are switched off)
+    ingest_extract(c->cfg.kind, c->key_bytes, codes.p, valid.p, 64 + n_carry, n_sym_total, c->window, c->comm ? 0 : c->passes, c->mix ? 1 : 0,
                    c->keys.p, c->cursor.p, c->keys_cap, c->hist.p, c->status.p, ws.sm_count, s, &ws.launches);
     u64 cur = 0;
     GSB_CUDA_TRY(cudaMemcpyAsync(&cur, c->cursor.p, 8, cudaMemcpyDeviceToHost, s));
@@ -335,6 +382,7 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     }
     c->timer.stop(c->stats.ms_extract);
     if (st.error) throw StatusError{GSB_EINVAL, "key buffer overflow (internal sizing error)"};
+    c->self_rc_windows += st.n_self_rc;
     c->n_keys = cur;
     c->file_open[format] = !last;
     c->line_base[format] = last ? 0 : c->line_base[format] + n_lines;
@@ -361,6 +409,33 @@ void write_kmer_set_files(gsb_ctx* c, Emitter& em, const std::string& prefix) {
     emit_sparse_array(em, c->key_bytes, c->acc.keys.p, m, universe, m, universe, prefix + ".kmers");
     u64 header[3] = {2011101701ull, k, m};             // KmerSet::Builder::end, src/KmerSet.hh:76-83
     em.put_host(prefix + ".header", header, sizeof(header));
+}
+
+// multi-GPU: every rank writes its own byte ranges of every file (emit.cu, "Multi-GPU emission")
+void write_graph_files_dist(gsb_ctx* c, Emitter& em, const std::string& prefix) {
+    const u64 k = (u64)c->cfg.k;
+    const u64 m = c->dist.off[c->dist.n];
+    if (c->dist.rank == 0) {
+        u64 header[3] = {2011101014ull, k, 0};
+        em.put_host(prefix + ".header", header, sizeof(header));
+    }
+    const unsigned rho2 = 2 * (unsigned)(k + 1);
+    U128 universe = rho2 < 64 ? U128{1ull << rho2, 0} : U128{0, 1ull << (rho2 - 64)};
+    emit_sparse_array_dist(em, c->comm, c->key_bytes, c->dist, universe, m, universe, prefix + "-edges");
+    emit_counts_dist(em, c->comm, c->dist, m, prefix + "-counts");
+    emit_count_histogram_dist(em, c->comm, c->dist, prefix + "-counts-hist.txt");
+}
+
+void write_kmer_set_files_dist(gsb_ctx* c, Emitter& em, const std::string& prefix) {
+    const u64 k = (u64)c->cfg.k;
+    const u64 m = c->dist.off[c->dist.n];
+    const unsigned bits = 2 * (unsigned)k;
+    U128 universe = bits < 64 ? U128{1ull << bits, 0} : U128{0, 1ull << (bits - 64)};
+    emit_sparse_array_dist(em, c->comm, c->key_bytes, c->dist, universe, m, universe, prefix + ".kmers");
+    if (c->dist.rank == 0) {
+        u64 header[3] = {2011101701ull, k, m};
+        em.put_host(prefix + ".header", header, sizeof(header));
+    }
 }
 
 void init_ctx(gsb_ctx* c) {
@@ -390,6 +465,7 @@ void init_ctx(gsb_ctx* c) {
 
     c->window = cfg.kind == GSB_KIND_GRAPH ? cfg.k + 1 : cfg.k;
     c->fold_w = cfg.kind == GSB_KIND_GRAPH ? c->window : 0;
+    c->mix = cfg.kind == GSB_KIND_GRAPH && cfg.min_count >= 2 && !getenv("GSB_FULL_SORT");
     c->key_bits = 2 * c->window;
     c->key_bytes = c->key_bits <= 64 ? 8 : 16;
     c->passes = (c->key_bits + 7) / 8;
@@ -485,6 +561,7 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
         if (!c->counted) {
             bool single = !c->have_acc;
             bool exchanged_instances = false;
+            c->any_self_rc = (c->comm ? exchange_sum(c->comm, c->ws, c->self_rc_windows) : c->self_rc_windows) > 0;
             if (c->comm && single) {
                 // Multi-GPU, everything still buffered as raw instances: route each instance to the
                 // rank that owns its key range FIRST (one all-to-all of raw keys over NVLink), then
@@ -521,11 +598,13 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
             if (!filtered_already) {
                 // merged batches (and/or exchanged reduced runs): still folded, raw occurrence counts
                 u64 local_distinct = c->acc.m;
-                if (c->fold_w && c->acc.m) {
+                if (c->fold_w && c->acc.m && c->any_self_rc) {
                     c->timer.start();
                     const u64 n_self = fold_double_self_rc(c->ws, c->key_bytes, c->fold_w, c->acc.keys.p, c->acc.counts.p, c->acc.m);
                     c->timer.stop(c->stats.ms_unfold);
                     local_distinct = 2 * c->acc.m - n_self;
+                } else if (c->fold_w) {
+                    local_distinct = 2 * c->acc.m;
                 }
                 if (min_count > 1 && c->acc.m) {
                     c->timer.start();
@@ -542,19 +621,77 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                 c->counts.n_distinct = c->comm ? exchange_sum(c->comm, c->ws, local_distinct) : local_distinct;
             }
             if (c->fold_w) {
-                // restore both strands: acc := sorted(acc U rc(acc))
-                c->timer.start();
-                unfold_run(c->ws, c->key_bytes, c->key_bits, c->fold_w, c->acc);
-                c->timer.stop(c->stats.ms_unfold);
-                if (c->comm) {
-                    // a rank's reverse complements fall into other ranks' key ranges: partition the full runs again
+                bool done = false;
+                if (c->acc_unsorted && !filtered_already) throw StatusError{GSB_EINVAL, "internal: unsorted run outside the single-batch path"};
+                if (c->comm && exchange_peer_memory_usable(c->comm)) {
+                    // Multi-GPU: a key's reverse complement falls into another rank's range of the FINAL order.
+                    // U = acc ++ rc(acc) is built unsorted, every pair is stored straight into the window of the rank
+                    // that owns its range (splitters sampled from U itself, so the final slices are balanced), and the
+                    // owner sorts what it received -- the slice is then already published for the emitters.
+                    const u64 m = c->acc.m;
+                    const int kb = c->key_bytes;
                     c->timer.start();
-                    exchange_runs(c->comm, c->ws, c->key_bytes, c->key_bits, c->acc);
+                    DevBuf<u8> uk(&c->ws, 2 * m * kb);
+                    DevBuf<u64> uc(&c->ws, 2 * m);
+                    if (m) {
+                        GSB_CUDA_TRY(cudaMemcpyAsync(uk.p, c->acc.keys.p, m * kb, cudaMemcpyDeviceToDevice, c->ws.stream));
+                        GSB_CUDA_TRY(cudaMemcpyAsync(uc.p, c->acc.counts.p, m * 8, cudaMemcpyDeviceToDevice, c->ws.stream));
+                    }
+                    const u64 n_rc = unfold_append_rc(c->ws, kb, c->fold_w, c->acc.keys.p, c->acc.counts.p, m, uk.p + m * kb, uc.p + m);
+                    c->timer.stop(c->stats.ms_unfold);
+                    c->timer.start();
+                    u8* rk = nullptr; u64* rc = nullptr;
+                    std::vector<u64> totals;
+                    const bool ok = exchange_pairs_p2p(c->comm, c->ws, kb, uk.p, uc.p, m + n_rc, &rk, &rc, &totals);
+                    c->timer.stop(c->stats.ms_exchange);
+                    if (ok) {
+                        uk.free(); uc.free();
+                        const u64 mine = totals[exchange_rank(c->comm)];
+                        c->timer.start();
+                        DevBuf<u8> bk(&c->ws, mine * kb);
+                        DevBuf<u64> bc(&c->ws, mine);
+                        const int where = sort_keys(c->ws, kb, c->key_bits, rk, bk.p, rc, bc.p, mine, nullptr, nullptr);
+                        if (mine) {                              // keep one copy in the window (for the peers) and one as acc
+                            const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+                            GSB_CUDA_TRY(cudaMemcpyAsync(where ? (void*)rk : (void*)bk.p, where ? (void*)bk.p : (void*)rk, mine * kb, d2d, c->ws.stream));
+                            GSB_CUDA_TRY(cudaMemcpyAsync(where ? rc : bc.p, where ? bc.p : rc, mine * 8, d2d, c->ws.stream));
+                        }
+                        c->acc.keys = std::move(bk); c->acc.counts = std::move(bc); c->acc.m = mine;
+                        c->timer.stop(c->stats.ms_unfold);
+                        c->timer.start();
+                        exchange_view(c->comm, kb, totals, &c->dist);
+                        exchange_barrier(c->comm, c->ws);        // every slice is sorted and in place before anyone reads a neighbour's
+                        c->dist_ready = true;
+                        c->timer.stop(c->stats.ms_exchange);
+                        done = true;
+                    }
+                }
+                if (!done) {
+                    // restore both strands locally: acc := sorted(acc U rc(acc))
+                    c->timer.start();
+                    unfold_run(c->ws, c->key_bytes, c->key_bits, c->fold_w, c->acc, !c->acc_unsorted);
+                    c->timer.stop(c->stats.ms_unfold);
+                    if (c->comm) {
+                        // a rank's reverse complements fall into other ranks' key ranges: partition the full runs again
+                        c->timer.start();
+                        exchange_runs(c->comm, c->ws, c->key_bytes, c->key_bits, c->acc);
+                        c->timer.stop(c->stats.ms_exchange);
+                    }
+                }
+                c->acc_unsorted = false;
+            }
+            if (c->comm) {
+                // publish the slice in this rank's peer-mapped window: the distributed emitters work from there
+                if (!c->dist_ready) {
+                    c->timer.start();
+                    c->dist_ready = exchange_publish(c->comm, c->ws, c->key_bytes, c->acc, &c->dist);
                     c->timer.stop(c->stats.ms_exchange);
                 }
+                c->counts.n_kept = c->dist_ready ? c->dist.off[c->dist.n] : exchange_sum(c->comm, c->ws, c->acc.m);
+                c->counts.n_instances = exchange_sum(c->comm, c->ws, c->counts.n_instances);
+            } else {
+                c->counts.n_kept = c->acc.m;
             }
-            c->counts.n_kept = c->comm ? exchange_sum(c->comm, c->ws, c->acc.m) : c->acc.m;
-            if (c->comm) c->counts.n_instances = exchange_sum(c->comm, c->ws, c->counts.n_instances);
             c->counted = true;
         }
         if (out) *out = c->counts;
@@ -567,9 +704,22 @@ int gsb_emit(gsb_ctx* c, const char* prefix, const gsb_sink* sink) {
         if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_emit before gsb_finish_counting"};
         Emitter em;
         em.ws = &c->ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
+        if (c->comm && !c->gathered && !c->dist_ready) {
+            // peer memory is not available here: fall back to shipping every slice to rank 0
+            c->timer.start();
+            exchange_gather(c->comm, c->ws, c->key_bytes, c->acc);
+            c->timer.stop(c->stats.ms_exchange);
+            c->gathered = true;
+        }
         c->timer.start();
-        if (c->cfg.kind == GSB_KIND_GRAPH) write_graph_files(c, em, prefix);
-        else write_kmer_set_files(c, em, prefix);
+        if (c->comm && !c->gathered) {
+            if (c->cfg.kind == GSB_KIND_GRAPH) write_graph_files_dist(c, em, prefix);
+            else write_kmer_set_files_dist(c, em, prefix);
+            exchange_barrier(c->comm, c->ws);                    // nobody reuses its window while a peer still reads it
+        } else if (!c->comm || exchange_rank(c->comm) == 0) {
+            if (c->cfg.kind == GSB_KIND_GRAPH) write_graph_files(c, em, prefix);
+            else write_kmer_set_files(c, em, prefix);
+        }
         c->timer.stop(c->stats.ms_emit);
         c->stats.bytes_out += em.bytes_out;
     });
@@ -615,6 +765,9 @@ int gsb_reset(gsb_ctx* c) {
     return guarded(c, [&] {
         c->acc.keys.free(); c->acc.counts.free(); c->acc.m = 0;
         c->have_acc = false; c->counted = false;
+        c->dist_ready = false; c->gathered = false;
+        c->self_rc_windows = 0; c->any_self_rc = true;
+        c->exchanged_instances = false; c->batch_src = nullptr; c->acc_unsorted = false;
         for (int f = 0; f < 3; ++f) { c->file_open[f] = false; c->line_base[f] = 0; }
         c->n_carry = 0;
         memset(&c->counts, 0, sizeof(c->counts));
@@ -651,9 +804,11 @@ int gsb_gather_to_root(gsb_ctx* c) {
     return guarded(c, [&] {
         if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_gather_to_root before gsb_finish_counting"};
         if (!c->comm) return;
+        if (c->gathered) return;
         c->timer.start();
         exchange_gather(c->comm, c->ws, c->key_bytes, c->acc);
         c->timer.stop(c->stats.ms_exchange);
+        c->gathered = true;
     });
 }
 

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "exchange.h"
 #include "kernels.h"
 #include "scan.cuh"
 
@@ -61,6 +62,31 @@ void Emitter::put_device(const std::string& name, const void* dev, u64 len, cons
     if (sink->close(sink->user, h) != 0) sink_fail("close", name);
 }
 
+// one contiguous piece [offset, offset + len) of a file whose total size is `total` (multi-GPU emission:
+// every rank hands over its own pieces; bytes nobody writes are zero)
+void Emitter::put_device_at(const std::string& name, u64 total, u64 offset, const void* dev, u64 len) {
+    bytes_out += len;
+    if (!sink || !len) return;
+    void* h = nullptr;
+    if (sink->open(sink->user, name.c_str(), total, &h) != 0) sink_fail("open", name);
+    for (u64 off = 0; off < len; off += pinned_bytes) {
+        u64 chunk = std::min<u64>(pinned_bytes, len - off);
+        GSB_CUDA_TRY(cudaMemcpyAsync(pinned, (const u8*)dev + off, chunk, cudaMemcpyDeviceToHost, ws->stream));
+        ws->sync();
+        if (sink->pwrite(sink->user, h, offset + off, pinned, chunk) != 0) sink_fail("pwrite", name);
+    }
+    if (sink->close(sink->user, h) != 0) sink_fail("close", name);
+}
+
+void Emitter::put_host_at(const std::string& name, u64 total, u64 offset, const void* data, u64 len) {
+    bytes_out += len;
+    if (!sink || !len) return;
+    void* h = nullptr;
+    if (sink->open(sink->user, name.c_str(), total, &h) != 0) sink_fail("open", name);
+    if (sink->pwrite(sink->user, h, offset, data, len) != 0) sink_fail("pwrite", name);
+    if (sink->close(sink->user, h) != 0) sink_fail("close", name);
+}
+
 // ------------------------------------------------------------------------------------------
 // K8: DenseSelect
 // ------------------------------------------------------------------------------------------
@@ -94,11 +120,13 @@ __device__ __forceinline__ u32 sub_block_type(u64 sub_span) {
     return T_SPILL32;
 }
 
+// blocks [b0, b0 + n_blocks) of the directory (b0 > 0: this rank's share in a multi-GPU emission);
+// outputs are indexed by b - b0
 template <typename F>
-__global__ void ds_classify_kernel(F f, u64 count, u64 n_blocks, u8* __restrict__ type, u64* __restrict__ bytes,
+__global__ void ds_classify_kernel(F f, u64 count, u64 b0, u64 n_blocks, u8* __restrict__ type, u64* __restrict__ bytes,
                                    u64* __restrict__ padded, u64* __restrict__ first_out) {
     for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (u64)gridDim.x * blockDim.x) {
-        const u64 j0 = b * kBlock;
+        const u64 j0 = (b0 + b) * kBlock;
         const u64 nb = count - j0 < kBlock ? count - j0 : kBlock;
         const u64 first = f(j0), last = f(j0 + nb - 1), span = last - first;
         u8 t; u64 sz;
@@ -128,20 +156,21 @@ __global__ void ds_stats_kernel(const u8* __restrict__ type, const u64* __restri
 }
 
 // one CTA of 128 threads per select block
+// `body` holds this launch's blocks; off[] are offsets into it and body_base is its offset in the file
 template <typename F>
-__global__ void __launch_bounds__(128) ds_write_kernel(F f, u64 count, const u8* __restrict__ type, const u64* __restrict__ off,
-                                                       const u64* __restrict__ first_in, u8* __restrict__ file,
-                                                       u64 index_off, u64 rank_off) {
+__global__ void __launch_bounds__(128) ds_write_kernel(F f, u64 count, u64 b0, const u8* __restrict__ type, const u64* __restrict__ off,
+                                                       const u64* __restrict__ first_in, u8* __restrict__ body, u64 body_base,
+                                                       u64* __restrict__ index_out, u64* __restrict__ rank_out) {
     __shared__ u32 scan_s[128 / 32 + 1];
     const u64 b = blockIdx.x;
-    const u64 j0 = b * kBlock;
+    const u64 j0 = (b0 + b) * kBlock;
     const u64 nb = count - j0 < kBlock ? count - j0 : kBlock;
     const u64 first = first_in[b];
     const u8 t = type[b];
-    u8* out = file + off[b];
+    u8* out = body + off[b];
     if (threadIdx.x == 0) {
-        reinterpret_cast<u64*>(file + index_off)[b] = off[b] | t;
-        reinterpret_cast<u64*>(file + rank_off)[b] = first;
+        index_out[b] = (body_base + off[b]) | t;
+        rank_out[b] = first;
     }
     if (t == T_SMALL) {
         reinterpret_cast<u16*>(out)[threadIdx.x] = (u16)(f(j0 + threadIdx.x * kSample) - first);
@@ -189,7 +218,7 @@ static void build_dense_select(Emitter& em, F f, u64 count, bool invert, const s
     DevBuf<u64> bytes(&ws, nb), padded(&ws, nb), first(&ws, nb), off(&ws, nb), tmp(&ws, scan_tmp_elems(nb)), scalars(&ws, 8);
     GSB_CUDA_TRY(cudaMemsetAsync(scalars.p, 0, 64, s));
     const int g = (int)std::min<u64>((nb + 127) / 128, (u64)ws.sm_count * 8);
-    ds_classify_kernel<F><<<g, 128, 0, s>>>(f, count, nb, type.p, bytes.p, padded.p, first.p);
+    ds_classify_kernel<F><<<g, 128, 0, s>>>(f, count, 0, nb, type.p, bytes.p, padded.p, first.p);
     ++ws.launches;
     exclusive_scan<u64, u64>(padded.p, off.p, nb, 4096ull, scalars.p + 6, tmp.p, s, &ws.launches);
     ds_stats_kernel<<<g, 128, 0, s>>>(type.p, bytes.p, nb, scalars.p);
@@ -207,7 +236,7 @@ static void build_dense_select(Emitter& em, F f, u64 count, bool invert, const s
     h.largeBlocks = host[4]; h.largeBlocksSize = host[5];
     DevBuf<u8> file(&ws, file_size);
     GSB_CUDA_TRY(cudaMemsetAsync(file.p, 0, file_size, s));
-    ds_write_kernel<F><<<(unsigned)nb, 128, 0, s>>>(f, count, type.p, off.p, first.p, file.p, h.indexArrayOffset, h.rankArrayOffset);
+    ds_write_kernel<F><<<(unsigned)nb, 128, 0, s>>>(f, count, 0, type.p, off.p, first.p, file.p, 0, (u64*)(file.p + h.indexArrayOffset), (u64*)(file.p + h.rankArrayOffset));
     ++ws.launches;
     em.put_device(name, file.p, file_size, &h, sizeof(h));
 }
@@ -328,14 +357,16 @@ __global__ void vba_flags_kernel(const u64* __restrict__ counts, u64 m, u8* __re
     }
 }
 
+// i_bias / a_bias: global index of this rank's first item / first ord1 entry (0 on one GPU)
 __global__ void vba_scatter_kernel(const u64* __restrict__ counts, u64 m, const u64* __restrict__ r1, const u64* __restrict__ r2,
-                                   u64* __restrict__ ord1_pos, u8* __restrict__ ord1, u64* __restrict__ ord2_pos, u16* __restrict__ ord2) {
+                                   u64* __restrict__ ord1_pos, u8* __restrict__ ord1, u64* __restrict__ ord2_pos, u16* __restrict__ ord2,
+                                   u64 i_bias, u64 a_bias) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
         const u32 c = (u32)counts[i];
         if (c >> 8) {
             const u64 a = r1[i];
-            ord1_pos[a] = i; ord1[a] = (u8)((c >> 8) & 0xFF);
-            if (c >> 16) { const u64 b = r2[i]; ord2_pos[b] = a; ord2[b] = (u16)(c >> 16); }
+            ord1_pos[a] = i + i_bias; ord1[a] = (u8)((c >> 8) & 0xFF);
+            if (c >> 16) { const u64 b = r2[i]; ord2_pos[b] = a + a_bias; ord2[b] = (u16)(c >> 16); }
         }
     }
 }
@@ -360,7 +391,7 @@ void emit_counts(Emitter& em, const u64* counts, u64 m, u64 m_est, const std::st
     DevBuf<u64> ord1_pos(&ws, n1), ord2_pos(&ws, n2);
     DevBuf<u8> ord1(&ws, n1);
     DevBuf<u16> ord2(&ws, n2);
-    if (n1) { vba_scatter_kernel<<<g, 256, 0, s>>>(counts, m, r1.p, r2.p, ord1_pos.p, ord1.p, ord2_pos.p, ord2.p); ++ws.launches; }
+    if (n1) { vba_scatter_kernel<<<g, 256, 0, s>>>(counts, m, r1.p, r2.p, ord1_pos.p, ord1.p, ord2_pos.p, ord2.p, 0, 0); ++ws.launches; }
     em.put_device(base + ".ord0", ord0.p, m);
     em.put_device(base + ".ord1", ord1.p, n1);
     em.put_device(base + ".ord2", ord2.p, n2 * 2);
@@ -392,6 +423,322 @@ void emit_count_histogram(Emitter& em, const u64* counts, u64 m, const std::stri
         for (u64 i = 0; i < run.m; ++i) text += std::to_string(vals[i]) + "\t" + std::to_string(freq[i]) + "\n";
     }
     em.put_host(name, text.data(), text.size());
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU emission (one process per GPU)
+// ------------------------------------------------------------------------------------------
+// After counting, rank r holds the r-th contiguous slice of the globally sorted run in its peer-mapped
+// window (DistRun, exchange.h).  Every byte of the reference's files is a function of the global index of
+// an element, so each rank writes the byte ranges that belong to its slice:
+//   .low-bits planes, .ord0        element i -> byte i * width: the rank's own index range
+//   .high-bits                     the words from the one holding the rank's first one-bit up to (not
+//                                  including) the next rank's; bits that earlier ranks' last elements put
+//                                  into the rank's first word are recomputed from those elements
+//   -d1 / -d0                      the select blocks that START in the rank's slice (ones) or in the range
+//                                  of high parts it covers (zeros); block sizes -> one all-gather -> file offsets
+// Elements of neighbouring slices (the tail of a block, the word shared with the previous rank, binary
+// searches that leave the slice) are loaded straight from the owner's memory over NVLink.
+// The wide-count planes (.ord1/.ord2 and their presence sets: counts >= 256) and the count histogram are
+// small; they are gathered and written by rank 0.
+template <typename K>
+struct GlobalKeys {
+    const K* base[kMaxRanks];
+    u64 off[kMaxRanks + 1];
+    const K* mine; u64 g0, g1;                                  // this rank's slice (fast path)
+    int n;
+    __device__ __forceinline__ K operator[](u64 i) const {
+        if (i >= g0 && i < g1) return mine[i - g0];
+        int r = 0;
+        while (r + 1 < n && i >= off[r + 1]) ++r;
+        return base[r][i - off[r]];
+    }
+};
+
+template <typename K> struct OnesPosG {
+    GlobalKeys<K> G; int D;
+    __device__ __forceinline__ u64 operator()(u64 j) const { return KeyOps<K>::shr64(G[j], D) + j; }
+};
+template <typename K> struct ZerosPosG {
+    GlobalKeys<K> G; u64 m; int D;
+    u64 jlo, jhi;                                               // high parts [jlo, jhi) resolve inside this rank's slice
+    __device__ __forceinline__ u64 operator()(u64 j) const {
+        u64 lo = 0, hi = m;                                     // #{i : (e_i >> D) <= j}
+        if (j >= jlo && j < jhi) { lo = G.g0; hi = G.g1; }
+        while (lo < hi) { u64 mid = lo + ((hi - lo) >> 1); if (KeyOps<K>::shr64(G[mid], D) <= j) lo = mid + 1; else hi = mid; }
+        return j + lo;
+    }
+};
+
+// out[2r] = high part of rank r's first element, out[2r+1] = position of its one-bit (non-empty ranks only)
+template <typename K>
+__global__ void first_elements_kernel(GlobalKeys<K> G, int D, u64* __restrict__ out) {
+    const int r = threadIdx.x;
+    if (r < G.n && G.off[r] < G.off[r + 1]) {
+        const u64 hi = KeyOps<K>::shr64(G.base[r][0], D);
+        out[2 * r] = hi; out[2 * r + 1] = hi + G.off[r];
+    }
+}
+
+template <typename K>
+__global__ void high_bits_dist_kernel(GlobalKeys<K> G, u64 i0, u64 i1, int D, u64 w0, u64 w1, u64* __restrict__ bitmap /* words [w0, w1) */) {
+    for (u64 i = i0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (u64)gridDim.x * blockDim.x) {
+        const u64 h = KeyOps<K>::shr64(G[i], D) + i;
+        const u64 w = h >> 6;
+        if (w >= w0 && w < w1) atomicOr(&bitmap[w - w0], 1ull << (h & 63));
+    }
+}
+
+template <typename F>
+static void build_dense_select_dist(Emitter& em, Exchange* x, F f, u64 count, bool invert, const std::string& name, u64 b0, u64 b1) {
+    Workspace& ws = *em.ws;
+    cudaStream_t s = ws.stream;
+    const int n = exchange_size(x), rank = exchange_rank(x);
+    DsHeader h;
+    memset(&h, 0, sizeof(h));
+    h.version = 2012092701ull; h.flags = invert ? 1 : 0;
+    h.logBlockSize = 13; h.blockSize = 8192; h.logSampleRate = 6; h.sampleRate = 64;
+    const u64 nb = (count + kBlock - 1) / kBlock;
+    std::vector<u8> page(4096, 0);
+    if (nb == 0) {
+        h.indexArrayOffset = h.rankArrayOffset = 4096;
+        memcpy(page.data(), &h, sizeof(h));
+        if (rank == 0) em.put_host(name, page.data(), page.size());
+        return;
+    }
+    const u64 nbl = b1 - b0;
+    DevBuf<u8> type(&ws, nbl);
+    DevBuf<u64> bytes(&ws, nbl), padded(&ws, nbl), first(&ws, nbl), off(&ws, nbl), tmp(&ws, scan_tmp_elems(nbl)), scalars(&ws, 8);
+    GSB_CUDA_TRY(cudaMemsetAsync(scalars.p, 0, 64, s));
+    u64 host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int g = (int)std::max<u64>(1, std::min<u64>((nbl + 127) / 128, (u64)ws.sm_count * 8));
+    if (nbl) {
+        ds_classify_kernel<F><<<g, 128, 0, s>>>(f, count, b0, nbl, type.p, bytes.p, padded.p, first.p);
+        ++ws.launches;
+        exclusive_scan<u64, u64>(padded.p, off.p, nbl, 0ull, scalars.p + 6, tmp.p, s, &ws.launches);
+        ds_stats_kernel<<<g, 128, 0, s>>>(type.p, bytes.p, nbl, scalars.p);
+        ++ws.launches;
+        GSB_CUDA_TRY(cudaMemcpyAsync(host, scalars.p, 64, cudaMemcpyDeviceToHost, s));
+        ws.sync();
+    }
+    std::vector<u64> all;
+    exchange_allgather_u64(x, ws, host, 7, all);                 // [6] = padded bytes of the rank's blocks, [0..5] = statistics
+    u64 body_base = 4096, body_end = 4096, st[6] = {0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < n; ++r) {
+        if (r < rank) body_base += all[7 * r + 6];
+        body_end += all[7 * r + 6];
+        for (int i = 0; i < 6; ++i) st[i] += all[7 * r + i];
+    }
+    h.indexArrayOffset = (body_end + 15) & ~15ull;
+    h.rankArrayOffset = h.indexArrayOffset + 8 * nb;
+    const u64 file_size = h.rankArrayOffset + 8 * nb;
+    h.numBlocks = nb; h.indexSize = 16 * nb;
+    h.smallBlocks = st[0]; h.smallBlocksSize = st[1];
+    h.intermediateBlocks = st[2]; h.intermediateBlocksSize = st[3];
+    h.largeBlocks = st[4]; h.largeBlocksSize = st[5];
+    if (nbl) {
+        const u64 body_bytes = host[6];
+        DevBuf<u8> body(&ws, body_bytes);
+        DevBuf<u64> index(&ws, nbl), ranks(&ws, nbl);
+        GSB_CUDA_TRY(cudaMemsetAsync(body.p, 0, body_bytes ? body_bytes : 1, s));
+        ds_write_kernel<F><<<(unsigned)nbl, 128, 0, s>>>(f, count, b0, type.p, off.p, first.p, body.p, body_base, index.p, ranks.p);
+        ++ws.launches;
+        em.put_device_at(name, file_size, body_base, body.p, body_bytes);
+        em.put_device_at(name, file_size, h.indexArrayOffset + 8 * b0, index.p, 8 * nbl);
+        em.put_device_at(name, file_size, h.rankArrayOffset + 8 * b0, ranks.p, 8 * nbl);
+    }
+    if (rank == 0) {
+        memcpy(page.data(), &h, sizeof(h));
+        em.put_host_at(name, file_size, 0, page.data(), page.size());
+        const u8 zeros[16] = {0};
+        if (h.indexArrayOffset > body_end) em.put_host_at(name, file_size, body_end, zeros, h.indexArrayOffset - body_end);   // alignment gap
+    }
+}
+
+template <typename K>
+static void emit_sparse_array_dist_t(Emitter& em, Exchange* x, const DistRun& run, U128 universe_ctor, u64 m_est, U128 universe_end, const std::string& base) {
+    Workspace& ws = *em.ws;
+    cudaStream_t s = ws.stream;
+    const int n = run.n, rank = run.rank;
+    const u64 m = run.off[n], g0 = run.off[rank], g1 = run.off[rank + 1], ml = g1 - g0;
+    if (m == 0) {                                               // nothing anywhere: rank 0 writes the empty structure
+        if (rank == 0) emit_sparse_array_t<K>(em, (const K*)nullptr, 0, universe_ctor, m_est, universe_end, base);
+        return;
+    }
+    const u64 D = sparse_array_d(universe_ctor, m_est);
+    const u64 qD = 8 * ((D + 7) / 8);
+    const u128_t nd128 = D >= 128 ? (u128_t)0 : (to128(universe_end) >> D);
+    if ((u64)(nd128 >> 64)) throw StatusError{GSB_EINVAL, "Internal error in SparseArray; nd does not fit 64 bits"};
+    const u64 nd = (u64)nd128;
+
+    GlobalKeys<K> G;
+    for (int r = 0; r < kMaxRanks; ++r) { G.base[r] = (const K*)run.keys[r]; G.off[r] = run.off[r]; }
+    G.off[kMaxRanks] = run.off[kMaxRanks];
+    G.mine = (const K*)run.keys[rank]; G.g0 = g0; G.g1 = g1; G.n = n;
+
+    // high part / one-bit position of every non-empty rank's first element
+    DevBuf<u64> firsts_d(&ws, 2 * (size_t)kMaxRanks);
+    std::vector<u64> firsts(2 * (size_t)kMaxRanks, 0);
+    first_elements_kernel<K><<<1, 32, 0, s>>>(G, (int)D, firsts_d.p);
+    ++ws.launches;
+    GSB_CUDA_TRY(cudaMemcpyAsync(firsts.data(), firsts_d.p, firsts.size() * 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    auto nonempty = [&](int r) { return run.off[r] < run.off[r + 1]; };
+    int first_nonempty = 0;
+    while (!nonempty(first_nonempty)) ++first_nonempty;
+    int next_nonempty = rank + 1;
+    while (next_nonempty < n && !nonempty(next_nonempty)) ++next_nonempty;
+
+    // ---- high bits ----
+    const u64 words = (nd + m + 3) / 64 + 1;
+    std::vector<u64> W(n + 1);
+    W[n] = words;
+    for (int r = n - 1; r >= 0; --r) W[r] = nonempty(r) ? (firsts[2 * r + 1] >> 6) : W[r + 1];
+    for (int r = 0; r <= first_nonempty; ++r) W[r] = 0;
+    {
+        const u64 wl = W[rank + 1] - W[rank];
+        if (wl) {
+            DevBuf<u64> bitmap(&ws, wl);
+            GSB_CUDA_TRY(cudaMemsetAsync(bitmap.p, 0, wl * 8, s));
+            const u64 i0 = g0 >= 64 ? g0 - 64 : 0;              // one-bit positions grow by >= 1 per element: older ones are in earlier words
+            if (g1 > i0) {
+                const int g = (int)std::max<u64>(1, std::min<u64>((g1 - i0 + 255) / 256, (u64)ws.sm_count * 16));
+                high_bits_dist_kernel<K><<<g, 256, 0, s>>>(G, i0, g1, (int)D, W[rank], W[rank + 1], bitmap.p);
+                ++ws.launches;
+            }
+            em.put_device_at(base + ".high-bits", words * 8, W[rank] * 8, bitmap.p, wl * 8);
+        }
+    }
+    // ---- select directory over the zeros: rank r takes the blocks that start inside the high parts it covers ----
+    {
+        const u64 count0 = nd + 2, nbz = (count0 + kBlock - 1) / kBlock;
+        std::vector<u64> B(n + 1);
+        B[n] = nbz;
+        for (int r = n - 1; r >= 0; --r) B[r] = nonempty(r) ? std::min<u64>(nbz, (firsts[2 * r] + kBlock - 1) / kBlock) : B[r + 1];
+        for (int r = 0; r <= first_nonempty; ++r) B[r] = 0;
+        ZerosPosG<K> f{G, m, (int)D, 0, 0};
+        if (ml) { f.jlo = firsts[2 * rank]; f.jhi = next_nonempty < n ? firsts[2 * next_nonempty] : ~0ull; }
+        build_dense_select_dist(em, x, f, count0, true, base + "-d0", B[rank], B[rank + 1]);
+    }
+    // ---- select directory over the ones: the blocks whose first element is in the rank's slice ----
+    build_dense_select_dist(em, x, OnesPosG<K>{G, (int)D}, m, false, base + "-d1", (g0 + kBlock - 1) / kBlock, (g1 + kBlock - 1) / kBlock);
+    // ---- low bits: the rank's own elements ----
+    const int g = (int)std::max<u64>(1, std::min<u64>((ml + 255) / 256, (u64)ws.sm_count * 16));
+    for (const PlaneSpec& p : integer_array_planes(qD)) {
+        if (!ml) continue;
+        DevBuf<u8> plane(&ws, ml * p.bytes);
+        switch (p.bytes) {
+            case 1: low_plane_kernel<K, u8><<<g, 256, 0, s>>>(G.mine, ml, (int)D, p.shift, (u8*)plane.p); break;
+            case 2: low_plane_kernel<K, u16><<<g, 256, 0, s>>>(G.mine, ml, (int)D, p.shift, (u16*)plane.p); break;
+            case 4: low_plane_kernel<K, u32><<<g, 256, 0, s>>>(G.mine, ml, (int)D, p.shift, (u32*)plane.p); break;
+            default: low_plane_kernel<K, u64><<<g, 256, 0, s>>>(G.mine, ml, (int)D, p.shift, (u64*)plane.p); break;
+        }
+        ++ws.launches;
+        em.put_device_at(base + ".low-bits" + p.suffix, m * p.bytes, g0 * p.bytes, plane.p, ml * p.bytes);
+    }
+    if (rank == 0) {
+        struct { u64 version, D, quantizedD, dmask[2], size[2], count; } hd;
+        hd.version = 2012030501ull; hd.D = D; hd.quantizedD = qD;
+        u128_t mask = D >= 128 ? ~(u128_t)0 : ((((u128_t)1) << D) - 1);
+        hd.dmask[0] = (u64)mask; hd.dmask[1] = (u64)(mask >> 64);
+        hd.size[0] = universe_end.lo; hd.size[1] = universe_end.hi;
+        hd.count = m;
+        em.put_host(base + ".header", &hd, sizeof(hd));
+    }
+}
+
+void emit_sparse_array_dist(Emitter& em, Exchange* x, int key_bytes, const DistRun& run, U128 universe_ctor, u64 m_est, U128 universe_end,
+                            const std::string& base) {
+    if (key_bytes == 8) emit_sparse_array_dist_t<u64>(em, x, run, universe_ctor, m_est, universe_end, base);
+    else emit_sparse_array_dist_t<Key128>(em, x, run, universe_ctor, m_est, universe_end, base);
+}
+
+void emit_counts_dist(Emitter& em, Exchange* x, const DistRun& run, u64 m_est, const std::string& base) {
+    Workspace& ws = *em.ws;
+    cudaStream_t s = ws.stream;
+    const int n = run.n, rank = run.rank;
+    const u64 m = run.off[n], g0 = run.off[rank], ml = run.off[rank + 1] - g0;
+    const u64* counts = run.counts[rank];
+    const int g = (int)std::max<u64>(1, std::min<u64>((ml + 255) / 256, (u64)ws.sm_count * 16));
+    DevBuf<u8> ord0(&ws, ml), f1(&ws, ml), f2(&ws, ml);
+    DevBuf<u64> r1(&ws, ml), r2(&ws, ml), tmp(&ws, scan_tmp_elems(ml)), totals(&ws, 2);
+    u64 mine[2] = {0, 0};
+    if (ml) {
+        vba_flags_kernel<<<g, 256, 0, s>>>(counts, ml, ord0.p, f1.p, f2.p);
+        ++ws.launches;
+        exclusive_scan<u8, u64>(f1.p, r1.p, ml, 0ull, totals.p, tmp.p, s, &ws.launches);
+        exclusive_scan<u8, u64>(f2.p, r2.p, ml, 0ull, totals.p + 1, tmp.p, s, &ws.launches);
+        GSB_CUDA_TRY(cudaMemcpyAsync(mine, totals.p, 16, cudaMemcpyDeviceToHost, s));
+        ws.sync();
+    }
+    std::vector<u64> all;
+    exchange_allgather_u64(x, ws, mine, 2, all);
+    u64 n1 = 0, n2 = 0, a_bias = 0;
+    std::vector<u64> b_pos1(n), b_ord1(n), b_pos2(n), b_ord2(n);
+    for (int r = 0; r < n; ++r) {
+        if (r < rank) a_bias += all[2 * r];
+        n1 += all[2 * r]; n2 += all[2 * r + 1];
+        b_pos1[r] = all[2 * r] * 8; b_ord1[r] = all[2 * r]; b_pos2[r] = all[2 * r + 1] * 8; b_ord2[r] = all[2 * r + 1] * 2;
+    }
+    em.put_device_at(base + ".ord0", m, g0, ord0.p, ml);
+    // counts >= 256 are the exception (repeats): their planes and presence sets go to rank 0
+    DevBuf<u8> pos1_all, ord1_all, pos2_all, ord2_all;
+    if (n1) {
+        DevBuf<u64> ord1_pos(&ws, mine[0]), ord2_pos(&ws, mine[1]);
+        DevBuf<u8> ord1(&ws, mine[0]);
+        DevBuf<u16> ord2(&ws, mine[1]);
+        if (mine[0]) { vba_scatter_kernel<<<g, 256, 0, s>>>(counts, ml, r1.p, r2.p, ord1_pos.p, ord1.p, ord2_pos.p, ord2.p, g0, a_bias); ++ws.launches; }
+        exchange_gatherv_root(x, ws, ord1_pos.p, b_pos1, pos1_all);
+        exchange_gatherv_root(x, ws, ord1.p, b_ord1, ord1_all);
+        exchange_gatherv_root(x, ws, ord2_pos.p, b_pos2, pos2_all);
+        exchange_gatherv_root(x, ws, ord2.p, b_ord2, ord2_all);
+    }
+    if (rank == 0) {
+        em.put_device(base + ".ord1", ord1_all.p, n1);
+        em.put_device(base + ".ord2", ord2_all.p, n2 * 2);
+        const U128 n_ctor{m_est, 0};
+        const u64 m_frac = (u64)(m_est * 0.001);
+        emit_sparse_array(em, 8, pos1_all.p, n1, n_ctor, m_frac, U128{m, 0}, base + ".ord1p");
+        emit_sparse_array(em, 8, pos2_all.p, n2, n_ctor, m_frac, U128{n1, 0}, base + ".ord2p");
+    }
+}
+
+void emit_count_histogram_dist(Emitter& em, Exchange* x, const DistRun& run, const std::string& name) {
+    Workspace& ws = *em.ws;
+    cudaStream_t s = ws.stream;
+    const int n = run.n, rank = run.rank;
+    const u64 ml = run.off[rank + 1] - run.off[rank];
+    std::vector<u64> pairs;                                       // (count value, frequency) of this rank's slice
+    if (ml) {
+        DevBuf<u64> a(&ws, ml), b(&ws, ml);
+        GSB_CUDA_TRY(cudaMemcpyAsync(a.p, run.counts[rank], ml * 8, cudaMemcpyDeviceToDevice, s));
+        int passes = 0;
+        int where = sort_keys(ws, 8, 64, a.p, b.p, nullptr, nullptr, ml, nullptr, &passes);
+        ReducedRun rr; u64 distinct = 0;
+        reduce_sorted(ws, 8, where ? b.p : a.p, nullptr, ml, 1, rr, &distinct);
+        std::vector<u64> vals(rr.m), freq(rr.m);
+        GSB_CUDA_TRY(cudaMemcpyAsync(vals.data(), rr.keys.p, rr.m * 8, cudaMemcpyDeviceToHost, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(freq.data(), rr.counts.p, rr.m * 8, cudaMemcpyDeviceToHost, s));
+        ws.sync();
+        pairs.resize(2 * rr.m);
+        for (u64 i = 0; i < rr.m; ++i) { pairs[2 * i] = vals[i]; pairs[2 * i + 1] = freq[i]; }
+    }
+    std::vector<u64> sizes;
+    const u64 mine_n = pairs.size() / 2;
+    exchange_allgather_u64(x, ws, &mine_n, 1, sizes);
+    u64 cap = 1;
+    for (int r = 0; r < n; ++r) cap = std::max(cap, sizes[r]);
+    pairs.resize(2 * cap, 0);
+    std::vector<u64> all;
+    exchange_allgather_u64(x, ws, pairs.data(), 2 * cap, all);
+    if (rank == 0) {
+        std::map<u64, u64> hist;
+        for (int r = 0; r < n; ++r)
+            for (u64 i = 0; i < sizes[r]; ++i) hist[all[2 * cap * r + 2 * i]] += all[2 * cap * r + 2 * i + 1];
+        std::string text;
+        for (const auto& kv : hist) text += std::to_string(kv.first) + "\t" + std::to_string(kv.second) + "\n";
+        em.put_host(name, text.data(), text.size());
+    }
 }
 
 }  // namespace gsb

@@ -90,7 +90,6 @@ __global__ void bounds_kernel(const K* __restrict__ keys, u64 m, const u64* __re
     bounds[j + 1] = lo;
 }
 
-static const int kMaxRanks = 32;
 struct Splitters { u64 lo[kMaxRanks], hi[kMaxRanks]; int n; };      // n = number of splitters (ranks - 1)
 
 template <typename K>
@@ -206,28 +205,29 @@ __global__ void __launch_bounds__(kPartThreads) dest_scatter_kernel(const K* __r
 // Fused partition + transfer: the same tile-local grouping by destination, but each destination's
 // run is stored straight into that rank's receive window over NVLink (peer-mapped memory), at the
 // offset reserved for this source rank.  No staging copy, no collective on the data path.
-struct PeerWindows { void* base[kMaxRanks]; };   // window of rank r, already offset to this source's region
+struct PeerWindows { void* base[kMaxRanks]; u64* vbase[kMaxRanks]; };   // window of rank r, already offset to this source's region
 
-template <typename K>
-__global__ void __launch_bounds__(kPartThreads) dest_scatter_p2p_kernel(const K* __restrict__ keys, u64 n, Splitters sp, u64* __restrict__ cursor,
-                                                                       PeerWindows win) {
-    constexpr int TILE = kPartThreads * kPartItems;
+template <typename K, int ITEMS, bool HAS_VALUES>
+__global__ void __launch_bounds__(kPartThreads) dest_scatter_p2p_kernel(const K* __restrict__ keys, const u64* __restrict__ values, u64 n, Splitters sp,
+                                                                       u64* __restrict__ cursor, PeerWindows win) {
+    constexpr int TILE = kPartThreads * ITEMS;
     __shared__ u32 cnt_s[kMaxRanks], start_s[kMaxRanks + 1];
     __shared__ u64 base_s[kMaxRanks];
     __shared__ K stage[TILE];
+    __shared__ u64 stage_v[HAS_VALUES ? TILE : 1];
     __shared__ u8 stage_dest[TILE];
     const int lane = threadIdx.x & 31;
     int bits = 0; while ((1 << bits) <= sp.n) ++bits;
     for (u64 base = (u64)blockIdx.x * TILE; base < n; base += (u64)gridDim.x * TILE) {
         if (threadIdx.x < kMaxRanks) cnt_s[threadIdx.x] = 0;
         __syncthreads();
-        K k[kPartItems]; int d[kPartItems]; u32 slot[kPartItems];
+        K k[ITEMS]; u64 v[HAS_VALUES ? ITEMS : 1]; int d[ITEMS]; u32 slot[ITEMS];
 #pragma unroll
-        for (int i = 0; i < kPartItems; ++i) {
+        for (int i = 0; i < ITEMS; ++i) {
             const u64 idx = base + (u64)i * kPartThreads + threadIdx.x;
             d[i] = -1; slot[i] = 0;
             const bool ok = idx < n;
-            if (ok) { k[i] = keys[idx]; d[i] = dest_of(k[i], sp); }
+            if (ok) { k[i] = keys[idx]; d[i] = dest_of(k[i], sp); if (HAS_VALUES) v[i] = values[idx]; }
             const u32 peers = same_dest_lanes(ok ? d[i] : 0, bits, ok);
             const int leader = __ffs(peers) - 1;
             u32 before = 0;
@@ -244,13 +244,15 @@ __global__ void __launch_bounds__(kPartThreads) dest_scatter_p2p_kernel(const K*
         if (threadIdx.x <= sp.n) base_s[threadIdx.x] = cnt_s[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (u64)cnt_s[threadIdx.x]) : 0;
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < kPartItems; ++i)
-            if (d[i] >= 0) { const u32 p = start_s[d[i]] + slot[i]; stage[p] = k[i]; stage_dest[p] = (u8)d[i]; }
+        for (int i = 0; i < ITEMS; ++i)
+            if (d[i] >= 0) { const u32 p = start_s[d[i]] + slot[i]; stage[p] = k[i]; stage_dest[p] = (u8)d[i]; if (HAS_VALUES) stage_v[p] = v[i]; }
         __syncthreads();
         const u32 total = start_s[sp.n + 1];
         for (u32 j = threadIdx.x; j < total; j += kPartThreads) {
             const int r = stage_dest[j];
-            static_cast<K*>(win.base[r])[base_s[r] + (j - start_s[r])] = stage[j];
+            const u64 o = base_s[r] + (j - start_s[r]);
+            static_cast<K*>(win.base[r])[o] = stage[j];
+            if (HAS_VALUES) win.vbase[r][o] = stage_v[j];
         }
         __syncthreads();
     }
@@ -319,6 +321,112 @@ u64 exchange_sum(Exchange* x, Workspace& ws, u64 v) {
     GSB_CUDA_TRY(cudaMemcpyAsync(&out, d.p + 1, 8, cudaMemcpyDeviceToHost, ws.stream));
     ws.sync();
     return out;
+}
+
+// Collective: afterwards every rank's receive window holds at least the bytes that rank asked for and is
+// mapped (CUDA IPC) by every other rank.  Returns false -- on every rank alike -- if that is not possible
+// here (IPC not permitted, no peer access): the callers then use NCCL send/recv.
+static bool ensure_windows(Exchange* x, Workspace& ws, u64 need_bytes) {
+    const int n = x->n;
+    cudaStream_t s = ws.stream;
+    NcclApi& api = nccl();
+    if (need_bytes > x->recv_cap_bytes || !x->recv_buf) {
+        ws.sync();
+        if (x->recv_buf) GSB_CUDA_TRY(cudaFree(x->recv_buf));
+        x->recv_buf = nullptr;
+        x->recv_cap_bytes = need_bytes + need_bytes / 8 + (1u << 20);
+        GSB_CUDA_TRY(cudaMalloc((void**)&x->recv_buf, x->recv_cap_bytes));
+    }
+    struct Slot { cudaIpcMemHandle_t h; u64 cap; u64 ok; };
+    Slot mine_h;
+    memset(&mine_h, 0, sizeof(mine_h));
+    mine_h.ok = cudaIpcGetMemHandle(&mine_h.h, x->recv_buf) == cudaSuccess ? 1 : 0;
+    if (!mine_h.ok) cudaGetLastError();
+    mine_h.cap = x->recv_cap_bytes;
+    DevBuf<u8> h_mine(&ws, sizeof(Slot)), h_all(&ws, sizeof(Slot) * n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(h_mine.p, &mine_h, sizeof(Slot), cudaMemcpyHostToDevice, s));
+    check(api.AllGather(h_mine.p, h_all.p, sizeof(Slot), ncclUint8, x->comm, s), "ncclAllGather(ipc handles)");
+    std::vector<Slot> slots(n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(slots.data(), h_all.p, sizeof(Slot) * n, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    bool all_ok = true;
+    for (int r = 0; r < n; ++r) all_ok = all_ok && slots[r].ok;
+    if (x->peer_ptr.empty()) { x->peer_ptr.assign(n, nullptr); x->peer_handle.resize(n); x->peer_open.assign(n, 0); }
+    u64 local_ok = all_ok ? 1 : 0;
+    if (all_ok) {
+        for (int r = 0; r < n && local_ok; ++r) {
+            if (r == x->rank) { x->peer_ptr[r] = x->recv_buf; continue; }
+            if (x->peer_open[r] && memcmp(&x->peer_handle[r], &slots[r].h, sizeof(cudaIpcMemHandle_t)) == 0) continue;
+            if (x->peer_open[r]) { cudaIpcCloseMemHandle(x->peer_ptr[r]); x->peer_open[r] = 0; }
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, slots[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); local_ok = 0; break; }
+            x->peer_ptr[r] = (u8*)p; x->peer_handle[r] = slots[r].h; x->peer_open[r] = 1;
+        }
+    }
+    const u64 n_ok = exchange_sum(x, ws, local_ok);                 // every rank must take the same path
+    return n_ok == (u64)n;
+}
+
+static inline u64 align256(u64 v) { return (v + 255) & ~255ull; }
+void exchange_view(const Exchange* x, int key_bytes, const std::vector<u64>& totals, DistRun* out);
+
+int exchange_rank(const Exchange* x) { return x->rank; }
+int exchange_size(const Exchange* x) { return x->n; }
+
+void exchange_allgather_u64(Exchange* x, Workspace& ws, const u64* mine_host, size_t n_words, std::vector<u64>& all_host) {
+    const int n = x->n;
+    cudaStream_t s = ws.stream;
+    DevBuf<u64> mine(&ws, n_words), all(&ws, n_words * n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(mine.p, mine_host, n_words * 8, cudaMemcpyHostToDevice, s));
+    check(nccl().AllGather(mine.p, all.p, n_words, ncclUint64, x->comm, s), "ncclAllGather");
+    all_host.resize(n_words * n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(all_host.data(), all.p, all_host.size() * 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+}
+
+void exchange_barrier(Exchange* x, Workspace& ws) { (void)exchange_sum(x, ws, 0); }
+
+void exchange_gatherv_root(Exchange* x, Workspace& ws, const void* mine, const std::vector<u64>& bytes, DevBuf<u8>& out_root) {
+    const int n = x->n;
+    cudaStream_t s = ws.stream;
+    NcclApi& api = nccl();
+    if (x->rank == 0) {
+        u64 total = 0;
+        for (int r = 0; r < n; ++r) total += bytes[r];
+        out_root.reset(&ws, total);
+        if (bytes[0]) GSB_CUDA_TRY(cudaMemcpyAsync(out_root.p, mine, bytes[0], cudaMemcpyDeviceToDevice, s));
+        check(api.GroupStart(), "ncclGroupStart");
+        u64 off = bytes[0];
+        for (int r = 1; r < n; ++r) {
+            if (bytes[r]) check(api.Recv(out_root.p + off, bytes[r], ncclUint8, r, x->comm, s), "ncclRecv(gatherv)");
+            off += bytes[r];
+        }
+        check(api.GroupEnd(), "ncclGroupEnd");
+    } else {
+        check(api.GroupStart(), "ncclGroupStart");
+        if (bytes[x->rank]) check(api.Send(mine, bytes[x->rank], ncclUint8, 0, x->comm, s), "ncclSend(gatherv)");
+        check(api.GroupEnd(), "ncclGroupEnd");
+    }
+    ws.sync();
+}
+
+
+bool exchange_publish(Exchange* x, Workspace& ws, int key_bytes, const ReducedRun& run, DistRun* out) {
+    if (!x->p2p_usable) return false;
+    const int n = x->n;
+    cudaStream_t s = ws.stream;
+    const u64 need = align256(run.m * key_bytes) + run.m * 8;
+    if (!ensure_windows(x, ws, need)) { x->p2p_usable = false; return false; }
+    if (run.m) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(x->recv_buf, run.keys.p, run.m * key_bytes, cudaMemcpyDeviceToDevice, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(x->recv_buf + align256(run.m * key_bytes), run.counts.p, run.m * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    // the all-gather of the slice sizes doubles as the barrier: it completes here only after every rank
+    // has enqueued it, i.e. after that rank's copies above
+    std::vector<u64> m_all;
+    exchange_allgather_u64(x, ws, &run.m, 1, m_all);
+    exchange_view(x, key_bytes, m_all, out);
+    return true;
 }
 
 void exchange_runs(Exchange* x, Workspace& ws, int key_bytes, int key_bits, ReducedRun& run) {
@@ -477,44 +585,9 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
     bool done = false;
     if (x->p2p_usable) {
         // ---- peer-memory path: make sure every rank's window is big enough and mapped everywhere ----
-        if (total * key_bytes > x->recv_cap_bytes) {
-            ws.sync();
-            if (x->recv_buf) GSB_CUDA_TRY(cudaFree(x->recv_buf));
-            x->recv_cap_bytes = (total + total / 8 + 4096) * key_bytes;
-            GSB_CUDA_TRY(cudaMalloc((void**)&x->recv_buf, x->recv_cap_bytes));
-        }
-        lap("window (re)allocation");
-        struct Slot { cudaIpcMemHandle_t h; u64 cap; u64 ok; };
-        Slot mine_h;
-        memset(&mine_h, 0, sizeof(mine_h));
-        mine_h.ok = cudaIpcGetMemHandle(&mine_h.h, x->recv_buf) == cudaSuccess ? 1 : 0;
-        if (!mine_h.ok) cudaGetLastError();
-        mine_h.cap = x->recv_cap_bytes;
-        DevBuf<u8> h_mine(&ws, sizeof(Slot)), h_all(&ws, sizeof(Slot) * n);
-        GSB_CUDA_TRY(cudaMemcpyAsync(h_mine.p, &mine_h, sizeof(Slot), cudaMemcpyHostToDevice, s));
-        check(api.AllGather(h_mine.p, h_all.p, sizeof(Slot), ncclUint8, x->comm, s), "ncclAllGather(ipc handles)");
-        std::vector<Slot> slots(n);
-        GSB_CUDA_TRY(cudaMemcpyAsync(slots.data(), h_all.p, sizeof(Slot) * n, cudaMemcpyDeviceToHost, s));
-        ws.sync();
-        bool all_ok = true;
-        for (int r = 0; r < n; ++r) all_ok = all_ok && slots[r].ok;
-        if (x->peer_ptr.empty()) { x->peer_ptr.assign(n, nullptr); x->peer_handle.resize(n); x->peer_open.assign(n, 0); }
-        u64 local_ok = all_ok ? 1 : 0;
-        if (all_ok) {
-            for (int r = 0; r < n && local_ok; ++r) {
-                if (r == x->rank) { x->peer_ptr[r] = x->recv_buf; continue; }
-                if (x->peer_open[r] && memcmp(&x->peer_handle[r], &slots[r].h, sizeof(cudaIpcMemHandle_t)) == 0) continue;
-                if (x->peer_open[r]) { cudaIpcCloseMemHandle(x->peer_ptr[r]); x->peer_open[r] = 0; }
-                void* p = nullptr;
-                if (cudaIpcOpenMemHandle(&p, slots[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); local_ok = 0; break; }
-                x->peer_ptr[r] = (u8*)p; x->peer_handle[r] = slots[r].h; x->peer_open[r] = 1;
-            }
-        }
-        lap("ipc handles exchange + map");
-        // every rank must take the same path
-        const u64 n_ok = exchange_sum(x, ws, local_ok);
-        lap("agree on path");
-        if (n_ok == (u64)n) {
+        const bool windows_ok = ensure_windows(x, ws, total * key_bytes);
+        lap("windows: (re)allocation, ipc handles, agree on path");
+        if (windows_ok) {
             PeerWindows win;
             memset(&win, 0, sizeof(win));
             for (int r = 0; r < n; ++r) {
@@ -525,8 +598,8 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
             GSB_CUDA_TRY(cudaMemsetAsync(totals.p + kMaxRanks, 0, kMaxRanks * 8, s));
             GSB_CUDA_TRY(cudaEventRecord(e0, s));
             if (n_keys) {
-                if (key_bytes == 8) dest_scatter_p2p_kernel<u64><<<grid, kPartThreads, 0, s>>>((const u64*)keys, n_keys, sp, totals.p + kMaxRanks, win);
-                else dest_scatter_p2p_kernel<Key128><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, n_keys, sp, totals.p + kMaxRanks, win);
+                if (key_bytes == 8) dest_scatter_p2p_kernel<u64, kPartItems, false><<<grid, kPartThreads, 0, s>>>((const u64*)keys, nullptr, n_keys, sp, totals.p + kMaxRanks, win);
+                else dest_scatter_p2p_kernel<Key128, kPartItems, false><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, nullptr, n_keys, sp, totals.p + kMaxRanks, win);
                 ++ws.launches;
             }
             // barrier: when this all-reduce completes here, every rank's scatter kernel has finished
@@ -571,6 +644,97 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (timing) { timing->ms_all_to_all += ms; timing->bytes_sent_remote += sent_remote; timing->used_peer_memory = done; }
     *n_recv = total;
+}
+
+bool exchange_peer_memory_usable(const Exchange* x) { return x->p2p_usable; }
+
+// Range-partition UNSORTED (key,count) pairs by splitters sampled from all ranks and store each pair
+// straight into its owner's window over NVLink (keys at the start of the window, counts behind them at a
+// 256-byte boundary).  Afterwards this rank's window holds every pair of its key range, in arbitrary
+// order; totals[r] = number of pairs rank r received.  Collective; false (on every rank) if peer memory
+// cannot be used.
+bool exchange_pairs_p2p(Exchange* x, Workspace& ws, int key_bytes, const void* keys, const u64* counts, u64 n_pairs,
+                        u8** recv_keys, u64** recv_counts, std::vector<u64>* totals_out) {
+    if (!x->p2p_usable) return false;
+    const int n = x->n;
+    cudaStream_t s = ws.stream;
+    NcclApi& api = nccl();
+    constexpr int ITEMS = 4;
+    const u32 S = kExchangeSamplesPerRank;
+    const size_t slot = 2 * (size_t)S + 2;
+    DevBuf<u64> mine(&ws, slot), all(&ws, slot * n);
+    GSB_CUDA_TRY(cudaMemsetAsync(mine.p, 0, slot * 8, s));
+    if (key_bytes == 8) sample_strided_kernel<u64><<<(S + 255) / 256, 256, 0, s>>>((const u64*)keys, n_pairs, S, mine.p);
+    else sample_strided_kernel<Key128><<<(S + 255) / 256, 256, 0, s>>>((const Key128*)keys, n_pairs, S, mine.p);
+    ++ws.launches;
+    check(api.AllGather(mine.p, all.p, slot, ncclUint64, x->comm, s), "ncclAllGather(samples)");
+    std::vector<u64> h(slot * n);
+    GSB_CUDA_TRY(cudaMemcpyAsync(h.data(), all.p, h.size() * 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    std::vector<u64> samples;
+    for (int r = 0; r < n; ++r) {
+        const u64* p = h.data() + slot * r;
+        if (p[2 * S] == 0) continue;
+        samples.insert(samples.end(), p, p + 2 * (size_t)S);
+    }
+    Splitters sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.n = n - 1;
+    if (!samples.empty()) {
+        std::vector<u64> split(2 * (size_t)(n - 1));
+        plan_splitters(samples.data(), samples.size() / 2, n, split.data());
+        for (int j = 0; j < n - 1; ++j) { sp.lo[j] = split[2 * j]; sp.hi[j] = split[2 * j + 1]; }
+    }
+    DevBuf<u64> totals(&ws, 2 * (size_t)kMaxRanks);
+    GSB_CUDA_TRY(cudaMemsetAsync(totals.p, 0, totals.bytes(), s));
+    const u64 tiles = (n_pairs + kPartThreads * ITEMS - 1) / (kPartThreads * ITEMS);
+    const int grid = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)ws.sm_count * 8));
+    if (n_pairs) {
+        if (key_bytes == 8) dest_count_kernel<u64><<<grid, kPartThreads, 0, s>>>((const u64*)keys, n_pairs, sp, totals.p);
+        else dest_count_kernel<Key128><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, n_pairs, sp, totals.p);
+        ++ws.launches;
+    }
+    std::vector<u64> send_cnt(kMaxRanks, 0);
+    GSB_CUDA_TRY(cudaMemcpyAsync(send_cnt.data(), totals.p, kMaxRanks * 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    std::vector<u64> cnt;                                           // cnt[src][dst]
+    exchange_allgather_u64(x, ws, send_cnt.data(), n, cnt);
+    std::vector<u64> total(n, 0);
+    for (int src = 0; src < n; ++src) for (int dst = 0; dst < n; ++dst) total[dst] += cnt[(size_t)src * n + dst];
+    const u64 mine_total = total[x->rank];
+    if (!ensure_windows(x, ws, align256(mine_total * key_bytes) + mine_total * 8)) { x->p2p_usable = false; return false; }
+    PeerWindows win;
+    memset(&win, 0, sizeof(win));
+    for (int r = 0; r < n; ++r) {
+        u64 before_me = 0;
+        for (int src = 0; src < x->rank; ++src) before_me += cnt[(size_t)src * n + r];
+        win.base[r] = x->peer_ptr[r] + before_me * key_bytes;
+        win.vbase[r] = (u64*)(x->peer_ptr[r] + align256(total[r] * key_bytes)) + before_me;
+    }
+    GSB_CUDA_TRY(cudaMemsetAsync(totals.p + kMaxRanks, 0, kMaxRanks * 8, s));
+    if (n_pairs) {
+        if (key_bytes == 8) dest_scatter_p2p_kernel<u64, ITEMS, true><<<grid, kPartThreads, 0, s>>>((const u64*)keys, counts, n_pairs, sp, totals.p + kMaxRanks, win);
+        else dest_scatter_p2p_kernel<Key128, ITEMS, true><<<grid, kPartThreads, 0, s>>>((const Key128*)keys, counts, n_pairs, sp, totals.p + kMaxRanks, win);
+        ++ws.launches;
+    }
+    exchange_barrier(x, ws);                                        // every rank's stores have landed
+    *recv_keys = x->recv_buf;
+    *recv_counts = (u64*)(x->recv_buf + align256(mine_total * key_bytes));
+    *totals_out = total;
+    return true;
+}
+
+// The global view of slices that already sit in the windows (layout of exchange_pairs_p2p / exchange_publish).
+void exchange_view(const Exchange* x, int key_bytes, const std::vector<u64>& totals, DistRun* out) {
+    const int n = x->n;
+    out->n = n; out->rank = x->rank;
+    out->off[0] = 0;
+    for (int r = 0; r < n; ++r) {
+        out->off[r + 1] = out->off[r] + totals[r];
+        out->keys[r] = x->peer_ptr[r];
+        out->counts[r] = (const u64*)(x->peer_ptr[r] + align256(totals[r] * key_bytes));
+    }
+    for (int r = n; r < kMaxRanks; ++r) { out->keys[r] = nullptr; out->counts[r] = nullptr; out->off[r + 1] = out->off[n]; }
 }
 
 void exchange_gather(Exchange* x, Workspace& ws, int key_bytes, ReducedRun& run) {

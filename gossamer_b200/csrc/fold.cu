@@ -170,20 +170,41 @@ u64 fold_double_self_rc(Workspace& ws, int key_bytes, int w, const void* keys, u
     return host;
 }
 
-void unfold_run(Workspace& ws, int key_bytes, int key_bits, int w, ReducedRun& run) {
-    const u64 m = run.m;
-    if (!m) return;
+u64 unfold_append_rc(Workspace& ws, int key_bytes, int w, const void* keys, const u64* counts, u64 m, void* out_keys, u64* out_counts) {
+    if (!m) return 0;
     cudaStream_t s = ws.stream;
-    DevBuf<u8> rk(&ws, m * key_bytes), rk_alt(&ws, m * key_bytes);
-    DevBuf<u64> rc(&ws, m), rc_alt(&ws, m), cursor(&ws, 1);
+    DevBuf<u64> cursor(&ws, 1);
     GSB_CUDA_TRY(cudaMemsetAsync(cursor.p, 0, 8, s));
     const unsigned tiles = (unsigned)((m + kFoldThreads * kFoldItems - 1) / (kFoldThreads * kFoldItems));
-    if (key_bytes == 8) unfold_rc_kernel<u64><<<tiles, kFoldThreads, 0, s>>>((const u64*)run.keys.p, run.counts.p, m, w, (u64*)rk.p, rc.p, cursor.p);
-    else unfold_rc_kernel<Key128><<<tiles, kFoldThreads, 0, s>>>((const Key128*)run.keys.p, run.counts.p, m, w, (Key128*)rk.p, rc.p, cursor.p);
+    if (key_bytes == 8) unfold_rc_kernel<u64><<<tiles, kFoldThreads, 0, s>>>((const u64*)keys, counts, m, w, (u64*)out_keys, out_counts, cursor.p);
+    else unfold_rc_kernel<Key128><<<tiles, kFoldThreads, 0, s>>>((const Key128*)keys, counts, m, w, (Key128*)out_keys, out_counts, cursor.p);
     ++ws.launches;
     u64 n_rc = 0;
     GSB_CUDA_TRY(cudaMemcpyAsync(&n_rc, cursor.p, 8, cudaMemcpyDeviceToHost, s));
     ws.sync();
+    return n_rc;
+}
+
+void unfold_run(Workspace& ws, int key_bytes, int key_bits, int w, ReducedRun& run, bool sorted_input) {
+    const u64 m = run.m;
+    if (!m) return;
+    cudaStream_t s = ws.stream;
+    if (!sorted_input) {
+        // U = run ++ rc(run), then one radix sort of the pairs by the full key
+        DevBuf<u8> uk(&ws, 2 * m * key_bytes), uk_alt(&ws, 2 * m * key_bytes);
+        DevBuf<u64> uc(&ws, 2 * m), uc_alt(&ws, 2 * m);
+        GSB_CUDA_TRY(cudaMemcpyAsync(uk.p, run.keys.p, m * key_bytes, cudaMemcpyDeviceToDevice, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(uc.p, run.counts.p, m * 8, cudaMemcpyDeviceToDevice, s));
+        const u64 n_rc = unfold_append_rc(ws, key_bytes, w, run.keys.p, run.counts.p, m, uk.p + m * key_bytes, uc.p + m);
+        const int where = sort_keys(ws, key_bytes, key_bits, uk.p, uk_alt.p, uc.p, uc_alt.p, m + n_rc, nullptr, nullptr);
+        run.keys = std::move(where ? uk_alt : uk);
+        run.counts = std::move(where ? uc_alt : uc);
+        run.m = m + n_rc;
+        return;
+    }
+    DevBuf<u8> rk(&ws, m * key_bytes), rk_alt(&ws, m * key_bytes);
+    DevBuf<u64> rc(&ws, m), rc_alt(&ws, m);
+    const u64 n_rc = unfold_append_rc(ws, key_bytes, w, run.keys.p, run.counts.p, m, rk.p, rc.p);
     if (!n_rc) return;                                           // every key is its own reverse complement
     const int where = sort_keys(ws, key_bytes, key_bits, rk.p, rk_alt.p, rc.p, rc_alt.p, n_rc, nullptr, nullptr);
     DevBuf<u8> out_keys(&ws, (m + n_rc) * key_bytes);

@@ -387,7 +387,7 @@ static const int kExItems = 4;                                  // stream positi
 // PASSES > 0 unrolls the histogram update (7 = k 25, 8 = k 31, 14 = k 55); 0 = run-time count.
 template <typename K, int MODE, int PASSES>
 __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restrict__ codes, const u32* __restrict__ valid,
-                                                             u64 p_begin, u64 p_end, int w, int passes_rt,
+                                                             u64 p_begin, u64 p_end, int w, int passes_rt, int mix,
                                                              K* __restrict__ out, u64* __restrict__ cursor, u64 capacity,
                                                              u64* __restrict__ digit_hist /* [passes][256] */, IngestStatus* st) {
     typedef KeyOps<K> KO;
@@ -423,6 +423,8 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
                     const K r = WO::rc(x[it], w);
                     if (MODE == GSB_KIND_GRAPH) {               // fold the two strands
                         if (KO::lt(r, x[it])) x[it] = r;
+                        else if (KO::eq(r, x[it])) atomicAdd(&st->n_self_rc, 1ull);   // rare: lets the reduce skip its self-complement test
+                        if (mix) x[it] = key_mix(x[it]);        // instances will only be grouped, not ordered (sort.cu)
                     } else {                                    // position_type::normalize, src/RankSelect.hh:126-140
                         const u64 h0 = WO::hash(x[it]), h1 = WO::hash(r);
                         if (h0 > h1 || (h0 == h1 && KO::lt(r, x[it]))) x[it] = r;
@@ -543,34 +545,34 @@ void ingest_save_carry(const u64* codes, const u32* valid, u64 n_sym_total, u32 
 }
 
 template <typename K, int PASSES>
-static void launch_extract_p(int kind, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
+static void launch_extract_p(int kind, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes, int mix,
                              K* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s) {
     const u64 span = (u64)kExThreads * kExItems;
     u64 tiles = (p_end - p_begin + span - 1) / span;
     int grid = (int)(tiles < (u64)sm_count * 8 ? tiles : (u64)sm_count * 8);
     size_t smem = (size_t)passes * 256 * sizeof(u32);
     if (kind == GSB_KIND_GRAPH)
-        extract_kernel<K, GSB_KIND_GRAPH, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+        extract_kernel<K, GSB_KIND_GRAPH, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st);
     else
-        extract_kernel<K, GSB_KIND_KMERSET, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st);
+        extract_kernel<K, GSB_KIND_KMERSET, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st);
 }
 
 template <typename K>
-static void launch_extract(int kind, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
+static void launch_extract(int kind, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes, int mix,
                            K* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s) {
     switch (passes) {
-        case 7: launch_extract_p<K, 7>(kind, codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st, sm_count, s); break;
-        case 8: launch_extract_p<K, 8>(kind, codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st, sm_count, s); break;
-        case 14: launch_extract_p<K, 14>(kind, codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st, sm_count, s); break;
-        default: launch_extract_p<K, 0>(kind, codes, valid, p_begin, p_end, w, passes, out, cursor, capacity, digit_hist, st, sm_count, s); break;
+        case 7: launch_extract_p<K, 7>(kind, codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st, sm_count, s); break;
+        case 8: launch_extract_p<K, 8>(kind, codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st, sm_count, s); break;
+        case 14: launch_extract_p<K, 14>(kind, codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st, sm_count, s); break;
+        default: launch_extract_p<K, 0>(kind, codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st, sm_count, s); break;
     }
 }
 
-void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
+void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes, int mix,
                     void* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s, u64* launches) {
     if (p_end <= p_begin) return;
-    if (key_bytes == 8) launch_extract<u64>(kind, codes, valid, p_begin, p_end, w, passes, (u64*)out, cursor, capacity, digit_hist, st, sm_count, s);
-    else launch_extract<Key128>(kind, codes, valid, p_begin, p_end, w, passes, (Key128*)out, cursor, capacity, digit_hist, st, sm_count, s);
+    if (key_bytes == 8) launch_extract<u64>(kind, codes, valid, p_begin, p_end, w, passes, mix, (u64*)out, cursor, capacity, digit_hist, st, sm_count, s);
+    else launch_extract<Key128>(kind, codes, valid, p_begin, p_end, w, passes, mix, (Key128*)out, cursor, capacity, digit_hist, st, sm_count, s);
     ++*launches;
 }
 

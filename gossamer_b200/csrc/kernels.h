@@ -28,6 +28,7 @@ struct IngestStatus {
     int fastq_irregular;
     u64 error_line;
     u64 n_reads;
+    u64 n_self_rc;             // graph mode: windows that are their own reverse complement (rare; see fold.cu)
 };
 
 // Device memory for one stream: a caching allocator.  Freed blocks are kept in size-ordered free
@@ -82,7 +83,8 @@ void ingest_symbol_offsets(const u32* nsym, u32* sym_off, u32 n_lines, u32* tota
 void ingest_pack(const u8* text, u64 text_bytes, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
                  const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, cudaStream_t s, u64* launches);
 void ingest_save_carry(const u64* codes, const u32* valid, u64 n_sym_total, u32 want, u8* carry_out, cudaStream_t s, u64* launches);
-void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes,
+// mix != 0 (graph mode only): the folded key is stored bit-mixed (key_mix, common.cuh)
+void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes, int mix,
                     void* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s, u64* launches);
 
 // ---- sort.cu ---------------------------------------------------------------------------------
@@ -107,8 +109,9 @@ u64 sort_scan_tmp_elems(u64 n);
 // Full sort of n keys (optionally with a u64 payload).  `a` holds the input; `b` is scratch of the
 // same size.  Digit histograms are computed here unless hist_dev (already accumulated, [passes][256])
 // is given.  Returns 0 if the result is in a, 1 if in b.  passes_run gets the number of sweeps.
+// Only the digits [digit_begin, digit_end) are swept (default: all): a stable LSD sort on those bits.
 int sort_keys(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64* va, u64* vb, u64 n,
-              const u64* hist_dev, int* passes_run, double* sweep_ms = nullptr);
+              const u64* hist_dev, int* passes_run, double* sweep_ms = nullptr, int digit_begin = 0, int digit_end = -1);
 
 // sorted keys (+ optional weights) -> distinct keys and summed counts, min-count filtered.
 // Outputs are freshly allocated; *m_distinct is the count before the filter.
@@ -123,13 +126,28 @@ struct ReducedRun {
 void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* weights, u64 n, u64 min_count,
                    ReducedRun& out, u64* m_distinct, int fold_w = 0, u64* n_self_rc = nullptr);
 
+// keys[i] = key_unmix(keys[i])
+void sort_unmix_inplace(int key_bytes, void* keys, u64 n, int sm_count, cudaStream_t s, u64* launches);
+// Counting from a PARTIAL sort (sort.cu, "counting from a partial sort"): `grouped` holds bit-MIXED keys (key_mix)
+// that have been LSD-sorted on their low group_bits bits only; the outputs are the real keys.  Produces the min-count-filtered (key, count) pairs in ARBITRARY order (the caller sorts the
+// survivors by the full key); fold_w as in reduce_sorted.  out_keys_scratch: room for n keys.  Returns false, with
+// nothing produced, if too many groups hold several keys or too many keys survive -- the caller then finishes the
+// sort (digits group_bits/8 .. P) and uses reduce_sorted.
+bool reduce_groups(Workspace& ws, int key_bytes, int key_bits, const void* grouped, u64 n, int group_bits, u64 min_count, int fold_w,
+                   void* out_keys_scratch, ReducedRun& out, u64* m_distinct, u64* n_self_rc);
+
 // ---- fold.cu ---------------------------------------------------------------------------------
 // Strand folding (graph mode): instances are counted as min(x, rc x); these restore both strands.
 // merged, still folded run with raw occurrence counts -> doubled counts for self-complementary keys;
 // returns how many of the m keys are self-complementary
 u64 fold_double_self_rc(Workspace& ws, int key_bytes, int w, const void* keys, u64* counts, u64 m);
+// appends (rc y, count) of every key y of the run that is not self-complementary to out_* (room for m pairs,
+// arbitrary order); returns how many were written
+u64 unfold_append_rc(Workspace& ws, int key_bytes, int w, const void* keys, const u64* counts, u64 m, void* out_keys, u64* out_counts);
 // folded, filtered run (final counts) -> the full sorted run: every key y plus rc(y) with the same count
-void unfold_run(Workspace& ws, int key_bytes, int key_bits, int w, ReducedRun& run);
+// sorted_input = false: the run is in arbitrary order (reduce_groups): run ++ rc(run) is sorted as a whole instead
+// of sorting rc(run) and merging
+void unfold_run(Workspace& ws, int key_bytes, int key_bits, int w, ReducedRun& run, bool sorted_input = true);
 // two sorted runs with disjoint key sets -> one sorted run (merge path)
 void merge_disjoint_runs(Workspace& ws, int key_bytes, const void* ka, const u64* ca, u64 na, const void* kb, const u64* cb, u64 nb,
                          void* out_keys, u64* out_counts);
@@ -145,6 +163,9 @@ struct Emitter {
     void put_host(const std::string& name, const void* data, u64 len);
     // whole file = optional host prefix that overrides the first prefix_len bytes + device payload
     void put_device(const std::string& name, const void* dev, u64 len, const void* host_prefix = nullptr, u64 prefix_len = 0);
+    // one piece of a file of `total` bytes (multi-GPU emission: every rank hands over its own pieces)
+    void put_device_at(const std::string& name, u64 total, u64 offset, const void* dev, u64 len);
+    void put_host_at(const std::string& name, u64 total, u64 offset, const void* data, u64 len);
 };
 
 struct U128 { u64 lo, hi; };

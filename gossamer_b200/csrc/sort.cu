@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
     K* keys_s = reinterpret_cast<K*>(smem_raw);                                   // [TILE]
     u32* warp_ofs = reinterpret_cast<u32*>(smem_raw + (size_t)TILE * sizeof(K));   // [WARPS][256] counts, then running offsets
     u64* gofs = reinterpret_cast<u64*>(warp_ofs + WARPS * 256);                    // [256]
-    u32* vpos_s = reinterpret_cast<u32*>(gofs + 256);                              // [TILE] only with values: source slot of each sorted key
+    u64* vals_s = gofs + 256;                                                     // [TILE] only with values: the payloads, reordered like the keys
     __shared__ u32 tile_s;
     __shared__ u32 scan_s[THREADS / 32 + 1];
 
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
             if (ok) {
                 const u32 pos = before + __popc(peers & lt_mask);
                 keys_s[pos] = key[i];
-                if (HAS_VALUES) vpos_s[pos] = wbase + i * 32;
+                if (HAS_VALUES) vals_s[pos] = vin[base + wbase + i * 32];   // coalesced load, reordered in shared memory
             }
         }
     } else {
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
             if (wbase + i * 32 < tile_n) {
                 const u32 pos = my_ofs[KO::digit(key[i], shift)] + rank[i];
                 keys_s[pos] = key[i];
-                if (HAS_VALUES) vpos_s[pos] = wbase + i * 32;
+                if (HAS_VALUES) vals_s[pos] = vin[base + wbase + i * 32];
             }
         }
     }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __rest
             const K k = keys_s[j];
             const u64 dst = (ablate & 1) ? (base + j) : gofs[KO::digit(k, shift)] + j;
             out[dst] = k;
-            if (HAS_VALUES) vout[dst] = vin[base + vpos_s[j]];
+            if (HAS_VALUES) vout[dst] = vals_s[j];
         }
     }
 }
@@ -250,7 +250,7 @@ template <typename K, typename LB, int THREADS, int ITEMS, bool HAS_VALUES, int 
 static void launch_onesweep(const void* in, void* out, const u64* vin, u64* vout, u64 n, int shift, const u64* digit_base,
                             void* lookback, u32* ticket, cudaStream_t s) {
     constexpr int TILE = THREADS * ITEMS;
-    const size_t smem = (size_t)TILE * sizeof(K) + (size_t)(THREADS / 32) * 256 * 4 + 256 * 8 + (HAS_VALUES ? (size_t)TILE * 4 : 0);
+    const size_t smem = (size_t)TILE * sizeof(K) + (size_t)(THREADS / 32) * 256 * 4 + 256 * 8 + (HAS_VALUES ? (size_t)TILE * 8 : 0);
     static bool configured = false;
     auto kern = onesweep_kernel<K, LB, THREADS, ITEMS, HAS_VALUES, MINB, MODE, LBW>;
     if (!configured) {
@@ -483,6 +483,199 @@ __global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// counting from a PARTIAL sort
+// ------------------------------------------------------------------------------------------
+// Equal keys agree in every digit, so after LSD sweeps over only the low `gb` bits all instances of a key
+// are already contiguous -- inside the "group" of keys that share those bits.  With gb >= log2(n) + 12 a
+// group almost always holds ONE distinct key (expected number of colliding pairs n^2 / 2^(gb+1)); then the
+// group is a run and its length is the count, exactly as after a full sort, and the remaining sweeps over
+// n instances are not needed: only the survivors of the min-count filter (a few % of the instances when
+// sequencing errors dominate the distinct keys) are sorted by the full key afterwards, together with their
+// reverse complements (fold.cu).  Groups that do hold different keys are copied out whole and go through
+// the full sort + run-length reduce ("impure" path), so the result never depends on the choice of gb.
+//
+// The instances are stored bit-MIXED (key_mix, common.cuh) when this path is taken, so that the low bits depend
+// on the whole window: with the raw key, a true k-mer and its error variants whose error lies in the high bases
+// would share their low bits and nearly every group would hold several keys.  Outputs are un-mixed.
+//
+// One streaming pass, output order arbitrary (warp-aggregated appends): the full-key sort that follows
+// makes the final order deterministic because the surviving keys are distinct.
+template <typename K> __device__ __forceinline__ bool same_group(const K& a, const K& b, int gb);
+template <> __device__ __forceinline__ bool same_group<u64>(const u64& a, const u64& b, int gb) {
+    return gb >= 64 ? a == b : ((a ^ b) << (64 - gb)) == 0;
+}
+template <> __device__ __forceinline__ bool same_group<Key128>(const Key128& a, const Key128& b, int gb) {
+    if (gb <= 64) return gb == 64 ? a.lo == b.lo : ((a.lo ^ b.lo) << (64 - gb)) == 0;
+    return a.lo == b.lo && (gb >= 128 ? a.hi == b.hi : ((a.hi ^ b.hi) << (128 - gb)) == 0);
+}
+
+// first index after the group of keys[known] (keys[known] is in the group of `key`): gallop, then bisect
+template <typename K>
+__device__ __forceinline__ u64 group_end(const K* __restrict__ keys, u64 n, u64 known, const K& key, int gb) {
+    u64 a = known, step = 1;
+    while (a + step < n && same_group<K>(keys[a + step], key, gb)) { a += step; step <<= 1; }
+    u64 lo = a + 1, hi = a + step < n ? a + step : n;
+    while (lo < hi) { const u64 mid = lo + ((hi - lo) >> 1); if (same_group<K>(keys[mid], key, gb)) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// any set bit at tile-relative positions [a, b) of a bit vector
+__device__ __forceinline__ bool bits_any(const u32* bits, u32 a, u32 b) {
+    if (a >= b) return false;
+    const u32 wa = a >> 5, wb = (b - 1) >> 5;
+    for (u32 w = wa; w <= wb; ++w) {
+        u32 mask = 0xffffffffu;
+        if (w == wa) mask &= 0xffffffffu << (a & 31);
+        if (w == wb && (b & 31)) mask &= (1u << (b & 31)) - 1;
+        if (bits[w] & mask) return true;
+    }
+    return false;
+}
+
+// ctr[0] survivors appended, ctr[1] impure elements appended, ctr[2] pure groups (= distinct keys in them),
+// ctr[3] pure groups whose key is its own reverse complement.  Appends beyond a capacity are dropped (the
+// counters still advance): the host then falls back to the full sort.
+template <typename K>
+__global__ void __launch_bounds__(kRleThreads, 3) rle_groups_kernel(const K* __restrict__ keys, u64 n, int gb, u64 min_count, int fold_w,
+                                                                    K* __restrict__ out_keys, u64* __restrict__ out_counts, u64 out_cap,
+                                                                    K* __restrict__ imp_keys, u64 imp_cap, u64* __restrict__ ctr) {
+    typedef KeyOps<K> KO;
+    constexpr int TILE = kRleThreads * kRleItems;
+    constexpr int WORDS = TILE / 32;
+    __shared__ u32 head_bits[WORDS], imp_bits[WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 tbase = (u64)blockIdx.x * TILE;
+    const u64 wbase = tbase + (u64)warp * 32 * kRleItems;
+    const u64 tile_end = tbase + TILE < n ? tbase + TILE : n;
+    const u32 lt = (1u << lane) - 1;
+    K k[kRleItems];
+    u32 headb[kRleItems];
+    K carry = KO::make(0, 0);
+    if (wbase > 0 && wbase < n) carry = keys[wbase - 1];
+#pragma unroll
+    for (int i = 0; i < kRleItems; ++i) {
+        const u64 idx = wbase + (u64)i * 32 + lane;
+        k[i] = idx < n ? keys[idx] : KO::make(0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < kRleItems; ++i) {
+        const u64 idx = wbase + (u64)i * 32 + lane;
+        const bool ok = idx < n;
+        const K& last_src = i ? k[i ? i - 1 : 0] : carry;
+        u64 up_lo = __shfl_up_sync(0xffffffffu, KO::lo(k[i]), 1), up_hi = 0;
+        u64 last_lo = __shfl_sync(0xffffffffu, KO::lo(last_src), i ? 31 : 0), last_hi = 0;
+        if (sizeof(K) == 16) {
+            up_hi = __shfl_up_sync(0xffffffffu, KO::hi(k[i]), 1);
+            last_hi = __shfl_sync(0xffffffffu, KO::hi(last_src), i ? 31 : 0);
+        }
+        const K prev = KO::make(lane ? up_lo : last_lo, lane ? up_hi : last_hi);
+        const bool ghead = ok && (idx == 0 || !same_group<K>(k[i], prev, gb));
+        const bool imp = ok && !ghead && !KO::eq(k[i], prev);      // a different key inside a group
+        headb[i] = __ballot_sync(0xffffffffu, ghead);
+        const u32 impb = __ballot_sync(0xffffffffu, imp);
+        if (lane == 0) { head_bits[warp * kRleItems + i] = headb[i]; imp_bits[warp * kRleItems + i] = impb; }
+    }
+    __syncthreads();
+    u32 pure_groups = 0, self_groups = 0;
+    u32 keepb[kRleItems];
+    u64 cnt[kRleItems];                                           // pure group: its count; impure group: its length
+    u32 wtot = 0, impmask = 0;
+    u64 my_imp = 0;
+#pragma unroll
+    for (int i = 0; i < kRleItems; ++i) {
+        bool keep = false;
+        cnt[i] = 0;
+        if ((headb[i] >> lane) & 1u) {
+            const u64 idx = wbase + (u64)i * 32 + lane;
+            int w = warp * kRleItems + i;
+            u32 m = lane == 31 ? 0u : (head_bits[w] & ~((2u << lane) - 1));
+            while (!m && ++w < WORDS) m = head_bits[w];
+            const u64 end = m ? tbase + (u64)w * 32 + (__ffs(m) - 1)
+                              : (tile_end < n ? group_end<K>(keys, n, tile_end - 1, k[i], gb) : n);
+            const u64 end_in = end < tile_end ? end : tile_end;
+            bool impure = bits_any(imp_bits, (u32)(idx + 1 - tbase), (u32)(end_in - tbase));
+            for (u64 j = tile_end; !impure && j < end; ++j) impure = !KO::eq(keys[j], k[i]);
+            const u64 len = end - idx;
+            k[i] = key_unmix(k[i]);                                 // the real key from here on
+            if (impure) {
+                impmask |= 1u << i;
+                cnt[i] = len;
+                my_imp += len;
+            } else {
+                ++pure_groups;
+                const bool self_rc = fold_w && KO::eq(key_rc(k[i], fold_w), k[i]);
+                self_groups += self_rc ? 1u : 0u;
+                cnt[i] = self_rc ? 2 * len : len;                   // both strands of a self-complementary key are this key
+                keep = cnt[i] >= min_count;
+            }
+        }
+        keepb[i] = __ballot_sync(0xffffffffu, keep);
+        wtot += __popc(keepb[i]);
+    }
+    // ONE append per tile and cursor: warp-level (survivors) or per-group (impure elements) atomics on a single
+    // address serialised the whole kernel (6 ms resp. 2 ms for 198 M keys)
+    __shared__ u32 warp_tot[kRleThreads / 32];
+    __shared__ u64 imp_warp_tot[kRleThreads / 32];
+    __shared__ u64 base_s, imp_base_s;
+    __shared__ u32 stat_s[2];
+    if (threadIdx.x < 2) stat_s[threadIdx.x] = 0;
+    if (lane == 0) warp_tot[warp] = wtot;
+    u64 imp_inc = my_imp;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, imp_inc, o);
+        if (lane >= o) imp_inc += t;
+    }
+    if (lane == 31) imp_warp_tot[warp] = imp_inc;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        pure_groups += __shfl_xor_sync(0xffffffffu, pure_groups, o);
+        self_groups += __shfl_xor_sync(0xffffffffu, self_groups, o);
+    }
+    if (lane == 0) {
+        if (pure_groups) atomicAdd(&stat_s[0], pure_groups);
+        if (self_groups) atomicAdd(&stat_s[1], self_groups);
+    }
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+#pragma unroll
+        for (int w = 0; w < kRleThreads / 32; ++w) { const u32 c = warp_tot[w]; warp_tot[w] = tot; tot += c; }
+        base_s = tot ? atomicAdd(&ctr[0], (u64)tot) : 0;
+        u64 itot = 0;
+#pragma unroll
+        for (int w = 0; w < kRleThreads / 32; ++w) { const u64 c = imp_warp_tot[w]; imp_warp_tot[w] = itot; itot += c; }
+        imp_base_s = itot ? atomicAdd(&ctr[1], itot) : 0;
+    }
+    __syncthreads();
+    if (impmask) {                                                // copy out the groups that hold several keys (un-mixed)
+        u64 pos = imp_base_s + imp_warp_tot[warp] + (imp_inc - my_imp);
+#pragma unroll
+        for (int i = 0; i < kRleItems; ++i) {
+            if ((impmask >> i) & 1u) {
+                const u64 idx = wbase + (u64)i * 32 + lane;
+                for (u64 q = 0; q < cnt[i]; ++q)
+                    if (pos + q < imp_cap) imp_keys[pos + q] = key_unmix(keys[idx + q]);
+                pos += cnt[i];
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (stat_s[0]) atomicAdd(&ctr[2], (u64)stat_s[0]);
+        if (stat_s[1]) atomicAdd(&ctr[3], (u64)stat_s[1]);
+    }
+    u64 j = base_s + warp_tot[warp];
+#pragma unroll
+    for (int i = 0; i < kRleItems; ++i) {
+        if ((keepb[i] >> lane) & 1u) {
+            const u64 o = j + __popc(keepb[i] & lt);
+            if (o < out_cap) { out_keys[o] = k[i]; out_counts[o] = cnt[i]; }
+        }
+        j += __popc(keepb[i]);
+    }
+}
+
 u64 rle_tiles(u64 n) { return (n + kRleThreads * kRleItems - 1) / (kRleThreads * kRleItems); }
 u64 rle_lookback_bytes(u64 n) { return rle_tiles(n) * 8 + 256; }
 
@@ -607,8 +800,9 @@ void sort_fill_random(int key_bytes, void* keys, u64 n, int key_bits, u64 seed, 
 }
 
 int sort_keys(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64* va, u64* vb, u64 n,
-              const u64* hist_dev, int* passes_run, double* sweep_ms) {
+              const u64* hist_dev, int* passes_run, double* sweep_ms, int digit_begin, int digit_end) {
     const int passes = (key_bits + 7) / 8;
+    if (digit_end < 0 || digit_end > passes) digit_end = passes;
     if (passes_run) *passes_run = 0;
     if (n == 0 || passes == 0) return 0;
     cudaStream_t s = ws.stream;
@@ -629,7 +823,7 @@ int sort_keys(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64*
     int cur = 0, run = 0;
     std::vector<cudaEvent_t> ev;
     if (sweep_ms) { ev.resize(2 * (size_t)passes); for (auto& e : ev) GSB_CUDA_TRY(cudaEventCreate(&e)); }
-    for (int p = 0; p < passes; ++p) {
+    for (int p = digit_begin; p < digit_end; ++p) {
         bool constant = false;
         for (int d = 0; d < 256; ++d) if (h[(size_t)p * 256 + d] == n) { constant = true; break; }
         if (constant) continue;                                // every key has the same digit here: the pass is the identity
@@ -705,6 +899,79 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
         out.keys = std::move(fkeys); out.counts = std::move(fcounts); out.m = k2;
     }
     ws.sync();
+}
+
+template <typename K>
+__global__ void unmix_kernel(K* keys, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) keys[i] = key_unmix(keys[i]);
+}
+
+void sort_unmix_inplace(int key_bytes, void* keys, u64 n, int sm_count, cudaStream_t s, u64* launches) {
+    if (!n) return;
+    const u64 blocks = (n + 255) / 256;
+    const int grid = (int)(blocks < (u64)sm_count * 16 ? blocks : (u64)sm_count * 16);
+    if (key_bytes == 8) unmix_kernel<u64><<<grid, 256, 0, s>>>((u64*)keys, n);
+    else unmix_kernel<Key128><<<grid, 256, 0, s>>>((Key128*)keys, n);
+    ++*launches;
+}
+
+bool reduce_groups(Workspace& ws, int key_bytes, int key_bits, const void* grouped, u64 n, int group_bits, u64 min_count, int fold_w,
+                   void* out_keys_scratch, ReducedRun& out, u64* m_distinct, u64* n_self_rc) {
+    cudaStream_t s = ws.stream;
+    out.m = 0;
+    *m_distinct = 0; *n_self_rc = 0;
+    if (n == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return true; }
+    if (min_count < 1) min_count = 1;
+    const bool trace = getenv("GSB_TRACE_REDUCE") != nullptr;
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto lap = [&](const char* what, u64 v) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[reduce_groups] %-22s %8.3f ms (%llu)\n", what, (t.tv_sec - ts0.tv_sec) * 1e3 + (t.tv_nsec - ts0.tv_nsec) * 1e-6, v);
+        ts0 = t;
+    };
+    const u64 out_cap = n / 4 + (1u << 16), imp_cap = n / 8 + (1u << 16);
+    DevBuf<u64> out_counts(&ws, out_cap), ctr(&ws, 4);
+    DevBuf<u8> imp(&ws, imp_cap * key_bytes);
+    GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 32, s));
+    const unsigned tiles = (unsigned)rle_tiles(n);
+    if (key_bytes == 8)
+        rle_groups_kernel<u64><<<tiles, kRleThreads, 0, s>>>((const u64*)grouped, n, group_bits, min_count, fold_w, (u64*)out_keys_scratch, out_counts.p, out_cap,
+                                                              (u64*)imp.p, imp_cap, ctr.p);
+    else
+        rle_groups_kernel<Key128><<<tiles, kRleThreads, 0, s>>>((const Key128*)grouped, n, group_bits, min_count, fold_w, (Key128*)out_keys_scratch, out_counts.p, out_cap,
+                                                                 (Key128*)imp.p, imp_cap, ctr.p);
+    ++ws.launches;
+    u64 h[4] = {0, 0, 0, 0};
+    GSB_CUDA_TRY(cudaMemcpyAsync(h, ctr.p, 32, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    lap("groups kernel", h[1]);
+    if (h[0] > out_cap || h[1] > imp_cap) return false;          // the low bits group badly / little duplication: finish the sort instead
+    ReducedRun slow; u64 d2 = 0, self2 = 0;
+    if (h[1]) {                                                   // groups holding several keys: full sort + run-length reduce
+        DevBuf<u8> alt(&ws, h[1] * key_bytes);
+        const int where = sort_keys(ws, key_bytes, key_bits, imp.p, alt.p, nullptr, nullptr, h[1], nullptr, nullptr);
+        reduce_sorted(ws, key_bytes, where ? alt.p : imp.p, nullptr, h[1], min_count, slow, &d2, fold_w, &self2);
+    }
+    lap("impure groups: sort+rle", slow.m);
+    const u64 m = h[0] + slow.m;
+    out.keys.reset(&ws, m * key_bytes);
+    out.counts.reset(&ws, m);
+    if (h[0]) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.keys.p, out_keys_scratch, h[0] * key_bytes, cudaMemcpyDeviceToDevice, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.counts.p, out_counts.p, h[0] * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    if (slow.m) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.keys.p + h[0] * key_bytes, slow.keys.p, slow.m * key_bytes, cudaMemcpyDeviceToDevice, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.counts.p + h[0], slow.counts.p, slow.m * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    out.m = m;
+    *m_distinct = h[2] + d2;
+    *n_self_rc = h[3] + self2;
+    ws.sync();
+    lap("copies", m);
+    return true;
 }
 
 }  // namespace gsb

@@ -22,41 +22,80 @@ def _reads(rank, n=20_000):
     return bytes(S.reads_fastq(g, 100, n + 3000 * rank, err=0.01, seed=43 + rank))
 
 
-def _worker(rank, world, nccl_id, k, min_count, out):
+def _worker(rank, world, nccl_id, k, min_count, mode, out):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     import gossamer_b200 as G
-    b = G.Builder(G.GRAPH, k, min_count=min_count, device=rank)
+    kind = G.KMERSET if mode == "kmerset" else G.GRAPH
+    b = G.Builder(kind, k, min_count=min_count, device=rank, max_batch_keys=400_000 if mode == "batches" else 0)
     b.attach(nccl_id, world, rank)
-    b.push(_reads(rank), G.FASTQ)
+    text = _reads(rank)
+    if mode == "batches":                                  # several sort+reduce+merge rounds per rank before the exchange
+        recs = text.split(b"\n@r")
+        chunks = [b"\n@r".join(recs[i:i + 4000]) for i in range(0, len(recs), 4000)]
+        for i, ch in enumerate(chunks):
+            b.push((b"" if i == 0 else b"@r") + ch + (b"\n" if i + 1 < len(chunks) else b""), G.FASTQ, last=True)
+    else:
+        b.push(text, G.FASTQ)
     counts = b.finish()
     lo, hi, cn = b.counts_arrays()
     slice_info = (int(lo.size), (int(hi[0]) << 64 | int(lo[0])) if lo.size else None, (int(hi[-1]) << 64 | int(lo[-1])) if lo.size else None)
-    b.gather_to_root()
-    files = None
-    if rank == 0:
-        sink = G.MemorySink()
-        b.emit("graph", sink)
-        files = sink.as_bytes()
+    if mode == "gather":
+        b.gather_to_root()
+    sink = G.MemorySink()
+    b.emit("graph", sink)                                  # collective: every rank hands over its own pieces of every file
+    files = {n: (bytes(v), sink.segments[n]) for n, v in sink.files.items()}
     out[rank] = (files, (counts.n_instances, counts.n_distinct, counts.n_kept), slice_info)
     b.close()
 
 
-@pytest.mark.parametrize("k,min_count", [(25, 1), (31, 2), (55, 1)])
-def test_multi_gpu_build_graph_bit_exact(k, min_count):
+def _assemble(per_rank):
+    """Put the pieces of all ranks together; pieces must not overlap and must cover what the oracle wrote."""
+    names = set()
+    for files in per_rank:
+        names |= set(files)
+    whole = {}
+    for n in names:
+        size = max(len(files[n][0]) for files in per_rank if n in files)
+        buf, covered = bytearray(size), np.zeros(size, np.uint8)
+        for files in per_rank:
+            if n not in files:
+                continue
+            data, segs = files[n]
+            for off, ln in segs:
+                assert not covered[off:off + ln].any(), f"{n}: two ranks wrote bytes {off}..{off + ln}"
+                covered[off:off + ln] = 1
+                buf[off:off + ln] = data[off:off + ln]
+        whole[n] = bytes(buf)
+    return whole
+
+
+@pytest.mark.parametrize("k,min_count,mode", [(25, 1, "dist"), (31, 2, "dist"), (55, 1, "dist"), (31, 3, "gather"), (27, 2, "batches"),
+                                              (5, 2, "dist"), (25, 1, "kmerset"), (40, 1, "kmerset")])
+def test_multi_gpu_build_bit_exact(k, min_count, mode):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     nccl_id = G.make_nccl_id()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, nccl_id, k, min_count, out), nprocs=world, join=True)
-    want, ost = O.build_graph([(_reads(r), O.FASTQ) for r in range(world)], k, min_count=min_count, threads=4)
-    files, counts, _ = out[0]
+    mp.spawn(_worker, args=(world, nccl_id, k, min_count, mode, out), nprocs=world, join=True)
+    inputs = [(_reads(r), O.FASTQ) for r in range(world)]
+    if mode == "kmerset":
+        want, ost = O.build_kmer_set(inputs, k, threads=4, base="graph")
+    else:
+        want, ost = O.build_graph(inputs, k, min_count=min_count, threads=4)
+    files = _assemble([out[r][0] for r in range(world)])
     ref = want.files()
     assert set(files) == set(ref)
     assert not [n for n in ref if files[n] != ref[n]]
-    assert counts == (ost.n_instances, ost.n_distinct, ost.n_kept)
+    counts = out[0][1]
+    if mode == "kmerset":
+        assert (counts[0], counts[2]) == (ost.n_instances, ost.n_kept)
+    else:
+        assert counts == (ost.n_instances, ost.n_distinct, ost.n_kept)
+    if mode != "gather":
+        assert sum(1 for r in range(world) if out[r][0]) == world      # every rank wrote pieces
     # slices are contiguous, ordered ranges of the global order
     last = -1
     for r in range(world):

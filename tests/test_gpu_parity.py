@@ -255,6 +255,24 @@ def test_self_complementary_edges_and_min_count(k, min_count):
     assert (counts2.n_instances, counts2.n_distinct, counts2.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
 
 
+@pytest.mark.parametrize("k,min_count", [(31, 2), (25, 3), (55, 2)])
+@pytest.mark.parametrize("digits", ["1", "2", "3", "4", "6"])
+def test_partial_sort_counting_any_group_width(k, min_count, digits, monkeypatch):
+    # counting from a partial sort (csrc/sort.cu): forcing few group digits makes most groups hold several keys (the
+    # "impure" path: those groups are fully sorted) or overflows its buffers (the sort is then finished instead);
+    # whatever happens the files must not change
+    text = _random_reads(11 * k + min_count, 30_000, 12_000, 100, err=0.01)
+    want, ost = O.build_graph([(text, O.FASTQ)], k, min_count=min_count, threads=4)
+    monkeypatch.setenv("GSB_GROUP_DIGITS", digits)
+    sink, counts, stats = G.build_graph([(text, G.FASTQ)], k, min_count=min_count)
+    assert not _diff(sink.as_bytes(), want.files())
+    assert (counts.n_instances, counts.n_distinct, counts.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
+    monkeypatch.setenv("GSB_FULL_SORT", "1")
+    sink2, counts2, stats2 = G.build_graph([(text, G.FASTQ)], k, min_count=min_count)
+    assert not _diff(sink2.as_bytes(), want.files())
+    assert stats2.sort_passes == stats2.sort_passes_model
+
+
 @pytest.mark.parametrize("k", [25, 32, 40, 63])
 def test_build_kmer_set_bit_exact(k):
     g = S.genome(60_000, seed=k)
