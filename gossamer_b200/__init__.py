@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgossamer_b200.so")
 GRAPH, KMERSET = 0, 1
 FASTA, FASTQ, LINE = 0, 1, 2
 LAST_OF_FILE = 1
+BLOCK_ASYNC = 2
 ABI_VERSION = 1
 NCCL_ID_BYTES = 128
 
@@ -231,8 +232,11 @@ class Builder:
             b = bytes(data)
             self._check(lib().gsb_push_block(self.h, b, len(b), fmt, LAST_OF_FILE if last else 0))
 
-    def push_pointer(self, host_ptr, nbytes, fmt, last=True):
-        self._check(lib().gsb_push_block(self.h, C.c_void_p(host_ptr), nbytes, fmt, LAST_OF_FILE if last else 0))
+    def push_pointer(self, host_ptr, nbytes, fmt, last=True, overlap=False):
+        """overlap=True (GSB_BLOCK_ASYNC): the copy of this block overlaps the device work of the previous one; the
+        memory must be page-locked and stay unchanged until the next push / finish returns."""
+        flags = (LAST_OF_FILE if last else 0) | (BLOCK_ASYNC if overlap else 0)
+        self._check(lib().gsb_push_block(self.h, C.c_void_p(host_ptr), nbytes, fmt, flags))
 
     def push_device(self, device_ptr, nbytes, fmt, last=True):
         self._check(lib().gsb_push_device_block(self.h, C.c_void_p(device_ptr), nbytes, fmt, LAST_OF_FILE if last else 0))

@@ -127,6 +127,14 @@ struct gsb_ctx {
     size_t pinned_bytes = 0;
     DevBuf<u8> text_dev;
     size_t text_cap = 0;
+    // GSB_BLOCK_ASYNC: two text buffers filled by a copy stream while the main stream works on the other one
+    cudaStream_t copy_stream = nullptr;
+    DevBuf<u8> atext[2];
+    size_t atext_cap[2] = {0, 0};
+    cudaEvent_t copied[2] = {nullptr, nullptr}, processed[2] = {nullptr, nullptr}, copy_begin = nullptr;
+    bool processed_valid[2] = {false, false};
+    struct { bool valid = false; int buf = 0; size_t nbytes = 0; int format = 0; u32 flags = 0; } pending;
+    int next_abuf = 0;
 
     ReducedRun acc;                // merged (key,count) run of all flushed batches
     bool have_acc = false;
@@ -487,6 +495,42 @@ void init_ctx(gsb_ctx* c) {
     c->ws.sync();
 }
 
+// process the block whose asynchronous copy was started by the previous GSB_BLOCK_ASYNC push
+void drain_pending(gsb_ctx* c) {
+    if (!c->pending.valid) return;
+    const int b = c->pending.buf;
+    c->pending.valid = false;
+    GSB_CUDA_TRY(cudaStreamWaitEvent(c->ws.stream, c->copied[b], 0));
+    process_block(c, c->atext[b].p, c->pending.nbytes, c->pending.format, c->pending.flags & ~GSB_BLOCK_ASYNC);
+    GSB_CUDA_TRY(cudaEventRecord(c->processed[b], c->ws.stream));
+    c->processed_valid[b] = true;
+}
+
+void push_async(gsb_ctx* c, const void* data, size_t nbytes, int format, u32 flags) {
+    if (!c->copy_stream) {
+        GSB_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            GSB_CUDA_TRY(cudaEventCreateWithFlags(&c->copied[i], cudaEventDisableTiming));
+            GSB_CUDA_TRY(cudaEventCreateWithFlags(&c->processed[i], cudaEventDisableTiming));
+        }
+    }
+    const int b = c->next_abuf;
+    c->next_abuf ^= 1;
+    if (nbytes + 16 > c->atext_cap[b]) {
+        if (c->processed_valid[b]) GSB_CUDA_TRY(cudaEventSynchronize(c->processed[b]));
+        c->atext[b].free();
+        c->atext_cap[b] = std::max<size_t>(nbytes + 16, 1 << 20);
+        c->atext[b].reset(&c->ws, c->atext_cap[b]);
+        c->ws.sync();                                            // the block may be recycled memory still in use on the main stream
+    }
+    // buffer b was last read by the block pushed two calls ago
+    if (c->processed_valid[b]) GSB_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->processed[b], 0));
+    if (nbytes) GSB_CUDA_TRY(cudaMemcpyAsync(c->atext[b].p, data, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
+    GSB_CUDA_TRY(cudaEventRecord(c->copied[b], c->copy_stream));
+    drain_pending(c);                                            // device work of the previous block overlaps this copy
+    c->pending.valid = true; c->pending.buf = b; c->pending.nbytes = nbytes; c->pending.format = format; c->pending.flags = flags;
+}
+
 }  // namespace
 
 extern "C" {
@@ -510,6 +554,12 @@ void gsb_destroy(gsb_ctx* c) {
         cudaStreamSynchronize(c->ws.stream);
     }
     if (c->comm) { exchange_destroy(c->comm); c->comm = nullptr; }
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 2; ++i) { if (c->copied[i]) cudaEventDestroy(c->copied[i]); if (c->processed[i]) cudaEventDestroy(c->processed[i]); c->atext[i].free(); }
+        cudaStreamDestroy(c->copy_stream);
+        c->copy_stream = nullptr;
+    }
     c->keys.free(); c->alt.free(); c->third.free(); c->cursor.free(); c->hist.free(); c->status.free(); c->carry.free(); c->text_dev.free();
     c->acc.keys.free(); c->acc.counts.free();
     c->timer.destroy();
@@ -526,6 +576,9 @@ int gsb_push_block(gsb_ctx* c, const void* data, size_t nbytes, int format, uint
     if (!c || (!data && nbytes)) return GSB_EINVAL;
     return guarded(c, [&] {
         if (nbytes > kMaxBlockBytes) throw StatusError{GSB_EINVAL, "input blocks are limited to 1 GiB; split the file at record boundaries"};
+        if (c->counted) throw StatusError{GSB_EINVAL, "gsb_push_block after gsb_finish_counting (call gsb_reset first)"};
+        if (flags & GSB_BLOCK_ASYNC) { push_async(c, data, nbytes, format, flags); return; }
+        drain_pending(c);
         if (nbytes + 16 > c->text_cap) {
             c->text_dev.free();
             c->text_cap = std::max<size_t>(nbytes + 16, 1 << 20);
@@ -541,6 +594,7 @@ int gsb_push_block(gsb_ctx* c, const void* data, size_t nbytes, int format, uint
 int gsb_push_device_block(gsb_ctx* c, const void* device_data, size_t nbytes, int format, uint32_t flags) {
     if (!c || (!device_data && nbytes)) return GSB_EINVAL;
     return guarded(c, [&] {
+        drain_pending(c);
         const u8* text = (const u8*)device_data;
         if (((uintptr_t)text & 15) != 0) {                     // vector loads need 16-byte alignment: take a private copy
             if (nbytes + 16 > c->text_cap) {
@@ -558,6 +612,7 @@ int gsb_push_device_block(gsb_ctx* c, const void* device_data, size_t nbytes, in
 int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
     if (!c) return GSB_EINVAL;
     return guarded(c, [&] {
+        drain_pending(c);
         if (!c->counted) {
             bool single = !c->have_acc;
             bool exchanged_instances = false;
@@ -768,6 +823,7 @@ int gsb_reset(gsb_ctx* c) {
         c->dist_ready = false; c->gathered = false;
         c->self_rc_windows = 0; c->any_self_rc = true;
         c->exchanged_instances = false; c->batch_src = nullptr; c->acc_unsorted = false;
+        if (c->pending.valid) { GSB_CUDA_TRY(cudaStreamSynchronize(c->copy_stream)); c->pending.valid = false; }
         for (int f = 0; f < 3; ++f) { c->file_open[f] = false; c->line_base[f] = 0; }
         c->n_carry = 0;
         memset(&c->counts, 0, sizeof(c->counts));

@@ -284,6 +284,7 @@ struct Exchange {
     std::vector<cudaIpcMemHandle_t> peer_handle;   // handle currently mapped for each peer
     std::vector<char> peer_open;
     bool p2p_usable = true;                        // cleared if IPC mapping fails: NCCL send/recv is used instead
+    std::vector<u64> peer_cap;                     // [rank] capacity of that rank's window as of the last handshake (same on every rank)
 };
 
 void exchange_make_id(void* id_out) {
@@ -326,10 +327,17 @@ u64 exchange_sum(Exchange* x, Workspace& ws, u64 v) {
 // Collective: afterwards every rank's receive window holds at least the bytes that rank asked for and is
 // mapped (CUDA IPC) by every other rank.  Returns false -- on every rank alike -- if that is not possible
 // here (IPC not permitted, no peer access): the callers then use NCCL send/recv.
-static bool ensure_windows(Exchange* x, Workspace& ws, u64 need_bytes) {
+// need_all (optional): the bytes EVERY rank needs, known to every rank (from a count matrix): if all the windows
+// mapped at the last handshake are large enough, nothing has to be agreed and no collective runs.
+static bool ensure_windows(Exchange* x, Workspace& ws, u64 need_bytes, const std::vector<u64>* need_all = nullptr) {
     const int n = x->n;
     cudaStream_t s = ws.stream;
     NcclApi& api = nccl();
+    if (need_all && (int)x->peer_cap.size() == n) {
+        bool enough = true;
+        for (int r = 0; r < n; ++r) enough = enough && (*need_all)[r] <= x->peer_cap[r];
+        if (enough) return true;
+    }
     if (need_bytes > x->recv_cap_bytes || !x->recv_buf) {
         ws.sync();
         if (x->recv_buf) GSB_CUDA_TRY(cudaFree(x->recv_buf));
@@ -364,6 +372,8 @@ static bool ensure_windows(Exchange* x, Workspace& ws, u64 need_bytes) {
         }
     }
     const u64 n_ok = exchange_sum(x, ws, local_ok);                 // every rank must take the same path
+    x->peer_cap.clear();
+    if (n_ok == (u64)n) for (int r = 0; r < n; ++r) x->peer_cap.push_back(slots[r].cap);
     return n_ok == (u64)n;
 }
 
@@ -585,7 +595,9 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
     bool done = false;
     if (x->p2p_usable) {
         // ---- peer-memory path: make sure every rank's window is big enough and mapped everywhere ----
-        const bool windows_ok = ensure_windows(x, ws, total * key_bytes);
+        std::vector<u64> need_all(n, 0);
+        for (int src = 0; src < n; ++src) for (int dst = 0; dst < n; ++dst) need_all[dst] += cnt[(size_t)src * n + dst] * key_bytes;
+        const bool windows_ok = ensure_windows(x, ws, total * key_bytes, &need_all);
         lap("windows: (re)allocation, ipc handles, agree on path");
         if (windows_ok) {
             PeerWindows win;
@@ -702,7 +714,9 @@ bool exchange_pairs_p2p(Exchange* x, Workspace& ws, int key_bytes, const void* k
     std::vector<u64> total(n, 0);
     for (int src = 0; src < n; ++src) for (int dst = 0; dst < n; ++dst) total[dst] += cnt[(size_t)src * n + dst];
     const u64 mine_total = total[x->rank];
-    if (!ensure_windows(x, ws, align256(mine_total * key_bytes) + mine_total * 8)) { x->p2p_usable = false; return false; }
+    std::vector<u64> need_all(n);
+    for (int r = 0; r < n; ++r) need_all[r] = align256(total[r] * key_bytes) + total[r] * 8;
+    if (!ensure_windows(x, ws, need_all[x->rank], &need_all)) { x->p2p_usable = false; return false; }
     PeerWindows win;
     memset(&win, 0, sizeof(win));
     for (int r = 0; r < n; ++r) {

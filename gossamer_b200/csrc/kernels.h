@@ -88,10 +88,10 @@ void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid,
                     void* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s, u64* launches);
 
 // ---- sort.cu ---------------------------------------------------------------------------------
-u64 sort_tile_keys(int key_bytes);
+u64 sort_tile_keys(int key_bytes, bool with_values = false);
 void sort_set_tuning(int id);
 void sort_fill_random(int key_bytes, void* keys, u64 n, int key_bits, u64 seed, cudaStream_t s);
-u64 sort_lookback_bytes(int key_bytes, u64 n);
+u64 sort_lookback_bytes(int key_bytes, u64 n, bool with_values = false);
 void sort_digit_hist(int key_bytes, const void* keys, u64 n, int passes, u64* hist, int sm_count, cudaStream_t s, u64* launches);
 void sort_digit_base(const u64* hist, u64* base, int passes, cudaStream_t s, u64* launches);
 void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vout, u64 n, int pass, const u64* digit_base_all,

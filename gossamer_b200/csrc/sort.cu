@@ -279,14 +279,22 @@ void sort_set_tuning(int id) {
     g_sort_tuning = (id >= 0 && id < kNumShapes64) ? id : 0;
 }
 
-u64 sort_tile_keys(int key_bytes) {
+// tile shape of the (key, payload) sweeps on 64-bit keys: 0 = 256 x 16 at 2 CTAs/SM, 1 = 256 x 8 at 4, 2 = 256 x 12 at 3
+static int pair_shape() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GSB_PAIR_SHAPE"); v = e ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
+    return v;
+}
+
+u64 sort_tile_keys(int key_bytes, bool with_values) {
+    if (key_bytes == 8 && with_values) { static const int items[3] = {16, 8, 12}; return 256ull * items[pair_shape()]; }
     const SortShape sh = key_bytes == 8 ? kShapes64[g_sort_tuning] : kShape128;
     return (u64)sh.threads * sh.items;
 }
 
 // bytes of look-back state needed for n keys (+ the ticket word at the end)
-u64 sort_lookback_bytes(int key_bytes, u64 n) {
-    u64 tiles = (n + sort_tile_keys(key_bytes) - 1) / sort_tile_keys(key_bytes);
+u64 sort_lookback_bytes(int key_bytes, u64 n, bool with_values) {
+    u64 tiles = (n + sort_tile_keys(key_bytes, with_values) - 1) / sort_tile_keys(key_bytes, with_values);
     u64 word = n < (1ull << 30) ? 4 : 8;
     return tiles * 256 * word + 256;
 }
@@ -310,7 +318,7 @@ void sort_digit_base(const u64* hist, u64* base, int passes, cudaStream_t s, u64
 void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vout, u64 n, int pass, const u64* digit_base_all,
                void* lookback, cudaStream_t s, u64* launches, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
     if (!n) return;
-    const u64 lb_bytes = sort_lookback_bytes(key_bytes, n);
+    const u64 lb_bytes = sort_lookback_bytes(key_bytes, n, vin != nullptr);
     GSB_CUDA_TRY(cudaMemsetAsync(lookback, 0, lb_bytes, s));
     if (ev_begin) GSB_CUDA_TRY(cudaEventRecord(ev_begin, s));
     u32* ticket = (u32*)((char*)lookback + lb_bytes - 256);
@@ -325,7 +333,18 @@ void sort_pass(int key_bytes, const void* in, void* out, const u64* vin, u64* vo
         else if (!hv) launch_onesweep<K, u64, T, I, false, MB, MD>(in, out, vin, vout, n, shift, db, lookback, ticket, s); \
         else launch_onesweep<K, u64, T, I, true, (MB > 2 ? 2 : MB), MD>(in, out, vin, vout, n, shift, db, lookback, ticket, s); \
     } while (0)
-    if (key_bytes == 8) {
+    if (key_bytes == 8 && hv) {
+        const int shape = pair_shape();
+        if (small) {
+            if (shape == 0) launch_onesweep<u64, u32, 256, 16, true, 2, 0>(in, out, vin, vout, n, shift, db, lookback, ticket, s);
+            else if (shape == 1) launch_onesweep<u64, u32, 256, 8, true, 4, 0>(in, out, vin, vout, n, shift, db, lookback, ticket, s);
+            else launch_onesweep<u64, u32, 256, 12, true, 3, 0>(in, out, vin, vout, n, shift, db, lookback, ticket, s);
+        } else {
+            if (shape == 0) launch_onesweep<u64, u64, 256, 16, true, 2, 0>(in, out, vin, vout, n, shift, db, lookback, ticket, s);
+            else if (shape == 1) launch_onesweep<u64, u64, 256, 8, true, 4, 0>(in, out, vin, vout, n, shift, db, lookback, ticket, s);
+            else launch_onesweep<u64, u64, 256, 12, true, 3, 0>(in, out, vin, vout, n, shift, db, lookback, ticket, s);
+        }
+    } else if (key_bytes == 8) {
         switch (g_sort_tuning) {
             default: GSB_LAUNCH(u64, 256, 16, 4, 0); break;
             case 1: if (small && !hv) { launch_onesweep<u64, u32, 256, 16, false, 4, 0, 8>(in, out, vin, vout, n, shift, db, lookback, ticket, s); break; }
@@ -533,102 +552,168 @@ __device__ __forceinline__ bool bits_any(const u32* bits, u32 a, u32 b) {
     return false;
 }
 
-// ctr[0] survivors appended, ctr[1] impure elements appended, ctr[2] pure groups (= distinct keys in them),
-// ctr[3] pure groups whose key is its own reverse complement.  Appends beyond a capacity are dropped (the
-// counters still advance): the host then falls back to the full sort.
+// ctr[0] survivors appended, ctr[1] impure groups recorded (descriptors {first index, length}; their elements are
+// copied out by copy_groups_kernel), ctr[2] pure groups (= distinct keys in them), ctr[3] pure groups whose key is its
+// own reverse complement.  Appends beyond a capacity are dropped (the counters still advance): the host then falls
+// back to the full sort.
+//
+// Blocked arrangement: a thread owns 8 CONSECUTIVE keys, so group heads and "differs from its predecessor" flags
+// come from register compares, and only a thread's LAST group needs the other threads (two 256-bit vectors in shared
+// memory: which threads contain a head, which have a differing key before their first head).  The first, warp-striped
+// version executed 1.43 G warp instructions for 198 M keys (ncu: XU pipe saturated by the per-item bit searches,
+// 23 % of the stall samples at the barrier) and took 1.8 ms.
+static const int kGrpThreads = 256;
+static const int kGrpItems = 8;
+
 template <typename K>
-__global__ void __launch_bounds__(kRleThreads, 3) rle_groups_kernel(const K* __restrict__ keys, u64 n, int gb, u64 min_count, int fold_w,
+__global__ void __launch_bounds__(kGrpThreads, 3) rle_groups_kernel(const K* __restrict__ keys, u64 n, int gb, u64 min_count, int fold_w,
                                                                     K* __restrict__ out_keys, u64* __restrict__ out_counts, u64 out_cap,
-                                                                    K* __restrict__ imp_keys, u64 imp_cap, u64* __restrict__ ctr) {
+                                                                    ulonglong2* __restrict__ imp_desc, u64 desc_cap, u64* __restrict__ ctr) {
     typedef KeyOps<K> KO;
-    constexpr int TILE = kRleThreads * kRleItems;
-    constexpr int WORDS = TILE / 32;
-    __shared__ u32 head_bits[WORDS], imp_bits[WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TILE = kGrpThreads * kGrpItems;
+    constexpr int WORDS = kGrpThreads / 32;
+    __shared__ u32 head_thr[WORDS], preimp_thr[WORDS];
+    __shared__ u8 first_head_s[kGrpThreads];
+    __shared__ u32 keep_warp[WORDS], imp_warp[WORDS], stat_s[2];
+    __shared__ u32 halo_head_s, halo_imp_s;
+    __shared__ u64 keep_base_s, imp_base_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const u64 tbase = (u64)blockIdx.x * TILE;
-    const u64 wbase = tbase + (u64)warp * 32 * kRleItems;
+    const u64 base = tbase + (u64)t * kGrpItems;
     const u64 tile_end = tbase + TILE < n ? tbase + TILE : n;
-    const u32 lt = (1u << lane) - 1;
-    K k[kRleItems];
-    u32 headb[kRleItems];
-    K carry = KO::make(0, 0);
-    if (wbase > 0 && wbase < n) carry = keys[wbase - 1];
-#pragma unroll
-    for (int i = 0; i < kRleItems; ++i) {
-        const u64 idx = wbase + (u64)i * 32 + lane;
-        k[i] = idx < n ? keys[idx] : KO::make(0, 0);
-    }
-#pragma unroll
-    for (int i = 0; i < kRleItems; ++i) {
-        const u64 idx = wbase + (u64)i * 32 + lane;
-        const bool ok = idx < n;
-        const K& last_src = i ? k[i ? i - 1 : 0] : carry;
-        u64 up_lo = __shfl_up_sync(0xffffffffu, KO::lo(k[i]), 1), up_hi = 0;
-        u64 last_lo = __shfl_sync(0xffffffffu, KO::lo(last_src), i ? 31 : 0), last_hi = 0;
-        if (sizeof(K) == 16) {
-            up_hi = __shfl_up_sync(0xffffffffu, KO::hi(k[i]), 1);
-            last_hi = __shfl_sync(0xffffffffu, KO::hi(last_src), i ? 31 : 0);
-        }
-        const K prev = KO::make(lane ? up_lo : last_lo, lane ? up_hi : last_hi);
-        const bool ghead = ok && (idx == 0 || !same_group<K>(k[i], prev, gb));
-        const bool imp = ok && !ghead && !KO::eq(k[i], prev);      // a different key inside a group
-        headb[i] = __ballot_sync(0xffffffffu, ghead);
-        const u32 impb = __ballot_sync(0xffffffffu, imp);
-        if (lane == 0) { head_bits[warp * kRleItems + i] = headb[i]; imp_bits[warp * kRleItems + i] = impb; }
-    }
-    __syncthreads();
-    u32 pure_groups = 0, self_groups = 0;
-    u32 keepb[kRleItems];
-    u64 cnt[kRleItems];                                           // pure group: its count; impure group: its length
-    u32 wtot = 0, impmask = 0;
-    u64 my_imp = 0;
-#pragma unroll
-    for (int i = 0; i < kRleItems; ++i) {
-        bool keep = false;
-        cnt[i] = 0;
-        if ((headb[i] >> lane) & 1u) {
-            const u64 idx = wbase + (u64)i * 32 + lane;
-            int w = warp * kRleItems + i;
-            u32 m = lane == 31 ? 0u : (head_bits[w] & ~((2u << lane) - 1));
-            while (!m && ++w < WORDS) m = head_bits[w];
-            const u64 end = m ? tbase + (u64)w * 32 + (__ffs(m) - 1)
-                              : (tile_end < n ? group_end<K>(keys, n, tile_end - 1, k[i], gb) : n);
-            const u64 end_in = end < tile_end ? end : tile_end;
-            bool impure = bits_any(imp_bits, (u32)(idx + 1 - tbase), (u32)(end_in - tbase));
-            for (u64 j = tile_end; !impure && j < end; ++j) impure = !KO::eq(keys[j], k[i]);
-            const u64 len = end - idx;
-            k[i] = key_unmix(k[i]);                                 // the real key from here on
-            if (impure) {
-                impmask |= 1u << i;
-                cnt[i] = len;
-                my_imp += len;
+    // Halo: heads / differing keys among the 32 keys that FOLLOW the tile, loaded together with the tile.  The last
+    // group of a tile nearly always ends there; searching for its end with dependent loads instead (gallop + bisect)
+    // kept every tile's 255 other threads waiting at the barrier for ~5 us (1.6 ms for 198 M keys).
+    if (warp == WORDS - 1) {
+        const u64 p = tile_end + lane;                             // p - 1 >= 0: the tile is not empty
+        bool h = false, im = false;
+        if (tile_end < n) {
+            if (p >= n) {
+                h = p == n;                                        // the end of the input closes the last group
             } else {
-                ++pure_groups;
-                const bool self_rc = fold_w && KO::eq(key_rc(k[i], fold_w), k[i]);
-                self_groups += self_rc ? 1u : 0u;
-                cnt[i] = self_rc ? 2 * len : len;                   // both strands of a self-complementary key are this key
-                keep = cnt[i] >= min_count;
+                const K a = keys[p], b = keys[p - 1];
+                h = !same_group<K>(a, b, gb);
+                im = !h && !KO::eq(a, b);
             }
         }
-        keepb[i] = __ballot_sync(0xffffffffu, keep);
-        wtot += __popc(keepb[i]);
+        const u32 hh = __ballot_sync(0xffffffffu, h), hi = __ballot_sync(0xffffffffu, im);
+        if (lane == 0) { halo_head_s = hh; halo_imp_s = hi; }
     }
-    // ONE append per tile and cursor: warp-level (survivors) or per-group (impure elements) atomics on a single
-    // address serialised the whole kernel (6 ms resp. 2 ms for 198 M keys)
-    __shared__ u32 warp_tot[kRleThreads / 32];
-    __shared__ u64 imp_warp_tot[kRleThreads / 32];
-    __shared__ u64 base_s, imp_base_s;
-    __shared__ u32 stat_s[2];
-    if (threadIdx.x < 2) stat_s[threadIdx.x] = 0;
-    if (lane == 0) warp_tot[warp] = wtot;
-    u64 imp_inc = my_imp;
+    const int nv = base >= n ? 0 : (int)(n - base < (u64)kGrpItems ? n - base : (u64)kGrpItems);
+    K k[kGrpItems];
+    if (sizeof(K) == 8 && nv == kGrpItems) {                       // 64 contiguous bytes per thread: four 128-bit loads
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(keys + base);
+#pragma unroll
+        for (int q = 0; q < kGrpItems / 2; ++q) {
+            const ulonglong2 v = p[q];
+            k[2 * q] = KO::make(v.x, 0); k[2 * q + 1] = KO::make(v.y, 0);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kGrpItems; ++j) k[j] = j < nv ? keys[base + j] : KO::make(0, 0);
+    }
+    K prev = KO::make(0, 0);
+    if (base > 0 && nv > 0) prev = keys[base - 1];
+    u32 headm = 0, impm = 0;
+#pragma unroll
+    for (int j = 0; j < kGrpItems; ++j) {
+        if (j < nv) {
+            const K& p = j ? k[j ? j - 1 : 0] : prev;
+            const bool h = (base + j == 0) || !same_group<K>(k[j], p, gb);
+            const bool im = !h && !KO::eq(k[j], p);                // a different key inside a group
+            headm |= (h ? 1u : 0u) << j;
+            impm |= (im ? 1u : 0u) << j;
+        }
+    }
+    const int first_head = headm ? __ffs(headm) - 1 : kGrpItems;
+    const bool pre_imp = (impm & ((1u << first_head) - 1)) != 0;
+    const u32 b1 = __ballot_sync(0xffffffffu, headm != 0), b2 = __ballot_sync(0xffffffffu, pre_imp);
+    if (lane == 0) { head_thr[warp] = b1; preimp_thr[warp] = b2; }
+    first_head_s[t] = (u8)first_head;
+    if (t < 2) stat_s[t] = 0;
+    __syncthreads();
+
+    u64 cnt[kGrpItems];                                            // pure group: its count; impure group: its length
+    u32 keepm = 0, impgm = 0, pure_groups = 0, self_groups = 0;
+    // groups that start AND end inside this thread's keys: everything is in registers
+#pragma unroll
+    for (int j = 0; j < kGrpItems; ++j) {
+        cnt[j] = 0;
+        const u32 after = ~((2u << j) - 1);
+        const u32 later = headm & after;
+        if (((headm >> j) & 1u) && later) {
+            const int j2 = __ffs(later) - 1;
+            const bool impure = (impm & after & ((1u << j2) - 1)) != 0;
+            const u64 len = (u64)(j2 - j);
+            k[j] = key_unmix(k[j]);                                 // the real key from here on
+            if (impure) {
+                impgm |= 1u << j;
+                cnt[j] = len;
+            } else {
+                ++pure_groups;
+                const bool self_rc = fold_w && KO::eq(key_rc(k[j], fold_w), k[j]);
+                self_groups += self_rc ? 1u : 0u;
+                cnt[j] = self_rc ? 2 * len : len;                   // both strands of a self-complementary key are this key
+                if (cnt[j] >= min_count) keepm |= 1u << j;
+            }
+        }
+    }
+    // the thread's LAST group ends in another thread, in the halo, or further on: handled once, outside the unrolled
+    // loop (inside it, the divergent search code ran for every j that is some lane's last head -- i.e. 8 times)
+    const int jl = headm ? 31 - __clz(headm) : -1;
+    K last_key = KO::make(0, 0);
+    u64 last_cnt = 0;
+    if (jl >= 0) {
+#pragma unroll
+        for (int j = 0; j < kGrpItems; ++j) if (j == jl) last_key = k[j];
+        bool impure = (impm & ~((2u << jl) - 1)) != 0;
+        u64 end;
+        int w = warp;
+        u32 m = lane == 31 ? 0u : (head_thr[w] & ~((2u << lane) - 1));
+        while (!m && ++w < WORDS) m = head_thr[w];
+        if (m) {                                                    // next head: in thread t2 of this tile
+            const u32 t2 = (u32)w * 32 + (__ffs(m) - 1);
+            end = tbase + (u64)t2 * kGrpItems + first_head_s[t2];
+            impure = impure || bits_any(preimp_thr, (u32)t + 1, t2 + 1);
+        } else {                                                    // the group runs to the end of the tile, maybe beyond
+            impure = impure || bits_any(preimp_thr, (u32)t + 1, (u32)kGrpThreads);
+            if (tile_end < n) {
+                const u32 hm = halo_head_s;
+                if (hm) {                                           // ends within the 32 keys after the tile
+                    const int p = __ffs(hm) - 1;
+                    end = tile_end + p;
+                    impure = impure || (halo_imp_s & ((1u << p) - 1)) != 0;
+                } else {                                            // a long group: search for its end
+                    impure = impure || halo_imp_s != 0;
+                    end = group_end<K>(keys, n, tile_end + 31, last_key, gb);
+                    for (u64 q = tile_end + 32; !impure && q < end; ++q) impure = !KO::eq(keys[q], last_key);
+                }
+            } else {
+                end = n;
+            }
+        }
+        const u64 len = end - (base + jl);
+        last_key = key_unmix(last_key);
+        if (impure) {
+            impgm |= 1u << jl;
+            last_cnt = len;
+        } else {
+            ++pure_groups;
+            const bool self_rc = fold_w && KO::eq(key_rc(last_key, fold_w), last_key);
+            self_groups += self_rc ? 1u : 0u;
+            last_cnt = self_rc ? 2 * len : len;
+            if (last_cnt >= min_count) keepm |= 1u << jl;
+        }
+    }
+    // ONE append per tile and cursor (a warp-level atomic on the single cursor serialised the whole kernel)
+    const u32 my_keep = __popc(keepm), my_imp = __popc(impgm);
+    u32 keep_inc = my_keep, imp_inc = my_imp;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(0xffffffffu, imp_inc, o);
-        if (lane >= o) imp_inc += t;
+        const u32 a = __shfl_up_sync(0xffffffffu, keep_inc, o), b = __shfl_up_sync(0xffffffffu, imp_inc, o);
+        if (lane >= o) { keep_inc += a; imp_inc += b; }
     }
-    if (lane == 31) imp_warp_tot[warp] = imp_inc;
-    __syncthreads();
+    if (lane == 31) { keep_warp[warp] = keep_inc; imp_warp[warp] = imp_inc; }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         pure_groups += __shfl_xor_sync(0xffffffffu, pure_groups, o);
@@ -638,42 +723,58 @@ __global__ void __launch_bounds__(kRleThreads, 3) rle_groups_kernel(const K* __r
         if (pure_groups) atomicAdd(&stat_s[0], pure_groups);
         if (self_groups) atomicAdd(&stat_s[1], self_groups);
     }
-    if (threadIdx.x == 0) {
-        u32 tot = 0;
-#pragma unroll
-        for (int w = 0; w < kRleThreads / 32; ++w) { const u32 c = warp_tot[w]; warp_tot[w] = tot; tot += c; }
-        base_s = tot ? atomicAdd(&ctr[0], (u64)tot) : 0;
-        u64 itot = 0;
-#pragma unroll
-        for (int w = 0; w < kRleThreads / 32; ++w) { const u64 c = imp_warp_tot[w]; imp_warp_tot[w] = itot; itot += c; }
-        imp_base_s = itot ? atomicAdd(&ctr[1], itot) : 0;
-    }
     __syncthreads();
-    if (impmask) {                                                // copy out the groups that hold several keys (un-mixed)
-        u64 pos = imp_base_s + imp_warp_tot[warp] + (imp_inc - my_imp);
+    if (t == 0) {
+        u32 kt = 0, it = 0;
 #pragma unroll
-        for (int i = 0; i < kRleItems; ++i) {
-            if ((impmask >> i) & 1u) {
-                const u64 idx = wbase + (u64)i * 32 + lane;
-                for (u64 q = 0; q < cnt[i]; ++q)
-                    if (pos + q < imp_cap) imp_keys[pos + q] = key_unmix(keys[idx + q]);
-                pos += cnt[i];
-            }
+        for (int w = 0; w < WORDS; ++w) {
+            const u32 a = keep_warp[w], b = imp_warp[w];
+            keep_warp[w] = kt; imp_warp[w] = it;
+            kt += a; it += b;
         }
-    }
-    if (threadIdx.x == 0) {
+        keep_base_s = kt ? atomicAdd(&ctr[0], (u64)kt) : 0;
+        imp_base_s = it ? atomicAdd(&ctr[1], (u64)it) : 0;
         if (stat_s[0]) atomicAdd(&ctr[2], (u64)stat_s[0]);
         if (stat_s[1]) atomicAdd(&ctr[3], (u64)stat_s[1]);
     }
-    u64 j = base_s + warp_tot[warp];
+    __syncthreads();
+    u64 ko = keep_base_s + keep_warp[warp] + (keep_inc - my_keep);
+    u64 io = imp_base_s + imp_warp[warp] + (imp_inc - my_imp);
 #pragma unroll
-    for (int i = 0; i < kRleItems; ++i) {
-        if ((keepb[i] >> lane) & 1u) {
-            const u64 o = j + __popc(keepb[i] & lt);
-            if (o < out_cap) { out_keys[o] = k[i]; out_counts[o] = cnt[i]; }
+    for (int j = 0; j < kGrpItems; ++j) {
+        const bool is_last = j == jl;
+        const u64 c = is_last ? last_cnt : cnt[j];
+        if ((keepm >> j) & 1u) {
+            if (ko < out_cap) { out_keys[ko] = is_last ? last_key : k[j]; out_counts[ko] = c; }
+            ++ko;
         }
-        j += __popc(keepb[i]);
+        if ((impgm >> j) & 1u) {
+            if (io < desc_cap) imp_desc[io] = make_ulonglong2(base + j, c);
+            ++io;
+        }
     }
+}
+
+// one thread per impure group: copies its elements, un-mixed, to `out` (one atomic per warp for the positions)
+template <typename K>
+__global__ void __launch_bounds__(256) copy_groups_kernel(const K* __restrict__ keys, const ulonglong2* __restrict__ desc, u64 n_desc,
+                                                          K* __restrict__ out, u64 out_cap, u64* __restrict__ cursor) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    u64 idx = 0, len = 0;
+    if (i < n_desc) { const ulonglong2 d = desc[i]; idx = d.x; len = d.y; }
+    u64 inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    u64 base = 0;
+    if (lane == 31 && inc) base = atomicAdd(cursor, inc);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const u64 pos = base + inc - len;
+    for (u64 q = 0; q < len; ++q)
+        if (pos + q < out_cap) out[pos + q] = key_unmix(keys[idx + q]);
 }
 
 u64 rle_tiles(u64 n) { return (n + kRleThreads * kRleItems - 1) / (kRleThreads * kRleItems); }
@@ -819,7 +920,7 @@ int sort_keys(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64*
     std::vector<u64> h((size_t)passes * 256);
     GSB_CUDA_TRY(cudaMemcpyAsync(h.data(), hist, h.size() * 8, cudaMemcpyDeviceToHost, s));
     ws.sync();
-    DevBuf<u8> lookback(&ws, sort_lookback_bytes(key_bytes, n));
+    DevBuf<u8> lookback(&ws, sort_lookback_bytes(key_bytes, n, va != nullptr));
     int cur = 0, run = 0;
     std::vector<cudaEvent_t> ev;
     if (sweep_ms) { ev.resize(2 * (size_t)passes); for (auto& e : ev) GSB_CUDA_TRY(cudaEventCreate(&e)); }
@@ -931,23 +1032,35 @@ bool reduce_groups(Workspace& ws, int key_bytes, int key_bits, const void* group
         fprintf(stderr, "[reduce_groups] %-22s %8.3f ms (%llu)\n", what, (t.tv_sec - ts0.tv_sec) * 1e3 + (t.tv_nsec - ts0.tv_nsec) * 1e-6, v);
         ts0 = t;
     };
-    const u64 out_cap = n / 4 + (1u << 16), imp_cap = n / 8 + (1u << 16);
-    DevBuf<u64> out_counts(&ws, out_cap), ctr(&ws, 4);
+    const u64 out_cap = n / 4 + (1u << 16), imp_cap = n / 8 + (1u << 16), desc_cap = n / 16 + (1u << 16);
+    DevBuf<u64> out_counts(&ws, out_cap), ctr(&ws, 8);
+    DevBuf<ulonglong2> desc(&ws, desc_cap);
+    GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 64, s));
     DevBuf<u8> imp(&ws, imp_cap * key_bytes);
-    GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 32, s));
-    const unsigned tiles = (unsigned)rle_tiles(n);
+    const unsigned tiles = (unsigned)((n + kGrpThreads * kGrpItems - 1) / (kGrpThreads * kGrpItems));
     if (key_bytes == 8)
-        rle_groups_kernel<u64><<<tiles, kRleThreads, 0, s>>>((const u64*)grouped, n, group_bits, min_count, fold_w, (u64*)out_keys_scratch, out_counts.p, out_cap,
-                                                              (u64*)imp.p, imp_cap, ctr.p);
+        rle_groups_kernel<u64><<<tiles, kGrpThreads, 0, s>>>((const u64*)grouped, n, group_bits, min_count, fold_w, (u64*)out_keys_scratch, out_counts.p, out_cap,
+                                                              desc.p, desc_cap, ctr.p);
     else
-        rle_groups_kernel<Key128><<<tiles, kRleThreads, 0, s>>>((const Key128*)grouped, n, group_bits, min_count, fold_w, (Key128*)out_keys_scratch, out_counts.p, out_cap,
-                                                                 (Key128*)imp.p, imp_cap, ctr.p);
+        rle_groups_kernel<Key128><<<tiles, kGrpThreads, 0, s>>>((const Key128*)grouped, n, group_bits, min_count, fold_w, (Key128*)out_keys_scratch, out_counts.p, out_cap,
+                                                                 desc.p, desc_cap, ctr.p);
     ++ws.launches;
-    u64 h[4] = {0, 0, 0, 0};
-    GSB_CUDA_TRY(cudaMemcpyAsync(h, ctr.p, 32, cudaMemcpyDeviceToHost, s));
+    u64 h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    GSB_CUDA_TRY(cudaMemcpyAsync(h, ctr.p, 64, cudaMemcpyDeviceToHost, s));
     ws.sync();
     lap("groups kernel", h[1]);
-    if (h[0] > out_cap || h[1] > imp_cap) return false;          // the low bits group badly / little duplication: finish the sort instead
+    // the low bits group badly / little duplication: the caller sorts by the full key instead
+    if (h[0] > out_cap || h[1] > desc_cap) return false;
+    if (h[1]) {
+        const unsigned blocks = (unsigned)((h[1] + 255) / 256);
+        if (key_bytes == 8) copy_groups_kernel<u64><<<blocks, 256, 0, s>>>((const u64*)grouped, desc.p, h[1], (u64*)imp.p, imp_cap, ctr.p + 5);
+        else copy_groups_kernel<Key128><<<blocks, 256, 0, s>>>((const Key128*)grouped, desc.p, h[1], (Key128*)imp.p, imp_cap, ctr.p + 5);
+        ++ws.launches;
+        GSB_CUDA_TRY(cudaMemcpyAsync(&h[1], ctr.p + 5, 8, cudaMemcpyDeviceToHost, s));
+        ws.sync();
+        if (h[1] > imp_cap) return false;
+    }
+    // h[1] = number of elements on the impure path from here on
     ReducedRun slow; u64 d2 = 0, self2 = 0;
     if (h[1]) {                                                   // groups holding several keys: full sort + run-length reduce
         DevBuf<u8> alt(&ws, h[1] * key_bytes);

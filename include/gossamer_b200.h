@@ -54,6 +54,12 @@ typedef enum gsb_format {
 /* gsb_push_* flags */
 #define GSB_BLOCK_LAST_OF_FILE 1u /* the file ends with this block; without it the next block of the same
                                      format continues the same file (FASTA records may straddle blocks) */
+#define GSB_BLOCK_ASYNC 2u        /* gsb_push_block only: start the host-to-device copy of this block and return after
+                                    processing the PREVIOUS asynchronous block, so that the copy overlaps the device
+                                    work (scan, pack, extraction) of its predecessor.  `data` must be page-locked
+                                    (gsb_host_alloc) and stay unchanged until the next gsb_push_block /
+                                    gsb_finish_counting on this context returns; a parse error in this block is
+                                    reported by that later call. */
 
 typedef void (*gsb_log_fn)(void* user, int severity /*0 info,1 warning,2 error*/, const char* message);
 

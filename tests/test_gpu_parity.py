@@ -301,6 +301,30 @@ def test_fasta_split_into_blocks_matches_whole_file():
     assert not _diff(sink.as_bytes(), want.files())
 
 
+def test_overlapped_block_pushes_match_one_block():
+    # GSB_BLOCK_ASYNC: the copy of block i+1 overlaps the device work of block i; same files, errors surface one call later
+    import torch
+    text = _random_reads(21, 40_000, 30_000, 100, err=0.01)
+    want, ost = O.build_graph([(text, O.FASTQ)], 31, min_count=2, threads=4)
+    host = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()
+    cuts = [0] + [text.index(b"\n@r", len(text) * i // 5) + 1 for i in range(1, 5)] + [len(text)]
+    b = G.Builder(G.GRAPH, 31, min_count=2)
+    for rep in range(2):
+        for i in range(5):
+            b.push_pointer(host.data_ptr() + cuts[i], cuts[i + 1] - cuts[i], G.FASTQ, last=True, overlap=True)
+        counts = b.finish()
+        sink = G.MemorySink()
+        b.emit("graph", sink)
+        assert not _diff(sink.as_bytes(), want.files())
+        assert (counts.n_instances, counts.n_distinct, counts.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
+        b.reset()
+    bad = torch.frombuffer(bytearray(b"@r1\nACGT\n+\nIII\n"), dtype=torch.uint8).pin_memory()
+    b.push_pointer(bad.data_ptr(), bad.numel(), G.FASTQ, last=True, overlap=True)      # accepted: not looked at yet
+    with pytest.raises(G.ParseError):
+        b.finish()
+    b.close()
+
+
 def test_multiple_inputs_and_formats():
     a = _random_reads(1, 30_000, 5000, 80)
     g = S.genome(30_000, seed=1)
