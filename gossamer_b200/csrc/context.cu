@@ -616,7 +616,10 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
         if (!c->counted) {
             bool single = !c->have_acc;
             bool exchanged_instances = false;
-            c->any_self_rc = (c->comm ? exchange_sum(c->comm, c->ws, c->self_rc_windows) : c->self_rc_windows) > 0;
+            // whether ANY rank saw a self-complementary window (rides on the sample all-gather of the instance exchange)
+            u64 self_rc_all = c->self_rc_windows;
+            if (c->comm && !single) self_rc_all = exchange_sum(c->comm, c->ws, self_rc_all);
+            c->any_self_rc = self_rc_all > 0;
             if (c->comm && single) {
                 // Multi-GPU, everything still buffered as raw instances: route each instance to the
                 // rank that owns its key range FIRST (one all-to-all of raw keys over NVLink), then
@@ -627,7 +630,8 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                 ExchangeTiming et;
                 ensure_alt(c, c->n_keys);
                 u8* recv_ptr = nullptr;
-                exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &recv_ptr, &n_recv, &et);
+                exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &recv_ptr, &n_recv, &et, &self_rc_all);
+                c->any_self_rc = self_rc_all > 0;
                 c->stats.ms_all_to_all += et.ms_all_to_all;
                 c->stats.exchange_bytes_sent += et.bytes_sent_remote;
                 c->stats.exchange_peer_memory = et.used_peer_memory ? 1 : 0;
@@ -649,7 +653,9 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
             }
             const u64 min_count = c->cfg.kind == GSB_KIND_GRAPH ? std::max<u64>(1, c->cfg.min_count) : 1;
             const bool filtered_already = single && (!c->comm || exchanged_instances);
-            if (exchanged_instances) c->counts.n_distinct = exchange_sum(c->comm, c->ws, c->counts.n_distinct);
+            bool stats_summed = false;                         // n_instances / n_distinct already summed over the ranks
+            const bool fast_p2p = exchanged_instances && c->fold_w && exchange_peer_memory_usable(c->comm);   // sums ride on a later all-gather
+            if (exchanged_instances && !fast_p2p) c->counts.n_distinct = exchange_sum(c->comm, c->ws, c->counts.n_distinct);
             if (!filtered_already) {
                 // merged batches (and/or exchanged reduced runs): still folded, raw occurrence counts
                 u64 local_distinct = c->acc.m;
@@ -715,7 +721,16 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                         c->timer.stop(c->stats.ms_unfold);
                         c->timer.start();
                         exchange_view(c->comm, kb, totals, &c->dist);
-                        exchange_barrier(c->comm, c->ws);        // every slice is sorted and in place before anyone reads a neighbour's
+                        // one all-gather: the global statistics, and the barrier that makes every slice sorted and in place
+                        // before anyone reads a neighbour's
+                        const u64 mine_stats[2] = {c->counts.n_instances, exchanged_instances ? c->counts.n_distinct : 0};
+                        std::vector<u64> all_stats;
+                        exchange_allgather_u64(c->comm, c->ws, mine_stats, 2, all_stats);
+                        u64 inst = 0, dist = 0;
+                        for (int r = 0; r < exchange_size(c->comm); ++r) { inst += all_stats[2 * r]; dist += all_stats[2 * r + 1]; }
+                        c->counts.n_instances = inst;
+                        if (exchanged_instances) c->counts.n_distinct = dist;
+                        stats_summed = true;
                         c->dist_ready = true;
                         c->timer.stop(c->stats.ms_exchange);
                         done = true;
@@ -743,7 +758,10 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                     c->timer.stop(c->stats.ms_exchange);
                 }
                 c->counts.n_kept = c->dist_ready ? c->dist.off[c->dist.n] : exchange_sum(c->comm, c->ws, c->acc.m);
-                c->counts.n_instances = exchange_sum(c->comm, c->ws, c->counts.n_instances);
+                if (!stats_summed) {
+                    c->counts.n_instances = exchange_sum(c->comm, c->ws, c->counts.n_instances);
+                    if (fast_p2p) c->counts.n_distinct = exchange_sum(c->comm, c->ws, c->counts.n_distinct);   // the p2p path declined after all
+                }
             } else {
                 c->counts.n_kept = c->acc.m;
             }

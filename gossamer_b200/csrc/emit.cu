@@ -156,10 +156,10 @@ __global__ void ds_stats_kernel(const u8* __restrict__ type, const u64* __restri
 }
 
 // one CTA of 128 threads per select block
-// `body` holds this launch's blocks; off[] are offsets into it and body_base is its offset in the file
+// `body` holds this launch's blocks; off[] are FILE offsets and body_file_off is the file offset of body[0]
 template <typename F>
 __global__ void __launch_bounds__(128) ds_write_kernel(F f, u64 count, u64 b0, const u8* __restrict__ type, const u64* __restrict__ off,
-                                                       const u64* __restrict__ first_in, u8* __restrict__ body, u64 body_base,
+                                                       const u64* __restrict__ first_in, u8* __restrict__ body, u64 body_file_off,
                                                        u64* __restrict__ index_out, u64* __restrict__ rank_out) {
     __shared__ u32 scan_s[128 / 32 + 1];
     const u64 b = blockIdx.x;
@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(128) ds_write_kernel(F f, u64 count, u64 b0, c
     const u64 nb = count - j0 < kBlock ? count - j0 : kBlock;
     const u64 first = first_in[b];
     const u8 t = type[b];
-    u8* out = body + off[b];
+    u8* out = body + (off[b] - body_file_off);
     if (threadIdx.x == 0) {
-        index_out[b] = (body_base + off[b]) | t;
+        index_out[b] = off[b] | t;
         rank_out[b] = first;
     }
     if (t == T_SMALL) {
@@ -489,11 +489,15 @@ __global__ void high_bits_dist_kernel(GlobalKeys<K> G, u64 i0, u64 i1, int D, u6
     }
 }
 
+// Every rank classifies ALL blocks of the directory (a block's class and size need its first and last position, plus
+// the 128 sample spans for the rare "intermediate" class; positions outside the rank's slice are read from the owner
+// over NVLink), so each rank knows every file offset and the header statistics without a collective; it then writes
+// only the blocks [b0, b1) it owns.
 template <typename F>
 static void build_dense_select_dist(Emitter& em, Exchange* x, F f, u64 count, bool invert, const std::string& name, u64 b0, u64 b1) {
     Workspace& ws = *em.ws;
     cudaStream_t s = ws.stream;
-    const int n = exchange_size(x), rank = exchange_rank(x);
+    const int rank = exchange_rank(x);
     DsHeader h;
     memset(&h, 0, sizeof(h));
     h.version = 2012092701ull; h.flags = invert ? 1 : 0;
@@ -506,44 +510,38 @@ static void build_dense_select_dist(Emitter& em, Exchange* x, F f, u64 count, bo
         if (rank == 0) em.put_host(name, page.data(), page.size());
         return;
     }
-    const u64 nbl = b1 - b0;
-    DevBuf<u8> type(&ws, nbl);
-    DevBuf<u64> bytes(&ws, nbl), padded(&ws, nbl), first(&ws, nbl), off(&ws, nbl), tmp(&ws, scan_tmp_elems(nbl)), scalars(&ws, 8);
+    DevBuf<u8> type(&ws, nb);
+    DevBuf<u64> bytes(&ws, nb), padded(&ws, nb), first(&ws, nb), off(&ws, nb + 1), tmp(&ws, scan_tmp_elems(nb)), scalars(&ws, 8);
     GSB_CUDA_TRY(cudaMemsetAsync(scalars.p, 0, 64, s));
-    u64 host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int g = (int)std::max<u64>(1, std::min<u64>((nbl + 127) / 128, (u64)ws.sm_count * 8));
-    if (nbl) {
-        ds_classify_kernel<F><<<g, 128, 0, s>>>(f, count, b0, nbl, type.p, bytes.p, padded.p, first.p);
-        ++ws.launches;
-        exclusive_scan<u64, u64>(padded.p, off.p, nbl, 0ull, scalars.p + 6, tmp.p, s, &ws.launches);
-        ds_stats_kernel<<<g, 128, 0, s>>>(type.p, bytes.p, nbl, scalars.p);
-        ++ws.launches;
-        GSB_CUDA_TRY(cudaMemcpyAsync(host, scalars.p, 64, cudaMemcpyDeviceToHost, s));
-        ws.sync();
-    }
-    std::vector<u64> all;
-    exchange_allgather_u64(x, ws, host, 7, all);                 // [6] = padded bytes of the rank's blocks, [0..5] = statistics
-    u64 body_base = 4096, body_end = 4096, st[6] = {0, 0, 0, 0, 0, 0};
-    for (int r = 0; r < n; ++r) {
-        if (r < rank) body_base += all[7 * r + 6];
-        body_end += all[7 * r + 6];
-        for (int i = 0; i < 6; ++i) st[i] += all[7 * r + i];
-    }
+    const int g = (int)std::min<u64>((nb + 127) / 128, (u64)ws.sm_count * 8);
+    ds_classify_kernel<F><<<g, 128, 0, s>>>(f, count, 0, nb, type.p, bytes.p, padded.p, first.p);
+    ++ws.launches;
+    exclusive_scan<u64, u64>(padded.p, off.p, nb, 4096ull, scalars.p + 6, tmp.p, s, &ws.launches);
+    ds_stats_kernel<<<g, 128, 0, s>>>(type.p, bytes.p, nb, scalars.p);
+    ++ws.launches;
+    u64 host[8], seg[2] = {0, 0};
+    GSB_CUDA_TRY(cudaMemcpyAsync(host, scalars.p, 64, cudaMemcpyDeviceToHost, s));
+    if (b0 < nb) GSB_CUDA_TRY(cudaMemcpyAsync(&seg[0], off.p + b0, 8, cudaMemcpyDeviceToHost, s));
+    if (b1 < nb) GSB_CUDA_TRY(cudaMemcpyAsync(&seg[1], off.p + b1, 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    const u64 body_end = 4096 + host[6];
+    const u64 seg_begin = b0 < nb ? seg[0] : body_end, seg_end = b1 < nb ? seg[1] : body_end;
     h.indexArrayOffset = (body_end + 15) & ~15ull;
     h.rankArrayOffset = h.indexArrayOffset + 8 * nb;
     const u64 file_size = h.rankArrayOffset + 8 * nb;
     h.numBlocks = nb; h.indexSize = 16 * nb;
-    h.smallBlocks = st[0]; h.smallBlocksSize = st[1];
-    h.intermediateBlocks = st[2]; h.intermediateBlocksSize = st[3];
-    h.largeBlocks = st[4]; h.largeBlocksSize = st[5];
+    h.smallBlocks = host[0]; h.smallBlocksSize = host[1];
+    h.intermediateBlocks = host[2]; h.intermediateBlocksSize = host[3];
+    h.largeBlocks = host[4]; h.largeBlocksSize = host[5];
+    const u64 nbl = b1 - b0;
     if (nbl) {
-        const u64 body_bytes = host[6];
+        const u64 body_bytes = seg_end - seg_begin;
         DevBuf<u8> body(&ws, body_bytes);
         DevBuf<u64> index(&ws, nbl), ranks(&ws, nbl);
         GSB_CUDA_TRY(cudaMemsetAsync(body.p, 0, body_bytes ? body_bytes : 1, s));
-        ds_write_kernel<F><<<(unsigned)nbl, 128, 0, s>>>(f, count, b0, type.p, off.p, first.p, body.p, body_base, index.p, ranks.p);
+        ds_write_kernel<F><<<(unsigned)nbl, 128, 0, s>>>(f, count, b0, type.p + b0, off.p + b0, first.p + b0, body.p, seg_begin, index.p, ranks.p);
         ++ws.launches;
-        em.put_device_at(name, file_size, body_base, body.p, body_bytes);
+        em.put_device_at(name, file_size, seg_begin, body.p, body_bytes);
         em.put_device_at(name, file_size, h.indexArrayOffset + 8 * b0, index.p, 8 * nbl);
         em.put_device_at(name, file_size, h.rankArrayOffset + 8 * b0, ranks.p, 8 * nbl);
     }
@@ -723,14 +721,26 @@ void emit_count_histogram_dist(Emitter& em, Exchange* x, const DistRun& run, con
         pairs.resize(2 * rr.m);
         for (u64 i = 0; i < rr.m; ++i) { pairs[2 * i] = vals[i]; pairs[2 * i + 1] = freq[i]; }
     }
-    std::vector<u64> sizes;
+    // one all-gather of [number of pairs, the first kInline pairs]; a second one only if some rank has more
+    const u64 kInline = 510;
     const u64 mine_n = pairs.size() / 2;
-    exchange_allgather_u64(x, ws, &mine_n, 1, sizes);
+    std::vector<u64> msg(1 + 2 * kInline, 0), got;
+    msg[0] = mine_n;
+    for (u64 i = 0; i < std::min(mine_n, kInline) * 2; ++i) msg[1 + i] = pairs[i];
+    exchange_allgather_u64(x, ws, msg.data(), msg.size(), got);
+    std::vector<u64> sizes(n);
     u64 cap = 1;
-    for (int r = 0; r < n; ++r) cap = std::max(cap, sizes[r]);
-    pairs.resize(2 * cap, 0);
+    for (int r = 0; r < n; ++r) { sizes[r] = got[(size_t)r * msg.size()]; cap = std::max(cap, sizes[r]); }
     std::vector<u64> all;
-    exchange_allgather_u64(x, ws, pairs.data(), 2 * cap, all);
+    if (cap > kInline) {
+        pairs.resize(2 * cap, 0);
+        exchange_allgather_u64(x, ws, pairs.data(), 2 * cap, all);
+    } else {
+        cap = kInline;
+        all.resize((size_t)n * 2 * cap);
+        for (int r = 0; r < n; ++r)
+            for (u64 i = 0; i < 2 * cap; ++i) all[(size_t)r * 2 * cap + i] = got[(size_t)r * msg.size() + 1 + i];
+    }
     if (rank == 0) {
         std::map<u64, u64> hist;
         for (int r = 0; r < n; ++r)

@@ -520,7 +520,7 @@ static double host_now_ms() {
 }
 
 void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, u8* parted_buf /* n_keys keys */,
-                        DevBuf<u8>& recv, u64* recv_cap, u8** recv_ptr_out, u64* n_recv, ExchangeTiming* timing) {
+                        DevBuf<u8>& recv, u64* recv_cap, u8** recv_ptr_out, u64* n_recv, ExchangeTiming* timing, u64* piggyback_sum) {
     const bool trace = getenv("GSB_TRACE_EXCHANGE") != nullptr;
     double t_prev = host_now_ms();
     auto lap = [&](const char* what) {
@@ -541,16 +541,21 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
     if (key_bytes == 8) sample_strided_kernel<u64><<<(S + 255) / 256, 256, 0, s>>>((const u64*)keys, n_keys, S, mine.p);
     else sample_strided_kernel<Key128><<<(S + 255) / 256, 256, 0, s>>>((const Key128*)keys, n_keys, S, mine.p);
     ++ws.launches;
+    // the spare word of the sample slot carries one caller-supplied number that is summed over the ranks
+    if (piggyback_sum) GSB_CUDA_TRY(cudaMemcpyAsync(mine.p + 2 * S + 1, piggyback_sum, 8, cudaMemcpyHostToDevice, s));
     check(api.AllGather(mine.p, all.p, slot, ncclUint64, x->comm, s), "ncclAllGather(samples)");
     std::vector<u64> h(slot * n);
     GSB_CUDA_TRY(cudaMemcpyAsync(h.data(), all.p, h.size() * 8, cudaMemcpyDeviceToHost, s));
     ws.sync();
     std::vector<u64> samples;
+    u64 piggy = 0;
     for (int r = 0; r < n; ++r) {
         const u64* p = h.data() + slot * r;
+        piggy += p[2 * S + 1];
         if (p[2 * S] == 0) continue;
         samples.insert(samples.end(), p, p + 2 * (size_t)S);
     }
+    if (piggyback_sum) *piggyback_sum = piggy;
     Splitters sp;
     memset(&sp, 0, sizeof(sp));
     sp.n = n - 1;

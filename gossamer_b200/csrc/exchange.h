@@ -35,7 +35,8 @@ struct ExchangeTiming { double ms_all_to_all = 0; u64 bytes_sent_remote = 0; boo
 // (`parted_buf`, scratch for n_keys keys) + grouped ncclSend/ncclRecv into `recv`.
 // *recv_ptr_out is where the received instances are (the window or recv.p).
 void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, u8* parted_buf,
-                        DevBuf<u8>& recv, u64* recv_cap, u8** recv_ptr_out, u64* n_recv, ExchangeTiming* timing);
+                        DevBuf<u8>& recv, u64* recv_cap, u8** recv_ptr_out, u64* n_recv, ExchangeTiming* timing,
+                        u64* piggyback_sum = nullptr /* in: this rank's number, out: the sum over all ranks (rides on the sample all-gather) */);
 int exchange_rank(const Exchange* x);
 int exchange_size(const Exchange* x);
 // Collective.  Copies this rank's slice into its window and returns the global view; false if peer
