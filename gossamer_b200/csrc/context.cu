@@ -15,9 +15,11 @@ namespace gsb {
 // Workspace
 // ------------------------------------------------------------------------------------------
 // Size classes: 512 B steps below 1 MiB; above, multiples of max(2 MiB, 1/8 of the largest power
-// of two below the request) -- at most 12.5 % slack.  A block is only ever reused for a request of
-// the SAME class, so a repeated sequence of requests (every benchmark / pipeline step) maps onto
-// exactly the same blocks and never reaches the driver again.
+// of two below the request) -- at most 12.5 % slack.  A request takes the smallest cached block that is at
+// least its class and at most twice as large.  On one GPU every step repeats the same sequence of sizes and
+// hits its own blocks exactly; with several GPUs the sizes move by a few per cent from step to step (the
+// splitters come from a sample of keys whose order depends on atomics), and insisting on the exact class sent
+// some request of almost every step to cudaMalloc -- tens of milliseconds each with eight peer-mapped devices.
 static size_t round_block(size_t bytes) {
     if (bytes < 512) return 512;
     if (bytes < (1u << 20)) return (bytes + 511) & ~(size_t)511;
@@ -29,8 +31,8 @@ static size_t round_block(size_t bytes) {
 void* Workspace::alloc(size_t bytes) {
     const size_t want = round_block(bytes);
     void* p = nullptr;
-    auto it = free_.find(want);
-    if (it != free_.end()) {                                               // same size class: reuse
+    auto it = free_.lower_bound(want);
+    if (it != free_.end() && (it->first == want || (want >= (1u << 20) && it->first <= 2 * want))) {
         p = it->second;
         free_.erase(it);
     } else {

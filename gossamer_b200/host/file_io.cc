@@ -96,6 +96,10 @@ bool BlockReader::next(const uint8_t*& data, size_t& size, bool& last) {
     if (done_) return false;
     for (;;) {
         uint8_t* b = buf_[cur_];
+        // The tail carried over from the previous block is placed only now: that block may still be on its way to the
+        // device (GSB_BLOCK_ASYNC), and this buffer -- the one of the block before it -- is free again once the push
+        // of the previous block has returned.
+        if (carry_) memcpy(b, carry_store_.data(), carry_);
         size_t filled = carry_;
         if (!eof_) {
             size_t got = in_.read(b + filled, cap_ - filled);
@@ -105,12 +109,11 @@ bool BlockReader::next(const uint8_t*& data, size_t& size, bool& last) {
         size_t cut = cut_point(filled, eof_);
         if (cut == 0 && !eof_)
             throw Error{"\t'" + in_.name() + "': a single record is larger than the " + std::to_string(cap_ >> 20) + " MiB input block; raise --block-mb\n"};
-        // carry the tail into the other buffer
-        const int other = cur_ ^ 1;
+        // keep the tail (an incomplete line / record) for the next block
         carry_ = filled - cut;
-        if (carry_) memcpy(buf_[other], b + cut, carry_);
+        carry_store_.assign(b + cut, b + cut + carry_);
         data = b; size = cut; last = eof_ && carry_ == 0;
-        cur_ = other;
+        cur_ ^= 1;
         if (last) done_ = true;
         return true;
     }

@@ -50,7 +50,8 @@ private:
     size_t cap_;
     uint8_t* buf_[2] = {nullptr, nullptr};
     int cur_ = 0;
-    size_t carry_ = 0;       // bytes at the start of buf_[cur_] carried from the previous block
+    size_t carry_ = 0;       // bytes carried from the previous block (held in carry_store_ until the next call)
+    std::vector<uint8_t> carry_store_;
     bool eof_ = false, done_ = false;
 };
 

@@ -61,7 +61,10 @@ void run_build(const BuildOptions& opt, const GossCmdContext& cxt, int kind) {
             BlockReader rd(name, it.format, (size_t)opt.block_mb << 20);
             const uint8_t* data; size_t size; bool last;
             while (rd.next(data, size, last)) {
-                rc = gsb_push_block(h.c, data, size, it.format, last ? GSB_BLOCK_LAST_OF_FILE : 0);
+                // all but the last block of a file are pushed asynchronously: the copy of block i+1 (and the file read
+                // behind it -- BlockReader double-buffers in pinned memory) overlaps the device work of block i; the last
+                // block is synchronous, so that a parse error is always reported while its file is the current one
+                rc = gsb_push_block(h.c, data, size, it.format, last ? GSB_BLOCK_LAST_OF_FILE : GSB_BLOCK_ASYNC);
                 if (rc != GSB_OK) fail_from_library(h.c, rc, name);
             }
         }
