@@ -155,10 +155,18 @@ int gsb_reset(gsb_ctx* ctx);
 
 /* Multi-GPU (one process per GPU).  Rank 0 makes an id, the host program broadcasts its 128
  * bytes (torch.distributed / MPI / a file), every rank attaches.  After that
- * gsb_finish_counting range-partitions the locally reduced (key,count) runs by sampled
- * splitters, exchanges them with one ncclSend/ncclRecv all-to-all and merges; rank r then holds
- * the r-th contiguous slice of the global order.  gsb_gather_to_root moves all slices to rank 0
- * (in order) so that rank 0 can gsb_emit the whole graph. */
+ *   - gsb_finish_counting is a COLLECTIVE: the instances are range-partitioned by splitters sampled
+ *     from all ranks and stored straight into the owners' peer-mapped receive windows over NVLink
+ *     (CUDA IPC; grouped ncclSend/ncclRecv if peer memory cannot be mapped); each rank counts its
+ *     range, and the survivors are re-partitioned the same way so that rank r ends up holding the
+ *     r-th contiguous slice of the global sorted (edge, count) run;
+ *   - gsb_emit is a COLLECTIVE too: every rank writes its own byte ranges of every file -- its sink
+ *     receives pieces as open(name, size of the WHOLE file) / pwrite(offset, ...) / close, a file may
+ *     be opened more than once, and bytes that no rank writes are zero (open must not truncate a
+ *     file another rank has written to: O_CREAT without O_TRUNC + ftruncate(size));
+ *   - gsb_gather_to_root (optional) moves all slices to rank 0 instead; gsb_emit then hands the
+ *     complete files to rank 0's sink only.  It is also what gsb_emit falls back to without peer
+ *     memory. */
 #define GSB_NCCL_ID_BYTES 128
 int gsb_comm_make_id(void* id_out /* GSB_NCCL_ID_BYTES */);
 int gsb_comm_attach(gsb_ctx* ctx, const void* id, int n_ranks, int rank);
