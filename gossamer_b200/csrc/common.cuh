@@ -68,14 +68,27 @@ __device__ __forceinline__ Key128 key_rc(const Key128& x, int w) {              
 }
 
 // Bijective bit mixing of a key, used when instances are only GROUPED (counting from a partial sort,
-// sort.cu): the low bits of the mixed key depend on every base of the window, so keys that differ by one
-// substitution anywhere -- a true k-mer and its sequencing-error variants share most of their bases --
-// fall into different groups.  x ^ (x >> 32) is its own inverse on 64 bits; the high word of a 128-bit key
-// is folded into the low word first and left unchanged itself.
-__host__ __device__ __forceinline__ u64 key_mix(u64 x) { return x ^ (x >> 32); }
-__host__ __device__ __forceinline__ u64 key_unmix(u64 x) { return x ^ (x >> 32); }
-__host__ __device__ __forceinline__ Key128 key_mix(const Key128& x) { Key128 r; const u64 t = x.lo ^ x.hi; r.lo = t ^ (t >> 32); r.hi = x.hi; return r; }
-__host__ __device__ __forceinline__ Key128 key_unmix(const Key128& x) { Key128 r; const u64 t = x.lo ^ (x.lo >> 32); r.lo = t ^ x.hi; r.hi = x.hi; return r; }
+// sort.cu): every bit of the mixed key depends on every base of the window, so that keys which differ by
+// one or two substitutions -- a true k-mer and its sequencing-error variants share most of their bases --
+// fall into the same group of equal low bits only by chance.  The splitmix64 finaliser (two odd
+// multiplications, three xor-shifts) and its exact inverse; the high word of a 128-bit key is folded into
+// the low word and left unchanged itself.  (The first version, x ^ (x >> 32), is linear: two variants of one
+// k-mer with the same substitution pattern 16 bases apart collide in the low 40 bits -- 1.5 M groups with
+// several keys at config 2 instead of the ~1.5 k that chance allows.)
+__host__ __device__ __forceinline__ u64 key_mix(u64 z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ u64 key_unmix(u64 z) {
+    z = z ^ (z >> 31) ^ (z >> 62);
+    z *= 0x319642B2D24D8EC3ull;                                 // inverse of 0x94D049BB133111EB mod 2^64
+    z = z ^ (z >> 27) ^ (z >> 54);
+    z *= 0x96DE1B173F119089ull;                                 // inverse of 0xBF58476D1CE4E5B9 mod 2^64
+    return z ^ (z >> 30) ^ (z >> 60);
+}
+__host__ __device__ __forceinline__ Key128 key_mix(const Key128& x) { Key128 r; r.hi = x.hi; r.lo = key_mix(x.lo ^ key_mix(x.hi)); return r; }
+__host__ __device__ __forceinline__ Key128 key_unmix(const Key128& x) { Key128 r; r.hi = x.hi; r.lo = key_unmix(x.lo) ^ key_mix(x.hi); return r; }
 
 // ---- decoupled look-back over tiles ---------------------------------------------------------
 // state word = status (top 2 bits: 0 empty, 1 tile aggregate, 2 inclusive prefix) | value.

@@ -258,7 +258,10 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     bool reduced = false;
     if (c->mix && fused_final) {
         int lg = 0; while ((1ull << lg) < c->n_keys) ++lg;
-        int group_digits = std::max(1, std::min(c->passes, (lg + 12 + 7) / 8));
+        // group bits >= log2(n) + 4: a key shares its group with another one with probability <= D / 2^gb <= 1/16 (D
+        // distinct keys); with the duplication that makes this path worthwhile a few per cent of the instances end
+        // up in groups of several keys and take the full-sort path inside reduce_groups
+        int group_digits = std::max(1, std::min(c->passes, (lg + 4 + 7) / 8));
         if (const char* e = getenv("GSB_GROUP_DIGITS")) group_digits = std::max(1, std::min(c->passes, atoi(e)));   // test / profiling knob
         c->timer.start();
         where = sort_keys(ws, kb, c->key_bits, src, alt.p, nullptr, nullptr, c->n_keys, hist, &passes_run, &c->stats.ms_sort_sweeps, 0, group_digits);

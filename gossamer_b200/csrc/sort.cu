@@ -506,8 +506,8 @@ __global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __res
 // counting from a PARTIAL sort
 // ------------------------------------------------------------------------------------------
 // Equal keys agree in every digit, so after LSD sweeps over only the low `gb` bits all instances of a key
-// are already contiguous -- inside the "group" of keys that share those bits.  With gb >= log2(n) + 12 a
-// group almost always holds ONE distinct key (expected number of colliding pairs n^2 / 2^(gb+1)); then the
+// are already contiguous -- inside the "group" of keys that share those bits.  With gb >= log2(n) + 4 a
+// group mostly holds ONE distinct key (a key meets another one in its group with probability D / 2^gb); then the
 // group is a run and its length is the count, exactly as after a full sort, and the remaining sweeps over
 // n instances are not needed: only the survivors of the min-count filter (a few % of the instances when
 // sequencing errors dominate the distinct keys) are sorted by the full key afterwards, together with their
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __res
 //
 // The instances are stored bit-MIXED (key_mix, common.cuh) when this path is taken, so that the low bits depend
 // on the whole window: with the raw key, a true k-mer and its error variants whose error lies in the high bases
-// would share their low bits and nearly every group would hold several keys.  Outputs are un-mixed.
+// share their low bits and nearly every group holds several keys.  Outputs are un-mixed.
 //
 // One streaming pass, output order arbitrary (warp-aggregated appends): the full-key sort that follows
 // makes the final order deterministic because the surviving keys are distinct.
