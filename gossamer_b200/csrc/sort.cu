@@ -1063,11 +1063,10 @@ bool reduce_groups(Workspace& ws, int key_bytes, int key_bits, const void* group
     // h[1] = number of elements on the impure path from here on
     ReducedRun slow; u64 d2 = 0, self2 = 0;
     if (h[1]) {
-        // Groups holding several keys.  Their elements were copied group by group, so equal keys (same group) sit in one
-        // contiguous chunk; a STABLE sort on the digits above the group bits makes them adjacent, which is all the
-        // run-length reduce needs (its output order is arbitrary here anyway).
+        // Groups holding several keys (a few per cent of the instances at most, chance collisions of the mixed low
+        // bits): their elements were copied out un-mixed and go through the ordinary full sort + run-length reduce.
         DevBuf<u8> alt(&ws, h[1] * key_bytes);
-        const int where = sort_keys(ws, key_bytes, key_bits, imp.p, alt.p, nullptr, nullptr, h[1], nullptr, nullptr, nullptr, group_bits / 8, -1);
+        const int where = sort_keys(ws, key_bytes, key_bits, imp.p, alt.p, nullptr, nullptr, h[1], nullptr, nullptr);
         reduce_sorted(ws, key_bytes, where ? alt.p : imp.p, nullptr, h[1], min_count, slow, &d2, fold_w, &self2);
     }
     lap("impure groups: sort+rle", slow.m);
