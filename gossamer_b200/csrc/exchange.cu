@@ -1,11 +1,17 @@
-// exchange.cu -- multi-GPU step of the counting phase (one process per GPU).
+// exchange.cu -- multi-GPU steps of the counting phase (one process per GPU).
 //
 // The reference has no distributed mode; its scale-out advice is "build
-// parts, then merge-graphs" (docs/goss.md:315-321).  Here every rank counts its own share of
-// the reads, the locally reduced (key,count) runs are range-partitioned by splitters taken
-// from a sample of all ranks' keys, exchanged with ONE all-to-all (ncclSend/ncclRecv pairs in
-// a group, NVLink 5 / NVSwitch underneath) and merged, so that rank r ends up owning the r-th
-// contiguous slice of the global sorted edge set.
+// parts, then merge-graphs" (docs/goss.md:315-321).  Here every rank extracts the folded instance
+// keys of its own share of the reads; the instances, and later the surviving (key,count) pairs, are
+// range-partitioned by splitters taken from a sample of all ranks' keys and stored STRAIGHT INTO THE
+// OWNER'S MEMORY over NVLink: every rank has a receive window (cudaMalloc + CUDA IPC, mapped by all
+// peers), the partition kernel groups a tile's elements by destination in shared memory and writes
+// each run into the owner's window at the offset a count matrix reserved for this source.  Rank r
+// ends up owning -- and publishing in its window -- the r-th contiguous slice of the global sorted
+// edge set, which the distributed emitters (emit.cu) read.  NCCL carries only the small all-gathers
+// (samples, count matrices, statistics) and barriers; grouped ncclSend/ncclRecv is the data-path
+// fallback when peer memory cannot be mapped, and exchange_runs / exchange_gather are the
+// sorted-run variants used for merged batches and for gsb_gather_to_root.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch already loaded when the
 // host program is a torchrun rank), so single-GPU users need no NCCL at all.

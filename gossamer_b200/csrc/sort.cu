@@ -1,5 +1,6 @@
 // sort.cu -- counting by sorting: LSD radix sort (8-bit digits, one sweep per digit with
-// decoupled look-back), run-length reduce, min-count filter.
+// decoupled look-back), run-length reduce of fully sorted keys, group reduce of partially sorted
+// (bit-mixed) keys, min-count filter.
 //
 // Replaces (result-wise) BackyardHash::insert + BackyardHash::sort/BlendedSort + the
 // duplicate-merging emit loop (src/BackyardHash.cc:115-271, src/BlendedSort.hh:58-167,
