@@ -105,3 +105,19 @@ def test_cli_without_gpu_fails_loudly(tmp_path):
     r = _goss("build-graph", "-k", "3", "-O", str(tmp_path / "g"), "-I", str(fa))
     assert r.returncode == 1 and "error performing build-graph" in r.stderr and "no CPU path" in r.stderr
     assert not list(tmp_path.glob("g*"))
+
+
+def test_key_mix_is_a_bijection_and_separates_substitution_variants(tmp_path):
+    """gossamer_b200/csrc/keys.h: key_unmix(key_mix(x)) == x (64- and 128-bit keys) and single-base substitutions never share
+    the low 32 bits of the mixed key beyond chance -- compiled with the host compiler alone (tests/cpp/mix_check.cc)."""
+    import shutil
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    inc = "/usr/local/cuda/include"
+    if not cxx or not os.path.exists(os.path.join(inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = str(tmp_path / "mix_check")
+    r = subprocess.run([cxx, "-O2", "-std=c++17", "-w", "-I", inc, "-o", exe, os.path.join(ROOT, "tests", "cpp", "mix_check.cc")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
