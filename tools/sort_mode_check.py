@@ -1,6 +1,7 @@
-"""Correctness + per-sweep time of a sweep-kernel variant (gsb_debug_set_tuning id), e.g. `python tools/sort_mode_check.py 8`.
-Sorts random and skewed key sets through the C ABI with that variant and compares with numpy, then times 8 sweeps over
-198.3 M 64-bit keys (the config-2 instance count) for the default and the variant."""
+"""Correctness + per-sweep time of sweep-kernel variants (gsb_debug_set_tuning ids: tile shapes / look-back widths, see
+kShapes64 in csrc/sort.cu), e.g. `python tools/sort_mode_check.py 7 6 5`.  Sorts random and skewed key sets through the C ABI
+with the FIRST variant and compares with numpy, then times 8 sweeps over 198.3 M 64-bit keys (the config-2 instance count)
+for the default and every variant given."""
 import os
 import sys
 import time
@@ -10,7 +11,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gossamer_b200 as G
 
-tuning = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+tunings = [int(a) for a in sys.argv[1:]] or [0]
+tuning = tunings[0]
 L = G.lib()
 rng = np.random.default_rng(1)
 ok = True
@@ -30,7 +32,7 @@ good = np.array_equal(slo, np.sort(skew))
 ok &= good
 print(f"tuning {tuning} skewed digits: {'sorted' if good else 'WRONG'} ({passes} sweeps)", flush=True)
 L.gsb_debug_set_tuning(0)
-for t in (0, tuning):
+for t in [0] + tunings:
     t0 = time.time()
     sweep_ms, sort_ms, sweeps = G.debug_sort_bench(198_333_373, 64, iters=3, tuning=t)
     print(f"tuning {t}: {sweep_ms:.3f} ms per sweep, {sort_ms:.2f} ms per sort ({sweeps} sweeps) [{time.time() - t0:.1f} s]", flush=True)
