@@ -50,7 +50,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ms_h2d", "ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_merge", "ms_emit",
                                           "ms_d2h", "ms_exchange", "ms_sort_sweeps", "ms_all_to_all", "ms_unfold")] + \
                [(n, C.c_uint64) for n in ("exchange_bytes_sent", "exchange_peer_memory", "bytes_in", "bytes_out", "n_symbols", "sort_key_bytes", "sort_passes",
-                                          "sort_passes_model", "n_batches", "kernel_launches", "hbm_peak_bytes", "n_sorted_keys")]
+                                          "sort_passes_model", "n_batches", "kernel_launches", "hbm_peak_bytes", "n_sorted_keys", "device_allocs")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -67,7 +67,7 @@ class Sink(C.Structure):
 
 EXPORTS = ["gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
            "gsb_emit", "gsb_timer_begin", "gsb_timer_end", "gsb_host_alloc", "gsb_host_free", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root", "gsb_plan_splitters", "gsb_samples_per_rank",
-           "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_sort_bench", "gsb_debug_set_tuning", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
+           "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_sort_bench", "gsb_debug_set_tuning", "gsb_debug_set_partition", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
            "gsb_debug_extract"]
 
 _lib = None
@@ -349,6 +349,19 @@ def debug_sort_keys(lo, hi, key_bits, device=0):
     if rc < 0:
         raise GossamerError(int(rc), lib().gsb_last_error(None).decode())
     return lo, hi, int(rc)
+
+
+LEGACY_COUNTING = 1 << 16
+
+
+def debug_set_tuning(tuning_id):
+    """Test / profiling switches (see include/gossamer_b200.h); LEGACY_COUNTING selects the LSD-sort counting path."""
+    lib().gsb_debug_set_tuning(int(tuning_id))
+
+
+def debug_set_partition(max_slots=0, total_bits=0):
+    """Test-only: force the bucket geometry of the partition counting (0 = default)."""
+    lib().gsb_debug_set_partition(int(max_slots), int(total_bits))
 
 
 def debug_sort_bench(n, key_bits, iters=3, tuning=0, device=0):

@@ -49,6 +49,7 @@ void* Workspace::alloc(size_t bytes) {
         }
         size_of_[p] = want;
         reserved_bytes += want;
+        ++device_allocs;
     }
     live_bytes += size_of_[p];
     peak_bytes = std::max(peak_bytes, live_bytes);
@@ -114,7 +115,9 @@ struct gsb_ctx {
     DevBuf<u8> third;              // receive buffer of the instance all-to-all (multi-GPU only)
     u64 third_cap = 0;
     DevBuf<u64> cursor;            // device-side append cursor
-    DevBuf<u64> hist;              // fused digit histograms [passes][256]
+    DevBuf<u64> hist;              // histograms fused into the extraction: [256] top byte of the low key word (partition counting) or
+                                   // [passes][256] every digit (legacy LSD counting)
+    bool hist_valid = false;       // ... describe exactly the current batch
     DevBuf<IngestStatus> status;
     u64 max_batch_keys = 0;
 
@@ -159,6 +162,9 @@ struct gsb_ctx {
 
 namespace {
 
+// test / profiling switch (gsb_debug_set_tuning bit 16): count by the full LSD sort of raw keys instead of by partitioning
+int g_legacy_counting = 0;
+
 thread_local std::string g_create_error;
 
 template <typename F>
@@ -201,6 +207,7 @@ void reset_batch(gsb_ctx* c) {
     cudaStream_t s = c->ws.stream;
     GSB_CUDA_TRY(cudaMemsetAsync(c->cursor.p, 0, 8, s));
     GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), s));
+    c->hist_valid = c->comm == nullptr;                        // with a communicator the extraction takes no histograms
     c->n_keys = 0;
 }
 
@@ -228,10 +235,20 @@ void ensure_alt(gsb_ctx* c, u64 n) {
     if (n <= c->alt_cap) return;
     c->alt.free();
     c->alt_cap = std::max<u64>(n, c->keys_cap);
-    c->alt.reset(&c->ws, c->alt_cap * c->key_bytes);
+    c->alt.reset(&c->ws, c->alt_cap * c->key_bytes + 64);         // slack: bulk tile loads are rounded up to 16 bytes
 }
 
-// sort + run-length reduce the buffered instance keys; fold into the accumulated run
+// order a run of distinct (key, count) pairs by key
+void sort_run(gsb_ctx* c, ReducedRun& run) {
+    if (run.m < 2) return;
+    Workspace& ws = c->ws;
+    DevBuf<u8> kalt(&ws, run.m * c->key_bytes);
+    DevBuf<u64> calt(&ws, run.m);
+    const int where = sort_keys(ws, c->key_bytes, c->key_bits, run.keys.p, kalt.p, run.counts.p, calt.p, run.m, nullptr, nullptr);
+    if (where) { run.keys = std::move(kalt); run.counts = std::move(calt); }
+}
+
+// count the buffered instance keys; fold the result into the accumulated run
 void flush_batch(gsb_ctx* c, bool final_and_only) {
     if (c->n_keys == 0) return;
     Workspace& ws = c->ws;
@@ -241,9 +258,6 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     u8* const src = c->batch_src ? c->batch_src : c->keys.p;
     c->batch_src = nullptr;
     int passes_run = 0;
-    // digit histograms: fused into the extraction on one GPU, taken from the received instances after an
-    // instance exchange; a batch flushed BEFORE the exchange (multi-batch input with a communicator) has none yet
-    const u64* hist = (c->comm && !c->exchanged_instances) ? nullptr : c->hist.p;
     ReducedRun run; u64 distinct = 0, n_self_rc = 0;
     // The only batch of a build (on this rank, after any instance exchange): doubling of the
     // self-complementary keys and the min-count filter are fused into the run-length reduce.
@@ -251,37 +265,40 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     const bool fused_final = final_and_only && (!c->comm || c->exchanged_instances);
     const u64 min_count = (fused_final && c->cfg.kind == GSB_KIND_GRAPH) ? std::max<u64>(1, c->cfg.min_count) : 1;
     const int fold_w = (fused_final && c->any_self_rc) ? c->fold_w : 0;
-    // With a min-count filter the survivors are few: count from a PARTIAL sort (low digits of the bit-mixed key only,
-    // enough of them that a group of equal low bits is almost surely one key) and sort just the survivors by the full
-    // key afterwards (sort.cu "counting from a partial sort", fold.cu).
+    // Counting by partitioning (partition.cu): the instances are stored bit-mixed; two most-significant-digit passes bring
+    // equal keys into one bucket of ~3000 instances, which one CTA counts exactly in shared memory.  The survivors come back
+    // un-mixed in arbitrary order; whoever needs them ordered sorts the (few) distinct keys afterwards.
     int where = 0;
     bool reduced = false;
-    if (c->mix && fused_final) {
-        int lg = 0; while ((1ull << lg) < c->n_keys) ++lg;
-        // group bits >= log2(n) + 4: a key shares its group with another one with probability <= D / 2^gb <= 1/16 (D
-        // distinct keys); with the duplication that makes this path worthwhile a few per cent of the instances end
-        // up in groups of several keys and take the full-sort path inside reduce_groups
-        int group_digits = std::max(1, std::min(c->passes, (lg + 4 + 7) / 8));
-        if (const char* e = getenv("GSB_GROUP_DIGITS")) group_digits = std::max(1, std::min(c->passes, atoi(e)));   // test / profiling knob
-        c->timer.start();
-        where = sort_keys(ws, kb, c->key_bits, src, alt.p, nullptr, nullptr, c->n_keys, hist, &passes_run, &c->stats.ms_sort_sweeps, 0, group_digits);
-        c->timer.stop(c->stats.ms_sort);
-        c->stats.sort_passes += passes_run;
-        c->timer.start();
-        reduced = reduce_groups(ws, kb, c->key_bits, where ? alt.p : src, c->n_keys, std::min(8 * group_digits, c->key_bits), min_count, fold_w,
-                                where ? src : alt.p, run, &distinct, &n_self_rc);
-        c->timer.stop(c->stats.ms_reduce);
-        if (reduced) c->acc_unsorted = true;
-        else c->log(0, "partial-sort counting declined (many survivors or colliding groups): sorting by the full key instead");
+    if (c->mix) {
+        // the fused top-byte histogram describes exactly this batch only if it came straight out of the extraction
+        const u64* hist_top = (c->comm || !c->hist_valid) ? nullptr : c->hist.p;
+        PartitionTiming pt;
+        reduced = count_partitioned(ws, kb, c->key_bits, src, alt.p, c->n_keys, min_count, fold_w, hist_top, run, &distinct, &n_self_rc, &where, &pt);
+        c->stats.ms_sort += pt.ms_partition;
+        c->stats.ms_reduce += pt.ms_count;
+        c->stats.ms_sort_sweeps += pt.ms_scatter;
+        c->stats.sort_passes += pt.scatter_launches;
+        passes_run = 0;
+        if (reduced) {
+            if (fused_final) {
+                c->acc_unsorted = true;
+            } else if (run.m) {                                    // a batch that will be merged with others: order it by key
+                c->timer.start();
+                sort_run(c, run);
+                c->timer.stop(c->stats.ms_sort);
+            }
+        } else {
+            c->log(0, "partition counting declined (hardly any duplication under a min-count filter): sorting by the full key instead");
+        }
     }
     if (!reduced) {
         u8* const from = where ? alt.p : src;
         u8* const other = where ? src : alt.p;
+        const u64* hist = nullptr;
         c->timer.start();
-        if (c->mix) {                                              // real keys again; the fused histograms described the mixed ones
-            sort_unmix_inplace(kb, from, c->n_keys, ws.sm_count, ws.stream, &ws.launches);
-            hist = nullptr;
-        }
+        if (c->mix) sort_unmix_inplace(kb, from, c->n_keys, ws.sm_count, ws.stream, &ws.launches);   // real keys again
+        else if (c->hist_valid) hist = c->hist.p;
         passes_run = 0;
         const int where2 = sort_keys(ws, kb, c->key_bits, from, other, nullptr, nullptr, c->n_keys, hist, &passes_run, &c->stats.ms_sort_sweeps);
         where ^= where2;
@@ -318,7 +335,7 @@ void ensure_key_capacity(gsb_ctx* c, u64 extra) {
     }
     if (c->n_keys + extra <= c->keys_cap) return;
     u64 want = std::max<u64>(c->n_keys + extra, std::min<u64>(c->keys_cap * 2, c->max_batch_keys));
-    DevBuf<u8> bigger(&c->ws, want * kb);
+    DevBuf<u8> bigger(&c->ws, want * kb + 64);
     if (c->n_keys) GSB_CUDA_TRY(cudaMemcpyAsync(bigger.p, c->keys.p, c->n_keys * kb, cudaMemcpyDeviceToDevice, c->ws.stream));
     c->keys = std::move(bigger);
     c->keys_cap = want;
@@ -380,7 +397,7 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     // K3: windows -> keys (+ fused digit histograms)
     // (with a communicator attached the instances are exchanged before the sort and the digit histograms are taken from
     // what arrives, so the fused histograms -- the dominant cost of the kernel -- are switched off)
-    ingest_extract(c->cfg.kind, c->key_bytes, codes.p, valid.p, 64 + n_carry, n_sym_total, c->window, c->comm ? 0 : c->passes, c->mix ? 1 : 0,
+    ingest_extract(c->cfg.kind, c->key_bytes, codes.p, valid.p, 64 + n_carry, n_sym_total, c->window, c->comm ? 0 : (c->mix ? -1 : c->passes), c->mix ? 1 : 0,
                    c->keys.p, c->cursor.p, c->keys_cap, c->hist.p, c->status.p, ws.sm_count, s, &ws.launches);
     u64 cur = 0;
     GSB_CUDA_TRY(cudaMemcpyAsync(&cur, c->cursor.p, 8, cudaMemcpyDeviceToHost, s));
@@ -478,7 +495,7 @@ void init_ctx(gsb_ctx* c) {
 
     c->window = cfg.kind == GSB_KIND_GRAPH ? cfg.k + 1 : cfg.k;
     c->fold_w = cfg.kind == GSB_KIND_GRAPH ? c->window : 0;
-    c->mix = cfg.kind == GSB_KIND_GRAPH && cfg.min_count >= 2 && !getenv("GSB_FULL_SORT");
+    c->mix = !g_legacy_counting;
     c->key_bits = 2 * c->window;
     c->key_bytes = c->key_bits <= 64 ? 8 : 16;
     c->passes = (c->key_bits + 7) / 8;
@@ -619,31 +636,40 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
     return guarded(c, [&] {
         drain_pending(c);
         if (!c->counted) {
-            bool single = !c->have_acc;
-            bool exchanged_instances = false;
-            // whether ANY rank saw a self-complementary window (rides on the sample all-gather of the instance exchange)
-            u64 self_rc_all = c->self_rc_windows;
-            if (c->comm && !single) self_rc_all = exchange_sum(c->comm, c->ws, self_rc_all);
+            // Every rank must take the same sequence of collectives: whether ANY rank has flushed a batch already (then all
+            // ranks merge runs instead of exchanging raw instances) and whether any rank saw a self-complementary window are
+            // agreed on first.
+            u64 spilled = c->have_acc ? 1 : 0, self_rc_all = c->self_rc_windows;
+            if (c->comm) {
+                const u64 mine[2] = {spilled, self_rc_all};
+                std::vector<u64> all;
+                exchange_allgather_u64(c->comm, c->ws, mine, 2, all);
+                spilled = 0; self_rc_all = 0;
+                for (int r = 0; r < exchange_size(c->comm); ++r) { spilled += all[2 * r]; self_rc_all += all[2 * r + 1]; }
+            }
+            const bool single = spilled == 0;
             c->any_self_rc = self_rc_all > 0;
+            bool exchanged_instances = false;
             if (c->comm && single) {
-                // Multi-GPU, everything still buffered as raw instances: route each instance to the
-                // rank that owns its key range FIRST (one all-to-all of raw keys over NVLink), then
-                // sort + reduce locally exactly as on one GPU.  No merge step is needed.
+                // Multi-GPU, everything still buffered as raw instances: route each instance to the rank that owns its key
+                // range FIRST (one all-to-all of raw keys over NVLink), then count locally exactly as on one GPU.
                 const u64 local_instances = c->n_keys;
                 c->timer.start();
                 u64 n_recv = 0;
                 ExchangeTiming et;
                 ensure_alt(c, c->n_keys);
                 u8* recv_ptr = nullptr;
-                exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &recv_ptr, &n_recv, &et, &self_rc_all);
-                c->any_self_rc = self_rc_all > 0;
+                exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &recv_ptr, &n_recv, &et, nullptr);
                 c->stats.ms_all_to_all += et.ms_all_to_all;
                 c->stats.exchange_bytes_sent += et.bytes_sent_remote;
                 c->stats.exchange_peer_memory = et.used_peer_memory ? 1 : 0;
-                c->batch_src = recv_ptr;                           // the received instances are the batch to sort
+                c->batch_src = recv_ptr;                           // the received instances are the batch to count
                 c->n_keys = n_recv;
-                GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), c->ws.stream));
-                sort_digit_hist(c->key_bytes, recv_ptr, c->n_keys, c->passes, c->hist.p, c->ws.sm_count, c->ws.stream, &c->ws.launches);
+                if (!c->mix) {                                     // legacy LSD counting wants the digit histograms of what arrived
+                    GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), c->ws.stream));
+                    sort_digit_hist(c->key_bytes, recv_ptr, c->n_keys, c->passes, c->hist.p, c->ws.sm_count, c->ws.stream, &c->ws.launches);
+                    c->hist_valid = true;
+                }
                 c->timer.stop(c->stats.ms_exchange);
                 exchanged_instances = true;
                 c->instances_before_exchange = local_instances;
@@ -659,10 +685,14 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
             const u64 min_count = c->cfg.kind == GSB_KIND_GRAPH ? std::max<u64>(1, c->cfg.min_count) : 1;
             const bool filtered_already = single && (!c->comm || exchanged_instances);
             bool stats_summed = false;                         // n_instances / n_distinct already summed over the ranks
-            const bool fast_p2p = exchanged_instances && c->fold_w && exchange_peer_memory_usable(c->comm);   // sums ride on a later all-gather
+            // after an instance exchange the keys of a rank are spread over the whole (real) key space -- they were routed by
+            // their mixed value -- and a graph's reverse complements belong to other ranks anyway: one more re-partition
+            const bool repartition = c->comm && (c->fold_w || exchanged_instances);
+            const bool fast_p2p = exchanged_instances && exchange_peer_memory_usable(c->comm);   // sums ride on a later all-gather
             if (exchanged_instances && !fast_p2p) c->counts.n_distinct = exchange_sum(c->comm, c->ws, c->counts.n_distinct);
             if (!filtered_already) {
-                // merged batches (and/or exchanged reduced runs): still folded, raw occurrence counts
+                // merged batches (and/or exchanged reduced runs): sorted, still folded, raw occurrence counts
+                if (c->acc_unsorted) throw StatusError{GSB_EINVAL, "internal: unsorted run outside the single-batch path"};
                 u64 local_distinct = c->acc.m;
                 if (c->fold_w && c->acc.m && c->any_self_rc) {
                     c->timer.start();
@@ -686,75 +716,72 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                 }
                 c->counts.n_distinct = c->comm ? exchange_sum(c->comm, c->ws, local_distinct) : local_distinct;
             }
-            if (c->fold_w) {
-                bool done = false;
-                if (c->acc_unsorted && !filtered_already) throw StatusError{GSB_EINVAL, "internal: unsorted run outside the single-batch path"};
-                if (c->comm && exchange_peer_memory_usable(c->comm)) {
-                    // Multi-GPU: a key's reverse complement falls into another rank's range of the FINAL order.
-                    // U = acc ++ rc(acc) is built unsorted, every pair is stored straight into the window of the rank
-                    // that owns its range (splitters sampled from U itself, so the final slices are balanced), and the
-                    // owner sorts what it received -- the slice is then already published for the emitters.
-                    const u64 m = c->acc.m;
-                    const int kb = c->key_bytes;
+            // acc: final counts, filtered, folded (graphs); sorted by key unless acc_unsorted
+            bool done = false;
+            if (repartition && exchange_peer_memory_usable(c->comm)) {
+                // U = acc (++ rc(acc) for graphs) is built unsorted, every pair is stored straight into the window of the rank
+                // that owns its range of the FINAL order (splitters sampled from U itself, so the slices are balanced), and
+                // the owner sorts what it received -- the slice is then already published for the emitters.
+                const u64 m = c->acc.m;
+                const int kb = c->key_bytes;
+                c->timer.start();
+                const u64 u_cap = c->fold_w ? 2 * m : m;
+                DevBuf<u8> uk(&c->ws, u_cap * kb);
+                DevBuf<u64> uc(&c->ws, u_cap);
+                if (m) {
+                    GSB_CUDA_TRY(cudaMemcpyAsync(uk.p, c->acc.keys.p, m * kb, cudaMemcpyDeviceToDevice, c->ws.stream));
+                    GSB_CUDA_TRY(cudaMemcpyAsync(uc.p, c->acc.counts.p, m * 8, cudaMemcpyDeviceToDevice, c->ws.stream));
+                }
+                const u64 n_rc = c->fold_w ? unfold_append_rc(c->ws, kb, c->fold_w, c->acc.keys.p, c->acc.counts.p, m, uk.p + m * kb, uc.p + m) : 0;
+                c->timer.stop(c->stats.ms_unfold);
+                c->timer.start();
+                u8* rk = nullptr; u64* rc = nullptr;
+                std::vector<u64> totals;
+                const bool ok = exchange_pairs_p2p(c->comm, c->ws, kb, uk.p, uc.p, m + n_rc, &rk, &rc, &totals);
+                c->timer.stop(c->stats.ms_exchange);
+                if (ok) {
+                    uk.free(); uc.free();
+                    const u64 mine = totals[exchange_rank(c->comm)];
                     c->timer.start();
-                    DevBuf<u8> uk(&c->ws, 2 * m * kb);
-                    DevBuf<u64> uc(&c->ws, 2 * m);
-                    if (m) {
-                        GSB_CUDA_TRY(cudaMemcpyAsync(uk.p, c->acc.keys.p, m * kb, cudaMemcpyDeviceToDevice, c->ws.stream));
-                        GSB_CUDA_TRY(cudaMemcpyAsync(uc.p, c->acc.counts.p, m * 8, cudaMemcpyDeviceToDevice, c->ws.stream));
+                    DevBuf<u8> bk(&c->ws, mine * kb);
+                    DevBuf<u64> bc(&c->ws, mine);
+                    const int where = sort_keys(c->ws, kb, c->key_bits, rk, bk.p, rc, bc.p, mine, nullptr, nullptr);
+                    if (mine) {                              // keep one copy in the window (for the peers) and one as acc
+                        const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+                        GSB_CUDA_TRY(cudaMemcpyAsync(where ? (void*)rk : (void*)bk.p, where ? (void*)bk.p : (void*)rk, mine * kb, d2d, c->ws.stream));
+                        GSB_CUDA_TRY(cudaMemcpyAsync(where ? rc : bc.p, where ? bc.p : rc, mine * 8, d2d, c->ws.stream));
                     }
-                    const u64 n_rc = unfold_append_rc(c->ws, kb, c->fold_w, c->acc.keys.p, c->acc.counts.p, m, uk.p + m * kb, uc.p + m);
+                    c->acc.keys = std::move(bk); c->acc.counts = std::move(bc); c->acc.m = mine;
                     c->timer.stop(c->stats.ms_unfold);
                     c->timer.start();
-                    u8* rk = nullptr; u64* rc = nullptr;
-                    std::vector<u64> totals;
-                    const bool ok = exchange_pairs_p2p(c->comm, c->ws, kb, uk.p, uc.p, m + n_rc, &rk, &rc, &totals);
+                    exchange_view(c->comm, kb, totals, &c->dist);
+                    // one all-gather: the global statistics, and the barrier that makes every slice sorted and in place
+                    // before anyone reads a neighbour's
+                    const u64 mine_stats[2] = {c->counts.n_instances, exchanged_instances ? c->counts.n_distinct : 0};
+                    std::vector<u64> all_stats;
+                    exchange_allgather_u64(c->comm, c->ws, mine_stats, 2, all_stats);
+                    u64 inst = 0, dist = 0;
+                    for (int r = 0; r < exchange_size(c->comm); ++r) { inst += all_stats[2 * r]; dist += all_stats[2 * r + 1]; }
+                    c->counts.n_instances = inst;
+                    if (exchanged_instances) c->counts.n_distinct = dist;
+                    stats_summed = true;
+                    c->dist_ready = true;
                     c->timer.stop(c->stats.ms_exchange);
-                    if (ok) {
-                        uk.free(); uc.free();
-                        const u64 mine = totals[exchange_rank(c->comm)];
-                        c->timer.start();
-                        DevBuf<u8> bk(&c->ws, mine * kb);
-                        DevBuf<u64> bc(&c->ws, mine);
-                        const int where = sort_keys(c->ws, kb, c->key_bits, rk, bk.p, rc, bc.p, mine, nullptr, nullptr);
-                        if (mine) {                              // keep one copy in the window (for the peers) and one as acc
-                            const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
-                            GSB_CUDA_TRY(cudaMemcpyAsync(where ? (void*)rk : (void*)bk.p, where ? (void*)bk.p : (void*)rk, mine * kb, d2d, c->ws.stream));
-                            GSB_CUDA_TRY(cudaMemcpyAsync(where ? rc : bc.p, where ? bc.p : rc, mine * 8, d2d, c->ws.stream));
-                        }
-                        c->acc.keys = std::move(bk); c->acc.counts = std::move(bc); c->acc.m = mine;
-                        c->timer.stop(c->stats.ms_unfold);
-                        c->timer.start();
-                        exchange_view(c->comm, kb, totals, &c->dist);
-                        // one all-gather: the global statistics, and the barrier that makes every slice sorted and in place
-                        // before anyone reads a neighbour's
-                        const u64 mine_stats[2] = {c->counts.n_instances, exchanged_instances ? c->counts.n_distinct : 0};
-                        std::vector<u64> all_stats;
-                        exchange_allgather_u64(c->comm, c->ws, mine_stats, 2, all_stats);
-                        u64 inst = 0, dist = 0;
-                        for (int r = 0; r < exchange_size(c->comm); ++r) { inst += all_stats[2 * r]; dist += all_stats[2 * r + 1]; }
-                        c->counts.n_instances = inst;
-                        if (exchanged_instances) c->counts.n_distinct = dist;
-                        stats_summed = true;
-                        c->dist_ready = true;
-                        c->timer.stop(c->stats.ms_exchange);
-                        done = true;
-                    }
+                    done = true;
                 }
-                if (!done) {
-                    // restore both strands locally: acc := sorted(acc U rc(acc))
-                    c->timer.start();
-                    unfold_run(c->ws, c->key_bytes, c->key_bits, c->fold_w, c->acc, !c->acc_unsorted);
-                    c->timer.stop(c->stats.ms_unfold);
-                    if (c->comm) {
-                        // a rank's reverse complements fall into other ranks' key ranges: partition the full runs again
-                        c->timer.start();
-                        exchange_runs(c->comm, c->ws, c->key_bytes, c->key_bits, c->acc);
-                        c->timer.stop(c->stats.ms_exchange);
-                    }
-                }
-                c->acc_unsorted = false;
             }
+            if (!done) {
+                c->timer.start();
+                if (c->fold_w) unfold_run(c->ws, c->key_bytes, c->key_bits, c->fold_w, c->acc, !c->acc_unsorted);   // acc := sorted(acc U rc(acc))
+                else if (c->acc_unsorted) sort_run(c, c->acc);
+                c->timer.stop(c->stats.ms_unfold);
+                if (repartition) {
+                    c->timer.start();
+                    exchange_runs(c->comm, c->ws, c->key_bytes, c->key_bits, c->acc);
+                    c->timer.stop(c->stats.ms_exchange);
+                }
+            }
+            c->acc_unsorted = false;
             if (c->comm) {
                 // publish the slice in this rank's peer-mapped window: the distributed emitters work from there
                 if (!c->dist_ready) {
@@ -835,6 +862,7 @@ int gsb_get_stats(const gsb_ctx* c, gsb_stats* out) {
     *out = c->stats;
     out->kernel_launches = c->ws.launches;
     out->hbm_peak_bytes = c->ws.peak_bytes;
+    out->device_allocs = c->ws.device_allocs;
     return GSB_OK;
 }
 
@@ -867,7 +895,10 @@ int gsb_comm_attach(gsb_ctx* c, const void* id, int n_ranks, int rank) {
     if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return GSB_EINVAL;
     return guarded(c, [&] {
         if (c->comm) throw StatusError{GSB_EINVAL, "communicator already attached"};
+        if (n_ranks > kMaxRanks) throw StatusError{GSB_EINVAL, "at most " + std::to_string(kMaxRanks) + " ranks are supported"};
+        if (c->n_keys || c->have_acc) throw StatusError{GSB_EINVAL, "gsb_comm_attach after input has been pushed (attach first, or gsb_reset)"};
         c->comm = exchange_create(id, n_ranks, rank, c->ws);
+        c->hist_valid = false;
     });
 }
 
@@ -930,9 +961,15 @@ int64_t gsb_debug_extract(int device, const void* text, size_t nbytes, int forma
         std::vector<u64> raw(take * (c->key_bytes / 8));
         GSB_CUDA_TRY(cudaMemcpyAsync(raw.data(), c->keys.p, take * c->key_bytes, cudaMemcpyDeviceToHost, c->ws.stream));
         c->ws.sync();
-        for (u64 i = 0; i < take; ++i) {
-            if (c->key_bytes == 8) { if (key_lo) key_lo[i] = raw[i]; if (key_hi) key_hi[i] = 0; }
-            else { if (key_lo) key_lo[i] = raw[2 * i]; if (key_hi) key_hi[i] = raw[2 * i + 1]; }
+        for (u64 i = 0; i < take; ++i) {                           // the instances are stored bit-mixed: hand back the real keys
+            if (c->key_bytes == 8) {
+                const u64 k = c->mix ? key_unmix(raw[i]) : raw[i];
+                if (key_lo) key_lo[i] = k; if (key_hi) key_hi[i] = 0;
+            } else {
+                Key128 k; k.lo = raw[2 * i]; k.hi = raw[2 * i + 1];
+                if (c->mix) k = key_unmix(k);
+                if (key_lo) key_lo[i] = k.lo; if (key_hi) key_hi[i] = k.hi;
+            }
         }
         if (n_reads) *n_reads = c->counts.n_reads;
     });
@@ -1030,7 +1067,9 @@ int gsb_debug_sort_bench(int device, uint64_t n, int key_bits, int iters, int tu
     });
 }
 
-int gsb_debug_set_tuning(int id) { sort_set_tuning(id); return GSB_OK; }
+int gsb_debug_set_partition(int max_slots, int total_bits) { partition_set_debug((u32)(max_slots < 0 ? 0 : max_slots), total_bits); return GSB_OK; }
+
+int gsb_debug_set_tuning(int id) { g_legacy_counting = (id >> 16) & 1; sort_set_tuning(id & 0xFFFF); return GSB_OK; }
 
 int gsb_debug_emit_sparse_array(int device, const uint64_t* key_lo, const uint64_t* key_hi, uint64_t m,
                                 uint64_t universe_lo, uint64_t universe_hi, uint64_t m_est,

@@ -350,6 +350,7 @@ static bool ensure_windows(Exchange* x, Workspace& ws, u64 need_bytes, const std
         x->recv_buf = nullptr;
         x->recv_cap_bytes = need_bytes + need_bytes / 8 + (1u << 20);
         GSB_CUDA_TRY(cudaMalloc((void**)&x->recv_buf, x->recv_cap_bytes));
+        ++ws.device_allocs;
     }
     struct Slot { cudaIpcMemHandle_t h; u64 cap; u64 ok; };
     Slot mine_h;
@@ -649,7 +650,7 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
         if (total > *recv_cap) {                                      // grow-only: steady-state steps allocate nothing
             recv.free();
             *recv_cap = total + total / 16 + 1024;
-            recv.reset(&ws, *recv_cap * key_bytes);
+            recv.reset(&ws, *recv_cap * key_bytes + 64);
         }
         GSB_CUDA_TRY(cudaEventRecord(e0, s));
         check(api.GroupStart(), "ncclGroupStart");

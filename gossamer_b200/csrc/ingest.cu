@@ -384,7 +384,8 @@ static const int kExThreads = 256;
 // instances; fold.cu restores both strands after the run-length reduce.
 static const int kExItems = 4;                                  // stream positions per thread per iteration
 
-// PASSES > 0 unrolls the histogram update (7 = k 25, 8 = k 31, 14 = k 55); 0 = run-time count.
+// PASSES > 0 unrolls the histogram update (7 = k 25, 8 = k 31, 14 = k 55); 0 = run-time count; -1 = ONE histogram, of
+// the top byte of the low key word (what the first partition pass of partition.cu splits by).
 template <typename K, int MODE, int PASSES>
 __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restrict__ codes, const u32* __restrict__ valid,
                                                              u64 p_begin, u64 p_end, int w, int passes_rt, int mix,
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
                                                              u64* __restrict__ digit_hist /* [passes][256] */, IngestStatus* st) {
     typedef KeyOps<K> KO;
     typedef WindowOps<K> WO;
-    const int passes = PASSES ? PASSES : passes_rt;
+    const int passes = PASSES > 0 ? PASSES : (PASSES < 0 ? 1 : passes_rt);
     extern __shared__ u32 hist_s[];                            // [passes][256]
     __shared__ u32 warp_cnt[kExThreads / 32];
     __shared__ u64 base_s;
@@ -424,11 +425,11 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
                     if (MODE == GSB_KIND_GRAPH) {               // fold the two strands
                         if (KO::lt(r, x[it])) x[it] = r;
                         else if (KO::eq(r, x[it])) atomicAdd(&st->n_self_rc, 1ull);   // rare: lets the reduce skip its self-complement test
-                        if (mix) x[it] = key_mix(x[it]);        // instances will only be grouped, not ordered (sort.cu)
                     } else {                                    // position_type::normalize, src/RankSelect.hh:126-140
                         const u64 h0 = WO::hash(x[it]), h1 = WO::hash(r);
                         if (h0 > h1 || (h0 == h1 && KO::lt(r, x[it]))) x[it] = r;
                     }
+                    if (mix) x[it] = key_mix(x[it]);            // instances will only be grouped, not ordered (partition.cu)
                 }
             }
             ballot[it] = __ballot_sync(0xffffffffu, ok);
@@ -450,9 +451,11 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
                 const u64 idx = base_s + (u64)(slot + __popc(ballot[it] & lt));
                 if (idx < capacity) out[idx] = x[it];
                 else st->error = GSB_PE_KEY_OVERFLOW;
-                if (PASSES) {
+                if (PASSES < 0) {
+                    atomicAdd(&hist_s[(u32)(KO::lo(x[it]) >> 56)], 1u);
+                } else if (PASSES > 0) {
 #pragma unroll
-                    for (int d = 0; d < (PASSES ? PASSES : 1); ++d) atomicAdd(&hist_s[d * 256 + KO::digit(x[it], 8 * d)], 1u);
+                    for (int d = 0; d < (PASSES > 0 ? PASSES : 1); ++d) atomicAdd(&hist_s[d * 256 + KO::digit(x[it], 8 * d)], 1u);
                 } else {
                     for (int d = 0; d < passes; ++d) atomicAdd(&hist_s[d * 256 + KO::digit(x[it], 8 * d)], 1u);
                 }
@@ -550,7 +553,7 @@ static void launch_extract_p(int kind, const u64* codes, const u32* valid, u64 p
     const u64 span = (u64)kExThreads * kExItems;
     u64 tiles = (p_end - p_begin + span - 1) / span;
     int grid = (int)(tiles < (u64)sm_count * 8 ? tiles : (u64)sm_count * 8);
-    size_t smem = (size_t)passes * 256 * sizeof(u32);
+    size_t smem = (size_t)(passes < 0 ? 1 : passes) * 256 * sizeof(u32);
     if (kind == GSB_KIND_GRAPH)
         extract_kernel<K, GSB_KIND_GRAPH, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st);
     else
@@ -561,6 +564,7 @@ template <typename K>
 static void launch_extract(int kind, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes, int mix,
                            K* out, u64* cursor, u64 capacity, u64* digit_hist, IngestStatus* st, int sm_count, cudaStream_t s) {
     switch (passes) {
+        case -1: launch_extract_p<K, -1>(kind, codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st, sm_count, s); break;
         case 7: launch_extract_p<K, 7>(kind, codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st, sm_count, s); break;
         case 8: launch_extract_p<K, 8>(kind, codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st, sm_count, s); break;
         case 14: launch_extract_p<K, 14>(kind, codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st, sm_count, s); break;

@@ -42,6 +42,7 @@ struct Workspace {
     int sm_count = 148;
     u64 launches = 0;
     u64 live_bytes = 0, peak_bytes = 0, reserved_bytes = 0;
+    u64 device_allocs = 0;       // cudaMalloc calls (the caching allocator's misses + the exchange windows)
     void* alloc(size_t bytes);
     void release(void* p, size_t bytes);
     void sync();
@@ -135,6 +136,24 @@ void sort_unmix_inplace(int key_bytes, void* keys, u64 n, int sm_count, cudaStre
 // sort (digits group_bits/8 .. P) and uses reduce_sorted.
 bool reduce_groups(Workspace& ws, int key_bytes, int key_bits, const void* grouped, u64 n, int group_bits, u64 min_count, int fold_w,
                    void* out_keys_scratch, ReducedRun& out, u64* m_distinct, u64* n_self_rc);
+
+// number of elements the descriptors {first index, length} cover -> *total_dev (sort.cu)
+void sort_desc_total(const ulonglong2* desc, u64 n_desc, u64* total_dev, cudaStream_t s, u64* launches);
+
+// ---- partition.cu ------------------------------------------------------------------------------
+struct PartitionPlan { int total_bits = 0, levels = 0; int bits[8] = {0, 0, 0, 0, 0, 0, 0, 0}; u32 max_slots = 0; };
+PartitionPlan partition_plan(int key_bytes, u64 n);
+u32 partition_tile_keys(int key_bytes);
+void partition_set_debug(u32 max_slots, int total_bits);          // test-only geometry overrides (0 = default)
+struct PartitionTiming { double ms_partition = 0, ms_count = 0, ms_scatter = 0; int levels = 0, total_bits = 0; u64 scatter_launches = 0, n_overflow_keys = 0; };
+// Counting by partitioning (partition.cu): n bit-MIXED keys in `a` (`b`: scratch of the same size, both overwritten; both
+// need 16 bytes of slack behind the n-th key) -> every distinct key (un-mixed) with final count >= min_count, in
+// ARBITRARY order.  fold_w as in reduce_sorted.  hist_top: optional [256] histogram of the top byte of the low key word.
+// key_bits: significant bits of the REAL key.  Returns false (nothing produced) when min_count > 1 and the survivors do
+// not fit the output buffers (hardly any duplication): the caller then sorts by the full key; *where_keys says whether the
+// (still mixed, permuted) keys are in a (0) or b (1).
+bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64 n, u64 min_count, int fold_w, const u64* hist_top,
+                       ReducedRun& out, u64* m_distinct, u64* n_self_rc, int* where_keys = nullptr, PartitionTiming* timing = nullptr);
 
 // ---- fold.cu ---------------------------------------------------------------------------------
 // Strand folding (graph mode): instances are counted as min(x, rc x); these restore both strands.

@@ -1,0 +1,692 @@
+// partition.cu -- counting by PARTITIONING: most-significant-digit passes over the bit-mixed instance keys until a
+// bucket fits into one SM's shared memory, then an exact hash count of every bucket in shared memory.
+//
+// Replaces (result-wise) BackyardHash::insert + the duplicate-merging emit loop + trim-graph's predicate
+// (src/BackyardHash.cc:115-242, src/GossCmdBuildGraph.cc:239-258, src/GossCmdTrimGraph.cc:119): the same multiset of
+// keys, the same count per distinct key.
+//
+// Why not the LSD sort of sort.cu for the instances: ncu showed the 8-bit LSD sweep bound by instruction issue, not by
+// HBM -- 120 SASS instructions per key, more than half of them the 8 warp ballots per key that a STABLE ranking needs.
+// Counting needs no order at all, only that equal keys meet.  So:
+//   * the keys are bit-mixed (key_mix, keys.h): uniform, whatever the genome looks like;
+//   * a pass splits every parent bucket by the next <= 8 high bits of the mixed key.  Nothing has to be stable, so the
+//     rank of a key inside its tile is simply what ONE shared-memory atomicAdd on its digit's counter returns, and the
+//     place of the tile's run inside the child bucket is what ONE global atomicAdd per (tile, digit) on the child's
+//     cursor returns -- no ballots, no look-back chain between tiles.  ~25 instructions per key: the pass is HBM bound.
+//     Tiles are fetched with cp.async.bulk into shared memory behind an mbarrier, one tile ahead of the ranking;
+//   * after ceil(log2(n / 3000)) bits (two passes at 200 M keys) a bucket holds ~3000 instances.  One CTA counts a
+//     bucket in an open-addressing table in shared memory (exact 64/128-bit key compare), applies the self-complement
+//     doubling and the min-count filter, un-mixes the survivors and appends (key, count) to the output.
+// Buckets that do not fit (a k-mer repeated a million times) are copied out and go through the full LSD sort +
+// run-length reduce of sort.cu, so the result never depends on the bucket geometry.
+#include <algorithm>
+#include <cstdio>
+
+#include "kernels.h"
+#include "scan.cuh"
+
+namespace gsb {
+
+namespace {
+
+static const int kPtThreads = 256;
+static const int kPtTileBytes = 32768;
+
+// ---- mbarrier / bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk) ------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra WAIT_DONE;\n\t"
+                 "bra WAIT_LOOP;\n\t"
+                 "WAIT_DONE:\n\t}" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+struct TileRef { u64 begin; u32 count; u32 parent; };
+
+// descs == nullptr: one parent covering [0, n)
+__device__ __forceinline__ TileRef tile_ref(const uint4* __restrict__ descs, u32 tile, u64 n, u32 tile_keys) {
+    TileRef r;
+    if (descs) {
+        const uint4 d = descs[tile];
+        r.begin = (u64)d.x | ((u64)d.y << 32); r.count = d.z; r.parent = d.w;
+    } else {
+        r.begin = (u64)tile * tile_keys;
+        const u64 rem = n - r.begin;
+        r.count = rem < (u64)tile_keys ? (u32)rem : tile_keys;
+        r.parent = 0;
+    }
+    return r;
+}
+
+// Consecutive tiles belong to the same parent and would hammer the same 2^bits cursors (one or two L2 slices):
+// CTAs take their tiles in a strided permutation so that the tiles in flight spread over all parents.
+__device__ __forceinline__ u32 perm_mul(u32 n_tiles) {
+    if (n_tiles < 64) return 1;
+    if (n_tiles % 7919u) return 7919u;
+    if (n_tiles % 10007u) return 10007u;
+    return 1;
+}
+__device__ __forceinline__ u32 perm_tile(u32 i, u32 mul, u32 n_tiles) { return (u32)(((u64)i * mul) % n_tiles); }
+
+struct PartArgs {
+    const void* in;
+    void* out;
+    const uint4* descs;        // per-tile {begin lo, begin hi, count, parent}; nullptr = single parent [0, n)
+    const u32* n_tiles_dev;    // nullptr = n_tiles
+    u32 n_tiles;
+    u64 n;
+    u64* cursor;               // [(parent << bits | digit) * cstride]: next free slot of the child (absolute index in out)
+    u64* hist;                 // [parent << bits | digit]
+    u32 cstride;
+    int shift, bits;           // digit = (word >> shift) & (2^bits - 1), word = low 64 bits of the mixed key
+};
+
+template <typename K> __device__ __forceinline__ u32 part_digit(const K& k, int shift, u32 mask) { return (u32)(KeyOps<K>::lo(k) >> shift) & mask; }
+
+// ---- digit histogram of one level ----------------------------------------------------------------------------------
+template <typename K>
+__global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
+    constexpr int ITEMS = kPtTileBytes / (int)sizeof(K) / kPtThreads;
+    constexpr u32 TILE = kPtThreads * ITEMS;
+    __shared__ u32 cnt_s[256];
+    const int t = threadIdx.x;
+    const K* __restrict__ in = (const K*)a.in;
+    const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles;
+    const u32 mul = perm_mul(n_tiles);
+    const u32 mask = (1u << a.bits) - 1;
+    cnt_s[t] = 0;
+    __syncthreads();
+    u32 cur_parent = 0xffffffffu;
+    auto flush = [&]() {
+        __syncthreads();
+        const u32 c = cnt_s[t];
+        if (c) atomicAdd(&a.hist[((u64)cur_parent << a.bits) | (u32)t], (u64)c);
+        cnt_s[t] = 0;
+        __syncthreads();
+    };
+    for (u32 it = blockIdx.x; it < n_tiles; it += gridDim.x) {
+        const TileRef tr = tile_ref(a.descs, perm_tile(it, mul, n_tiles), a.n, TILE);
+        if (tr.parent != cur_parent) {                               // uniform over the CTA
+            if (cur_parent != 0xffffffffu) flush();
+            cur_parent = tr.parent;
+        }
+        K key[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const u32 j = (u32)t + (u32)i * kPtThreads;
+            if (j < tr.count) key[i] = in[tr.begin + j];
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const u32 j = (u32)t + (u32)i * kPtThreads;
+            if (j < tr.count) atomicAdd(&cnt_s[part_digit<K>(key[i], a.shift, mask)], 1u);
+        }
+    }
+    if (cur_parent != 0xffffffffu) flush();
+}
+
+// ---- one partition pass ------------------------------------------------------------------------------------------------
+// Persistent CTAs; per tile:
+//   wait for the tile in shared memory (bulk copy issued one tile ahead) -> keys to registers, rank = what the atomicAdd on
+//   the digit's counter returns -> [barrier] -> issue the bulk copy of the NEXT tile into the staging buffer, scan the 2^bits
+//   counts, reserve the tile's run in every child with one global atomicAdd per digit -> [barrier] -> keys into the exchange
+//   buffer grouped by digit -> [barrier] -> write-out, one contiguous run per digit.
+template <typename K>
+__global__ void __launch_bounds__(kPtThreads, 3) part_scatter_kernel(PartArgs a) {
+    constexpr int ITEMS = kPtTileBytes / (int)sizeof(K) / kPtThreads;
+    constexpr u32 TILE = kPtThreads * ITEMS;
+    extern __shared__ __align__(128) unsigned char part_smem[];
+    K* stage = reinterpret_cast<K*>(part_smem);                               // TILE keys + 16 bytes (a 64-bit tile may start at an odd index)
+    K* out_s = reinterpret_cast<K*>(part_smem + kPtTileBytes + 128);          // TILE keys
+    __shared__ u32 cnt_s[256], start_s[256];
+    __shared__ u64 gofs_s[256];
+    __shared__ u32 scan_s[kPtThreads / 32 + 1];
+    __shared__ __align__(8) u64 full_bar;
+
+    const int t = threadIdx.x;
+    const K* __restrict__ in = (const K*)a.in;
+    K* __restrict__ out = (K*)a.out;
+    const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles;
+    const u32 mul = perm_mul(n_tiles);
+    const u32 mask = (1u << a.bits) - 1;
+    cnt_s[t] = 0;
+    if (t == 0) mbar_init(&full_bar, 1);
+    __syncthreads();
+
+    auto issue = [&](const TileRef& tr) {                                   // thread 0 only
+        const u32 skip = sizeof(K) == 8 ? (u32)(tr.begin & 1) : 0u;
+        const u32 bytes = (((skip + tr.count) * (u32)sizeof(K)) + 15u) & ~15u;
+        mbar_expect_tx(&full_bar, bytes);
+        bulk_load(stage, in + (tr.begin - skip), bytes, &full_bar);
+    };
+
+    u32 it = blockIdx.x;
+    TileRef cur{0, 0, 0};
+    if (it < n_tiles) {
+        cur = tile_ref(a.descs, perm_tile(it, mul, n_tiles), a.n, TILE);
+        if (t == 0) issue(cur);
+    }
+    u32 parity = 0;
+    for (; it < n_tiles; it += gridDim.x) {
+        const u32 nit = it + gridDim.x;
+        TileRef nxt{0, 0, 0};
+        if (nit < n_tiles) nxt = tile_ref(a.descs, perm_tile(nit, mul, n_tiles), a.n, TILE);
+        mbar_wait(&full_bar, parity);
+        parity ^= 1;
+        const u32 skip = sizeof(K) == 8 ? (u32)(cur.begin & 1) : 0u;
+        K key[ITEMS];
+        u32 rank[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const u32 j = (u32)t + (u32)i * kPtThreads;
+            if (j < cur.count) key[i] = stage[skip + j];
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const u32 j = (u32)t + (u32)i * kPtThreads;
+            rank[i] = 0;
+            if (j < cur.count) rank[i] = atomicAdd(&cnt_s[part_digit<K>(key[i], a.shift, mask)], 1u);
+        }
+        __syncthreads();                                                  // every key is in registers, every count is final
+        if (t == 0 && nit < n_tiles) issue(nxt);
+        const u32 c = cnt_s[t];
+        const u32 ex = block_exclusive_scan<u32, kPtThreads>(c, (u32*)nullptr, scan_s);
+        u64 g = 0;
+        if (c) g = atomicAdd(&a.cursor[(((u64)cur.parent << a.bits) | (u32)t) * a.cstride], (u64)c);   // consumed after the scatter below
+        start_s[t] = ex;
+        cnt_s[t] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const u32 j = (u32)t + (u32)i * kPtThreads;
+            if (j < cur.count) out_s[start_s[part_digit<K>(key[i], a.shift, mask)] + rank[i]] = key[i];
+        }
+        gofs_s[t] = g - (u64)ex;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const u32 j = (u32)t + (u32)i * kPtThreads;
+            if (j < cur.count) {
+                const K k = out_s[j];
+                out[gofs_s[part_digit<K>(k, a.shift, mask)] + j] = k;
+            }
+        }
+        cur = nxt;
+    }
+}
+
+// ---- tiles of the next level: every parent bucket is cut into tiles of its own ------------------------------------------
+__global__ void tiles_per_parent_kernel(const u64* __restrict__ cstart, u32 n_parents, u32 tile_keys, u32* __restrict__ tp) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_parents) tp[p] = (u32)((cstart[p + 1] - cstart[p] + tile_keys - 1) / tile_keys);
+}
+
+__global__ void fill_descs_kernel(const u64* __restrict__ cstart, const u32* __restrict__ tile_first, u32 n_parents,
+                                  const u32* __restrict__ n_tiles_dev, u32 tile_keys, uint4* __restrict__ descs) {
+    const u32 tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= *n_tiles_dev) return;
+    u32 lo = 0, hi = n_parents;                                     // last parent whose first tile is <= tile (empty parents share the value)
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (tile_first[mid] <= tile) lo = mid + 1; else hi = mid; }
+    const u32 p = lo - 1;
+    const u64 begin = cstart[p] + (u64)(tile - tile_first[p]) * tile_keys;
+    const u64 rem = cstart[p + 1] - begin;
+    descs[tile] = make_uint4((u32)begin, (u32)(begin >> 32), rem < (u64)tile_keys ? (u32)rem : tile_keys, p);
+}
+
+__global__ void init_cursor_kernel(const u64* __restrict__ cstart, u64* __restrict__ cursor, u64 n_children, u32 cstride) {
+    const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_children) cursor[c * cstride] = cstart[c];
+}
+
+// ---- exact count of every bucket in shared memory -------------------------------------------------------------------------
+// Open addressing, linear probing, no deletions.  The home slot comes from the bits of the mixed key just below the
+// partition bits.  A slot is claimed with a 64-bit compare-and-swap on the (low) key word; the plain read in front of it
+// makes the common case -- the key is there already -- one shared-memory load and one atomicAdd on the count.
+// ctr[0] survivors appended, ctr[1] overflow descriptors {first index, length} appended (buckets that do not fit, keys
+// that equal the empty marker), ctr[2] distinct keys counted here, ctr[3] of those, self-complementary ones.
+static const u64 kEmptyWord = ~0ull;
+
+static const int kBkThreads = 512;
+
+template <typename K> struct CountTable;
+template <> struct CountTable<u64> {
+    static const int kSlotBytes = 12;
+    static const int kPrefetch = 6;                                   // keys per thread held in registers for the NEXT bucket
+    volatile u64* key; u32* cnt;
+    __device__ __forceinline__ void bind(unsigned char* smem, u32 max_slots) { key = (volatile u64*)smem; cnt = (u32*)(smem + (size_t)max_slots * 8); }
+    __device__ __forceinline__ void clear(u32 slots, int t) {
+        ulonglong2* k2 = (ulonglong2*)key;
+        for (u32 s = t; s < slots / 2; s += kBkThreads) k2[s] = make_ulonglong2(kEmptyWord, kEmptyWord);
+        uint4* c4 = (uint4*)cnt;
+        for (u32 s = t; s < slots / 4; s += kBkThreads) c4[s] = make_uint4(0, 0, 0, 0);
+    }
+    __device__ __forceinline__ static bool is_marker(u64 k) { return k == kEmptyWord; }
+    __device__ __forceinline__ void insert(u64 k, u32 h, u32 mask) {
+        u64 cur = key[h];
+        while (cur != k) {
+            if (cur == kEmptyWord) {
+                const u64 old = atomicCAS((u64*)&key[h], kEmptyWord, k);
+                if (old == kEmptyWord || old == k) break;
+            }
+            h = (h + 1) & mask;
+            cur = key[h];
+        }
+        atomicAdd(&cnt[h], 1u);
+    }
+    __device__ __forceinline__ u64 load(u32 s) const { return key[s]; }
+};
+template <> struct CountTable<Key128> {
+    static const int kSlotBytes = 20;
+    static const int kPrefetch = 4;
+    volatile u64* lo; volatile u64* hi; u32* cnt;
+    __device__ __forceinline__ void bind(unsigned char* smem, u32 max_slots) {
+        lo = (volatile u64*)smem; hi = (volatile u64*)(smem + (size_t)max_slots * 8); cnt = (u32*)(smem + (size_t)max_slots * 16);
+    }
+    __device__ __forceinline__ void clear(u32 slots, int t) {
+        ulonglong2* a = (ulonglong2*)lo; ulonglong2* b = (ulonglong2*)hi;
+        for (u32 s = t; s < slots / 2; s += kBkThreads) { a[s] = make_ulonglong2(kEmptyWord, kEmptyWord); b[s] = make_ulonglong2(kEmptyWord, kEmptyWord); }
+        uint4* c4 = (uint4*)cnt;
+        for (u32 s = t; s < slots / 4; s += kBkThreads) c4[s] = make_uint4(0, 0, 0, 0);
+    }
+    // the high word of a real key has at most 62 significant bits, so all-ones marks an unset high word; a key whose LOW
+    // word equals the marker cannot claim a slot and takes the overflow path
+    __device__ __forceinline__ static bool is_marker(const Key128& k) { return k.lo == kEmptyWord; }
+    __device__ __forceinline__ void insert(const Key128& k, u32 h, u32 mask) {
+        for (;;) {
+            u64 cur = lo[h];
+            if (cur == kEmptyWord) {
+                const u64 old = atomicCAS((u64*)&lo[h], kEmptyWord, k.lo);
+                cur = old == kEmptyWord ? k.lo : old;
+            }
+            if (cur == k.lo) {
+                u64 hc = hi[h];
+                if (hc == kEmptyWord) {
+                    const u64 old = atomicCAS((u64*)&hi[h], kEmptyWord, k.hi);
+                    hc = old == kEmptyWord ? k.hi : old;
+                }
+                if (hc == k.hi) { atomicAdd(&cnt[h], 1u); return; }
+            }
+            h = (h + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ Key128 load(u32 s) const { Key128 k; k.lo = lo[s]; k.hi = hi[s]; return k; }
+};
+
+// a bucket of up to this many keys always finds a table (slots = pow2 >= n + n/8 + 1 <= max_slots)
+__host__ __device__ __forceinline__ u32 bucket_cap(u32 max_slots) { return max_slots - max_slots / 8 - 2; }
+
+// FOLD: the keys are strand-folded and self-complementary keys exist (their counts are doubled before the filter)
+template <typename K, bool FOLD>
+__global__ void __launch_bounds__(kBkThreads, 2) bucket_count_kernel(const K* __restrict__ keys, const u64* __restrict__ cstart, u32 n_buckets,
+                                                                     int part_bits, u32 max_slots, u64 min_count, int fold_w,
+                                                                     K* __restrict__ out_keys, u64* __restrict__ out_counts, u64 out_cap,
+                                                                     ulonglong2* __restrict__ ovf_desc, u64 ovf_cap, u64* __restrict__ ctr) {
+    typedef KeyOps<K> KO;
+    constexpr int PRE = CountTable<K>::kPrefetch;
+    extern __shared__ __align__(16) unsigned char tab_smem[];
+    __shared__ u32 scan_s[kBkThreads / 32 + 1];
+    __shared__ u64 base_s;
+    __shared__ u32 stat_s[2];
+    CountTable<K> tab;
+    tab.bind(tab_smem, max_slots);
+    const int t = threadIdx.x;
+    const u32 cap = bucket_cap(max_slots);
+    if (t < 2) stat_s[t] = 0;
+    __syncthreads();
+    u32 my_distinct = 0, my_self = 0;
+
+    // software pipeline: the first PRE * threads keys of the NEXT bucket are fetched into registers while the table of the
+    // current one is scanned
+    K pre[PRE];
+    u32 b = blockIdx.x;
+    u64 start = 0, n_b64 = 0;
+    auto fetch = [&](u32 bucket, u64& st, u64& nb) {
+        st = 0; nb = 0;
+        if (bucket < n_buckets) {
+            st = cstart[bucket];
+            nb = cstart[bucket + 1] - st;
+            if (nb <= (u64)cap) {
+#pragma unroll
+                for (int j = 0; j < PRE; ++j) {
+                    const u32 idx = (u32)j * kBkThreads + (u32)t;
+                    if (idx < (u32)nb) pre[j] = keys[st + idx];
+                }
+            }
+        }
+    };
+    fetch(b, start, n_b64);
+    for (; b < n_buckets; b += gridDim.x) {
+        const u32 nb_next = b + gridDim.x;
+        const u64 cur_start = start, cur_n64 = n_b64;
+        if (cur_n64 == 0 || cur_n64 > (u64)cap) {
+            if (cur_n64 && t == 0) {                                   // does not fit: the whole bucket goes the slow way
+                const u64 o = atomicAdd(&ctr[1], 1ull);
+                if (o < ovf_cap) ovf_desc[o] = make_ulonglong2(cur_start, cur_n64);
+            }
+            fetch(nb_next, start, n_b64);
+            continue;
+        }
+        const u32 n_b = (u32)cur_n64;
+        u32 slots = 64;
+        while (slots < n_b + n_b / 8 + 1) slots <<= 1;
+        const u32 mask = slots - 1;
+        const int hb = 31 - __clz(slots);
+        tab.clear(slots, t);
+        __syncthreads();
+        auto put = [&](const K& k, u32 idx) {
+            if (CountTable<K>::is_marker(k)) {
+                const u64 o = atomicAdd(&ctr[1], 1ull);
+                if (o < ovf_cap) ovf_desc[o] = make_ulonglong2(cur_start + idx, 1ull);
+                return;
+            }
+            tab.insert(k, (u32)((KO::lo(k) << part_bits) >> (64 - hb)), mask);
+        };
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) {
+            const u32 idx = (u32)j * kBkThreads + (u32)t;
+            if (idx < n_b) put(pre[j], idx);
+        }
+        for (u32 idx = (u32)PRE * kBkThreads + (u32)t; idx < n_b; idx += kBkThreads) put(keys[cur_start + idx], idx);   // a rare long bucket
+        fetch(nb_next, start, n_b64);                                 // in flight during the table passes below
+        __syncthreads();
+        // pass 1 over the table: final count of every key (self-complementary keys stand for both strands), survivors noted
+        u32 keptmask = 0, my_keep = 0;
+        {
+            u32 i = 0;
+            for (u32 s = t; s < slots; s += kBkThreads, ++i) {
+                const u32 c = tab.cnt[s];
+                u64 c2 = c;
+                if (FOLD) {
+                    if (c) {
+                        const K real = key_unmix(tab.load(s));
+                        if (KO::eq(key_rc(real, fold_w), real)) { c2 <<= 1; ++my_self; tab.cnt[s] = (u32)c2; }
+                    }
+                }
+                my_distinct += c != 0 ? 1u : 0u;
+                const bool keep = c != 0 && c2 >= min_count;
+                keptmask |= (keep ? 1u : 0u) << i;
+                my_keep += keep ? 1u : 0u;
+            }
+        }
+        u32 total = 0;
+        const u32 ex = block_exclusive_scan<u32, kBkThreads>(my_keep, &total, scan_s);
+        if (t == 0) base_s = total ? atomicAdd(&ctr[0], (u64)total) : 0ull;
+        __syncthreads();
+        // pass 2: the survivors, un-mixed
+        u64 o = base_s + ex;
+        while (keptmask) {
+            const u32 s = (u32)t + (u32)(__ffs(keptmask) - 1) * kBkThreads;
+            keptmask &= keptmask - 1;
+            if (o < out_cap) { out_keys[o] = key_unmix(tab.load(s)); out_counts[o] = tab.cnt[s]; }
+            ++o;
+        }
+        __syncthreads();                                              // the table is cleared again at the top of the loop
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        my_distinct += __shfl_xor_sync(0xffffffffu, my_distinct, o);
+        my_self += __shfl_xor_sync(0xffffffffu, my_self, o);
+    }
+    if ((t & 31) == 0) {
+        if (my_distinct) atomicAdd(&stat_s[0], my_distinct);
+        if (my_self) atomicAdd(&stat_s[1], my_self);
+    }
+    __syncthreads();
+    if (t == 0) {
+        if (stat_s[0]) atomicAdd(&ctr[2], (u64)stat_s[0]);
+        if (stat_s[1]) atomicAdd(&ctr[3], (u64)stat_s[1]);
+    }
+}
+
+// overflow descriptors {first index, length}: one warp copies one range, un-mixed
+template <typename K>
+__global__ void __launch_bounds__(256) copy_overflow_kernel(const K* __restrict__ keys, const ulonglong2* __restrict__ desc, u64 n_desc,
+                                                            K* __restrict__ out, u64 out_cap, u64* __restrict__ cursor) {
+    const int lane = threadIdx.x & 31;
+    for (u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_desc; w += ((u64)gridDim.x * blockDim.x) >> 5) {
+        const ulonglong2 d = desc[w];
+        u64 base = 0;
+        if (lane == 0) base = atomicAdd(cursor, d.y);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (u64 q = lane; q < d.y; q += 32)
+            if (base + q < out_cap) out[base + q] = key_unmix(keys[d.x + q]);
+    }
+}
+
+template <typename K>
+static void launch_hist(const PartArgs& a, int grid, cudaStream_t s) { part_hist_kernel<K><<<grid, kPtThreads, 0, s>>>(a); }
+
+template <typename K>
+static void launch_scatter(const PartArgs& a, int grid, int device, cudaStream_t s) {
+    const size_t smem = 2 * (size_t)kPtTileBytes + 256;
+    static bool configured[64] = {false};
+    if (device < 0 || device >= 64 || !configured[device]) {
+        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        if (device >= 0 && device < 64) configured[device] = true;
+    }
+    part_scatter_kernel<K><<<grid, kPtThreads, smem, s>>>(a);
+}
+
+template <typename K>
+static void launch_bucket_count(const K* keys, const u64* cstart, u32 n_buckets, int part_bits, u32 max_slots, u64 min_count, int fold_w,
+                                K* out_keys, u64* out_counts, u64 out_cap, ulonglong2* ovf, u64 ovf_cap, u64* ctr, int grid, int device, cudaStream_t s) {
+    const size_t smem = (size_t)max_slots * CountTable<K>::kSlotBytes;
+    static size_t configured[64][2] = {{0, 0}};
+    const int f = fold_w ? 1 : 0;
+    if (device < 0 || device >= 64 || configured[device][f] < smem) {
+        if (f) {
+            GSB_CUDA_TRY(cudaFuncSetAttribute(bucket_count_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GSB_CUDA_TRY(cudaFuncSetAttribute(bucket_count_kernel<K, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        } else {
+            GSB_CUDA_TRY(cudaFuncSetAttribute(bucket_count_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GSB_CUDA_TRY(cudaFuncSetAttribute(bucket_count_kernel<K, false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        }
+        if (device >= 0 && device < 64) configured[device][f] = smem;
+    }
+    if (f)
+        bucket_count_kernel<K, true><<<grid, kBkThreads, smem, s>>>(keys, cstart, n_buckets, part_bits, max_slots, min_count, fold_w, out_keys, out_counts, out_cap,
+                                                                    ovf, ovf_cap, ctr);
+    else
+        bucket_count_kernel<K, false><<<grid, kBkThreads, smem, s>>>(keys, cstart, n_buckets, part_bits, max_slots, min_count, fold_w, out_keys, out_counts, out_cap,
+                                                                     ovf, ovf_cap, ctr);
+}
+
+}  // namespace
+
+u32 partition_tile_keys(int key_bytes) { return (u32)(kPtTileBytes / key_bytes); }
+
+// test-only overrides of the bucket geometry (gsb_debug_set_partition): results must not depend on them
+static u32 g_force_max_slots = 0;
+static int g_force_total_bits = 0;
+void partition_set_debug(u32 max_slots, int total_bits) { g_force_max_slots = max_slots; g_force_total_bits = total_bits; }
+
+// Bits the partition passes consume for n keys, and how they are split over the passes.
+PartitionPlan partition_plan(int key_bytes, u64 n) {
+    PartitionPlan p;
+    p.max_slots = key_bytes == 8 ? 8192u : 4096u;
+    if (g_force_max_slots >= 64 && g_force_max_slots <= p.max_slots && (g_force_max_slots & (g_force_max_slots - 1)) == 0) p.max_slots = g_force_max_slots;
+    const u64 cap = bucket_cap(p.max_slots);
+    const u64 mean_target = cap / 2;                                  // mean bucket = half of what fits: >= 10 sigma of head room at 50x coverage
+    int bits = 0;
+    while (bits < 40 && (n >> bits) > mean_target) ++bits;
+    if (g_force_total_bits > 0) bits = std::min(g_force_total_bits, 40);
+    while (bits > 0 && (1ull << bits) > 64 * n + 256) --bits;          // never (many) more buckets than keys
+    p.total_bits = bits;
+    p.levels = (bits + 7) / 8;
+    for (int l = 0; l < p.levels; ++l) p.bits[l] = bits / p.levels + (l < bits % p.levels ? 1 : 0);
+    return p;
+}
+
+// Count the n bit-mixed keys in `a` (b: scratch of the same size; both are overwritten).  Produces every distinct key
+// (un-mixed) whose final count is >= min_count, in ARBITRARY order, with its count; fold_w > 0 doubles the count of
+// self-complementary keys before the filter (fold.cu).  hist_top: optional [256] histogram of the top byte of the low key
+// word (fused into the extraction kernel), used when the first pass happens to split by exactly those 8 bits.
+// Returns false (nothing produced) only when min_count > 1 and more keys survive than the output buffers hold -- the
+// caller then sorts by the full key instead.
+bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64 n, u64 min_count, int fold_w, const u64* hist_top,
+                       ReducedRun& out, u64* m_distinct, u64* n_self_rc, int* where_keys, PartitionTiming* timing) {
+    cudaStream_t s = ws.stream;
+    out.m = 0;
+    *m_distinct = 0; *n_self_rc = 0;
+    if (where_keys) *where_keys = 0;
+    if (n == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return true; }
+    if (min_count < 1) min_count = 1;
+    const PartitionPlan plan = partition_plan(key_bytes, n);
+    const u32 tile_keys = partition_tile_keys(key_bytes);
+    cudaEvent_t ev[24];
+    int n_ev = 0;
+    auto mark = [&]() { if (timing && n_ev < 24) { GSB_CUDA_TRY(cudaEventCreate(&ev[n_ev])); GSB_CUDA_TRY(cudaEventRecord(ev[n_ev], s)); ++n_ev; } };
+
+    // ---- partition passes ----
+    void* cur = a; void* other = b;
+    DevBuf<u64> cstart;                                                // child starts of the last pass run: [children + 1]
+    u64 n_parents = 1;
+    int consumed = 0;
+    mark();
+    for (int l = 0; l < plan.levels; ++l) {
+        const int bits = plan.bits[l];
+        const u64 n_children = n_parents << bits;
+        PartArgs pa;
+        pa.in = cur; pa.out = other; pa.n = n;
+        pa.shift = 64 - consumed - bits; pa.bits = bits;
+        DevBuf<uint4> descs;
+        DevBuf<u32> tile_first, n_tiles_dev, scan_tmp32;
+        u64 tiles_ub = (n + tile_keys - 1) / tile_keys + (l ? n_parents : 0);
+        if (tiles_ub > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
+        if (l == 0) {
+            pa.descs = nullptr; pa.n_tiles_dev = nullptr; pa.n_tiles = (u32)tiles_ub;
+        } else {
+            descs.reset(&ws, tiles_ub);
+            tile_first.reset(&ws, n_parents + 1);
+            n_tiles_dev.reset(&ws, 1);
+            scan_tmp32.reset(&ws, scan_tmp_elems(n_parents));
+            tiles_per_parent_kernel<<<(unsigned)((n_parents + 255) / 256), 256, 0, s>>>(cstart.p, (u32)n_parents, tile_keys, tile_first.p);
+            exclusive_scan<u32, u32>(tile_first.p, tile_first.p, n_parents, 0u, n_tiles_dev.p, scan_tmp32.p, s, &ws.launches);
+            fill_descs_kernel<<<(unsigned)((tiles_ub + 255) / 256), 256, 0, s>>>(cstart.p, tile_first.p, (u32)n_parents, n_tiles_dev.p, tile_keys, descs.p);
+            ws.launches += 2;
+            pa.descs = descs.p; pa.n_tiles_dev = n_tiles_dev.p; pa.n_tiles = (u32)tiles_ub;
+        }
+        const int grid_hist = (int)std::min<u64>(tiles_ub, (u64)ws.sm_count * 8);
+        const int grid_scatter = (int)std::min<u64>(tiles_ub, (u64)ws.sm_count * 3);
+        // histogram of this level's digit per parent -> child starts
+        DevBuf<u64> hist(&ws, n_children), cnext(&ws, n_children + 1), scan_tmp(&ws, scan_tmp_elems(n_children));
+        const u64* hsrc = hist.p;
+        if (l == 0 && bits == 8 && hist_top) {
+            hsrc = hist_top;
+        } else {
+            GSB_CUDA_TRY(cudaMemsetAsync(hist.p, 0, n_children * 8, s));
+            pa.hist = hist.p;
+            if (key_bytes == 8) launch_hist<u64>(pa, grid_hist, s); else launch_hist<Key128>(pa, grid_hist, s);
+            ++ws.launches;
+        }
+        exclusive_scan<u64, u64>(hsrc, cnext.p, n_children, 0ull, cnext.p + n_children, scan_tmp.p, s, &ws.launches);
+        // cursors: spread over distinct cache lines when there are few of them (every tile in flight hits all of them)
+        const u32 cstride = n_children <= 4096 ? 32u : 1u;
+        DevBuf<u64> cursor(&ws, n_children * cstride);
+        init_cursor_kernel<<<(unsigned)((n_children + 255) / 256), 256, 0, s>>>(cnext.p, cursor.p, n_children, cstride);
+        ++ws.launches;
+        pa.cursor = cursor.p; pa.cstride = cstride; pa.hist = nullptr;
+        mark();
+        if (key_bytes == 8) launch_scatter<u64>(pa, grid_scatter, ws.device, s); else launch_scatter<Key128>(pa, grid_scatter, ws.device, s);
+        mark();
+        ++ws.launches;
+        std::swap(cur, other);
+        cstart = std::move(cnext);
+        n_parents = n_children;
+        consumed += bits;
+    }
+    mark();
+    if (plan.levels == 0) {
+        cstart.reset(&ws, 2);
+        const u64 h[2] = {0, n};
+        GSB_CUDA_TRY(cudaMemcpyAsync(cstart.p, h, 16, cudaMemcpyHostToDevice, s));
+        ws.sync();                                                     // h is on the stack
+    }
+
+    // ---- count every bucket ----
+    const u64 n_buckets = n_parents;
+    const u64 out_cap = min_count > 1 ? n / 2 + 65536 : n;
+    const u64 ovf_cap = std::max<u64>(n_buckets, 1u << 16) + n / 1024;
+    DevBuf<u64> out_counts(&ws, out_cap), ctr(&ws, 8);
+    DevBuf<ulonglong2> ovf(&ws, ovf_cap);
+    GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 64, s));
+    const int grid = (int)std::min<u64>(n_buckets, (u64)ws.sm_count * 2 * 4);       // 2 resident CTAs per SM, 4 interleaved rounds
+    if (key_bytes == 8)
+        launch_bucket_count<u64>((const u64*)cur, cstart.p, (u32)n_buckets, consumed, plan.max_slots, min_count, fold_w, (u64*)other, out_counts.p, out_cap,
+                                 ovf.p, ovf_cap, ctr.p, grid, ws.device, s);
+    else
+        launch_bucket_count<Key128>((const Key128*)cur, cstart.p, (u32)n_buckets, consumed, plan.max_slots, min_count, fold_w, (Key128*)other, out_counts.p, out_cap,
+                                    ovf.p, ovf_cap, ctr.p, grid, ws.device, s);
+    ++ws.launches;
+    mark();
+    u64 h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    GSB_CUDA_TRY(cudaMemcpyAsync(h, ctr.p, 64, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    if (where_keys) *where_keys = cur == a ? 0 : 1;
+    if (timing) {
+        // events: [0] begin, then (before, after) per scatter launch, then end of the passes, then end of the bucket count
+        float ms = 0;
+        const int e_part = 1 + 2 * plan.levels, e_count = e_part + 1;
+        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, ev[0], ev[e_part])); timing->ms_partition += ms;
+        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, ev[e_part], ev[e_count])); timing->ms_count += ms;
+        for (int l = 0; l < plan.levels; ++l) { GSB_CUDA_TRY(cudaEventElapsedTime(&ms, ev[1 + 2 * l], ev[2 + 2 * l])); timing->ms_scatter += ms; }
+        timing->levels = plan.levels; timing->total_bits = plan.total_bits;
+        timing->scatter_launches += plan.levels;
+        for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
+    }
+    if (h[0] > out_cap) return false;
+    if (h[1] > ovf_cap) throw StatusError{GSB_EINVAL, "internal: overflow list of the bucket count exceeded"};
+
+    // ---- buckets that did not fit: copied out un-mixed, full sort + run-length reduce ----
+    ReducedRun slow; u64 d2 = 0, self2 = 0;
+    if (h[1]) {
+        DevBuf<u64> total(&ws, 1);
+        sort_desc_total(ovf.p, h[1], total.p, s, &ws.launches);
+        u64 n_slow = 0;
+        GSB_CUDA_TRY(cudaMemcpyAsync(&n_slow, total.p, 8, cudaMemcpyDeviceToHost, s));
+        ws.sync();
+        DevBuf<u8> imp(&ws, n_slow * key_bytes), alt(&ws, n_slow * key_bytes);
+        GSB_CUDA_TRY(cudaMemsetAsync(total.p, 0, 8, s));
+        {
+            const unsigned blocks = (unsigned)std::min<u64>((h[1] + 7) / 8, (u64)ws.sm_count * 16);
+            if (key_bytes == 8) copy_overflow_kernel<u64><<<blocks, 256, 0, s>>>((const u64*)cur, ovf.p, h[1], (u64*)imp.p, n_slow, total.p);
+            else copy_overflow_kernel<Key128><<<blocks, 256, 0, s>>>((const Key128*)cur, ovf.p, h[1], (Key128*)imp.p, n_slow, total.p);
+            ++ws.launches;
+        }
+        const int where = sort_keys(ws, key_bytes, key_bits, imp.p, alt.p, nullptr, nullptr, n_slow, nullptr, nullptr);
+        reduce_sorted(ws, key_bytes, where ? alt.p : imp.p, nullptr, n_slow, min_count, slow, &d2, fold_w, &self2);
+        if (timing) timing->n_overflow_keys += n_slow;
+    }
+    const u64 m = h[0] + slow.m;
+    out.keys.reset(&ws, m * key_bytes);
+    out.counts.reset(&ws, m);
+    if (h[0]) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.keys.p, other, h[0] * key_bytes, cudaMemcpyDeviceToDevice, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.counts.p, out_counts.p, h[0] * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    if (slow.m) {
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.keys.p + h[0] * key_bytes, slow.keys.p, slow.m * key_bytes, cudaMemcpyDeviceToDevice, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(out.counts.p + h[0], slow.counts.p, slow.m * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    out.m = m;
+    *m_distinct = h[2] + d2;
+    *n_self_rc = h[3] + self2;
+    ws.sync();
+    return true;
+}
+
+}  // namespace gsb

@@ -8,6 +8,7 @@
 // (src/GossCmdTrimGraph.cc:119).  A cuckoo hash is a random-access structure; on a GPU with
 // 8 TB/s of streaming bandwidth the same multiset is counted faster by sorting the instances
 // and measuring run lengths, and the sorted order is what the succinct writers need anyway.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
@@ -252,12 +253,14 @@ static void launch_onesweep(const void* in, void* out, const u64* vin, u64* vout
                             void* lookback, u32* ticket, cudaStream_t s) {
     constexpr int TILE = THREADS * ITEMS;
     const size_t smem = (size_t)TILE * sizeof(K) + (size_t)(THREADS / 32) * 256 * 4 + 256 * 8 + (HAS_VALUES ? (size_t)TILE * 8 : 0);
-    static bool configured = false;
+    static bool configured[64] = {false};                   // function attributes are per device
     auto kern = onesweep_kernel<K, LB, THREADS, ITEMS, HAS_VALUES, MINB, MODE, LBW>;
-    if (!configured) {
+    int dev = 0;
+    GSB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         GSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const u64 tiles = (n + TILE - 1) / TILE;
     kern<<<(unsigned)tiles, THREADS, smem, s>>>((const K*)in, (K*)out, vin, vout, n, shift, digit_base, (LB*)lookback, ticket, g_sort_ablate_fwd);
@@ -776,6 +779,22 @@ __global__ void __launch_bounds__(256) copy_groups_kernel(const K* __restrict__ 
     const u64 pos = base + inc - len;
     for (u64 q = 0; q < len; ++q)
         if (pos + q < out_cap) out[pos + q] = key_unmix(keys[idx + q]);
+}
+
+__global__ void desc_total_kernel(const ulonglong2* __restrict__ desc, u64 n_desc, u64* __restrict__ total) {
+    u64 mine = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_desc; i += (u64)gridDim.x * blockDim.x) mine += desc[i].y;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
+}
+
+void sort_desc_total(const ulonglong2* desc, u64 n_desc, u64* total_dev, cudaStream_t s, u64* launches) {
+    GSB_CUDA_TRY(cudaMemsetAsync(total_dev, 0, 8, s));
+    if (!n_desc) return;
+    const unsigned blocks = (unsigned)std::min<u64>((n_desc + 255) / 256, 1024);
+    desc_total_kernel<<<blocks, 256, 0, s>>>(desc, n_desc, total_dev);
+    ++*launches;
 }
 
 u64 rle_tiles(u64 n) { return (n + kRleThreads * kRleItems - 1) / (kRleThreads * kRleItems); }

@@ -110,8 +110,10 @@ typedef struct gsb_stats {
     uint64_t n_batches;         /* sort+reduce rounds */
     uint64_t kernel_launches;   /* launches of this library's kernels so far */
     uint64_t hbm_peak_bytes;    /* high-water mark of device allocations */
-    uint64_t n_sorted_keys;     /* keys that went through the instance sort (graph mode: one per window,
+    uint64_t n_sorted_keys;     /* keys that went through the counting passes (graph mode: one per window,
                                    = n_instances / 2, because the two strands are folded) */
+    uint64_t device_allocs;     /* cudaMalloc calls made by this context so far (NOT reset by gsb_reset): a steady-state
+                                   step makes none -- every buffer comes from the context's caching allocator */
 } gsb_stats;
 
 /* Replaces: GossCmdFactoryBuildGraph::create parameter checks (src/GossCmdBuildGraph.cc:428-477)
@@ -183,7 +185,9 @@ int64_t gsb_debug_copy_counts(gsb_ctx* ctx, uint64_t* key_lo, uint64_t* key_hi, 
  * component's kernels run, results returned through the sink or out arrays). */
 int64_t gsb_debug_sort_keys(int device, uint64_t* key_lo, uint64_t* key_hi, uint64_t n, int key_bits);
 int gsb_debug_sort_bench(int device, uint64_t n, int key_bits, int iters, int tuning, double* sweep_ms, double* sort_ms, int* sweeps);
-int gsb_debug_set_tuning(int id);
+int gsb_debug_set_tuning(int id);   /* bits 0-7 sweep tile shape, 8-15 profiling ablations, bit 16: contexts created afterwards count with the
+                                       full LSD sort of raw keys (the round-1 path) instead of by partitioning */
+int gsb_debug_set_partition(int max_slots, int total_bits); /* bucket geometry of the partition counting, 0 = default; results never depend on it */
 int gsb_debug_emit_sparse_array(int device, const uint64_t* key_lo, const uint64_t* key_hi, uint64_t m,
                                 uint64_t universe_lo, uint64_t universe_hi, uint64_t m_est,
                                 const char* base, const gsb_sink* sink);

@@ -257,22 +257,50 @@ def test_self_complementary_edges_and_min_count(k, min_count):
     assert (counts2.n_instances, counts2.n_distinct, counts2.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
 
 
-@pytest.mark.parametrize("k,min_count", [(31, 2), (25, 3), (55, 2)])
-@pytest.mark.parametrize("digits", ["1", "2", "3", "4", "6"])
-def test_partial_sort_counting_any_group_width(k, min_count, digits, monkeypatch):
-    # counting from a partial sort (csrc/sort.cu): forcing few group digits makes most groups hold several keys (the
-    # "impure" path: those groups are fully sorted) or overflows its buffers (the sort is then finished instead);
-    # whatever happens the files must not change
+@pytest.mark.parametrize("k,min_count", [(31, 2), (25, 1), (55, 2), (40, 1)])
+@pytest.mark.parametrize("max_slots,total_bits", [(0, 0), (256, 3), (1024, 0), (0, 20), (64, 12), (4096, 9)])
+def test_partition_counting_any_bucket_geometry(k, min_count, max_slots, total_bits):
+    # counting by partitioning (csrc/partition.cu): forcing few partition bits / small tables makes buckets overflow (they
+    # then take the full-sort path), forcing many bits gives three passes over tiny buckets; whatever happens the files
+    # must not change
     text = _random_reads(11 * k + min_count, 30_000, 12_000, 100, err=0.01)
     want, ost = O.build_graph([(text, O.FASTQ)], k, min_count=min_count, threads=4)
-    monkeypatch.setenv("GSB_GROUP_DIGITS", digits)
-    sink, counts, stats = G.build_graph([(text, G.FASTQ)], k, min_count=min_count)
+    try:
+        G.debug_set_partition(max_slots, total_bits)
+        sink, counts, stats = G.build_graph([(text, G.FASTQ)], k, min_count=min_count)
+    finally:
+        G.debug_set_partition(0, 0)
     assert not _diff(sink.as_bytes(), want.files())
     assert (counts.n_instances, counts.n_distinct, counts.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
-    monkeypatch.setenv("GSB_FULL_SORT", "1")
-    sink2, counts2, stats2 = G.build_graph([(text, G.FASTQ)], k, min_count=min_count)
+
+
+@pytest.mark.parametrize("k,min_count", [(31, 2), (25, 1), (55, 2)])
+def test_legacy_lsd_counting_still_matches(k, min_count):
+    # the round-1 counting path (full LSD sort of the raw keys + run-length reduce) stays as the overflow path of the
+    # partition counting and as a cross-check: same files
+    text = _random_reads(11 * k + min_count, 30_000, 12_000, 100, err=0.01)
+    want, ost = O.build_graph([(text, O.FASTQ)], k, min_count=min_count, threads=4)
+    try:
+        G.debug_set_tuning(G.LEGACY_COUNTING)
+        sink2, counts2, stats2 = G.build_graph([(text, G.FASTQ)], k, min_count=min_count)
+    finally:
+        G.debug_set_tuning(0)
     assert not _diff(sink2.as_bytes(), want.files())
+    assert (counts2.n_instances, counts2.n_distinct, counts2.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
     assert stats2.sort_passes == stats2.sort_passes_model
+
+
+def test_partition_counting_heavy_repeats():
+    # one k-mer repeated 200,000 times (poly-A reads) next to ordinary reads: its bucket cannot fit a shared-memory table
+    # and must come back through the overflow path with the exact count
+    reads = _random_reads(77, 20_000, 3_000, 100, err=0.01)
+    poly = b"".join(b"@p%d\n%s\n+\n%s\n" % (i, b"A" * 100, b"I" * 100) for i in range(3000))
+    text = reads + poly
+    for k, m in ((25, 1), (31, 2)):
+        want, ost = O.build_graph([(text, O.FASTQ)], k, min_count=m, threads=4)
+        sink, counts, _ = G.build_graph([(text, G.FASTQ)], k, min_count=m)
+        assert not _diff(sink.as_bytes(), want.files())
+        assert (counts.n_instances, counts.n_distinct, counts.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
 
 
 @pytest.mark.parametrize("k", [25, 32, 40, 63])
