@@ -14,15 +14,17 @@ namespace gsb {
 // ------------------------------------------------------------------------------------------
 // Workspace
 // ------------------------------------------------------------------------------------------
-// Size classes: 512 B steps below 1 MiB; above, multiples of max(2 MiB, 1/8 of the largest power
-// of two below the request) -- at most 12.5 % slack.  A request takes the smallest cached block that is at
-// least its class and at most twice as large.  On one GPU every step repeats the same sequence of sizes and
-// hits its own blocks exactly; with several GPUs the sizes move by a few per cent from step to step (the
-// splitters come from a sample of keys whose order depends on atomics), and insisting on the exact class sent
-// some request of almost every step to cudaMalloc -- tens of milliseconds each with eight peer-mapped devices.
+// Size classes: powers of two below 64 KiB, multiples of 64 KiB below 1 MiB; above, multiples of max(2 MiB, 1/8 of the
+// largest power of two below the request) -- at most 12.5 % slack.  A request takes the smallest cached block that is at
+// least its class and at most twice (small blocks: four times) as large.  On one GPU every step repeats the same sequence
+// of sizes and hits its own blocks exactly; with several GPUs the sizes move by a few per cent from step to step (how many
+// keys a rank receives, how many survive), so a MISS allocates one class more than was asked for: the block then also
+// serves the slightly larger requests of later steps, and a steady-state step makes no driver allocation at all
+// (cudaMalloc costs tens of milliseconds with eight peer-mapped devices; gsb_stats.device_allocs counts them).
 static size_t round_block(size_t bytes) {
     if (bytes < 512) return 512;
-    if (bytes < (1u << 20)) return (bytes + 511) & ~(size_t)511;
+    if (bytes < (64u << 10)) { size_t p = 512; while (p < bytes) p <<= 1; return p; }
+    if (bytes < (1u << 20)) return (bytes + 65535) & ~(size_t)65535;
     size_t p2 = (size_t)1 << (63 - __builtin_clzll((unsigned long long)bytes));
     size_t g = std::max<size_t>((size_t)2 << 20, p2 / 8);
     return (bytes + g - 1) / g * g;
@@ -32,24 +34,25 @@ void* Workspace::alloc(size_t bytes) {
     const size_t want = round_block(bytes);
     void* p = nullptr;
     auto it = free_.lower_bound(want);
-    if (it != free_.end() && (it->first == want || (want >= (1u << 20) && it->first <= 2 * want))) {
+    if (it != free_.end() && it->first <= (want >= (1u << 20) ? 2 * want : 4 * want)) {
         p = it->second;
         free_.erase(it);
     } else {
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {                                            // out of memory: drop the cache and retry once
+        const size_t get = want >= (1u << 20) ? round_block(want + want / 8) : want;   // head room for the next, slightly larger request
+        cudaError_t e = cudaMalloc(&p, get);
+        if (e != cudaSuccess) {                                            // out of memory: drop the cache and retry once, without head room
             cudaGetLastError();
             GSB_CUDA_TRY(cudaStreamSynchronize(stream));
             trim();
             e = cudaMalloc(&p, want);
+            if (e == cudaSuccess) { size_of_[p] = want; reserved_bytes += want; ++device_allocs; }
+        } else {
+            size_of_[p] = get; reserved_bytes += get; ++device_allocs;
         }
         if (e != cudaSuccess) {
             cudaGetLastError();
             throw StatusError{GSB_ENOMEM, std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e)};
         }
-        size_of_[p] = want;
-        reserved_bytes += want;
-        ++device_allocs;
     }
     live_bytes += size_of_[p];
     peak_bytes = std::max(peak_bytes, live_bytes);
@@ -75,18 +78,40 @@ Workspace::~Workspace() {
 
 void Workspace::sync() { GSB_CUDA_TRY(cudaStreamSynchronize(stream)); }
 
+// Device time per phase: CUDA events on the library's stream around each phase, resolved LAZILY (gsb_get_stats /
+// gsb_reset) -- recording an interval never makes the host wait for the device.
 struct PhaseTimer {
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    struct Interval { cudaEvent_t e0, e1; double* acc; };
+    std::vector<Interval> open_, free_;
     cudaStream_t s = nullptr;
-    void init(cudaStream_t st) { s = st; GSB_CUDA_TRY(cudaEventCreate(&e0)); GSB_CUDA_TRY(cudaEventCreate(&e1)); }
-    void destroy() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); e0 = e1 = nullptr; }
-    void start() { GSB_CUDA_TRY(cudaEventRecord(e0, s)); }
+    Interval cur_{nullptr, nullptr, nullptr};
+    void init(cudaStream_t st) { s = st; }
+    void destroy() {
+        for (auto& v : {&open_, &free_}) { for (auto& i : *v) { cudaEventDestroy(i.e0); cudaEventDestroy(i.e1); } v->clear(); }
+    }
+    void start() {
+        if (free_.empty()) {
+            Interval i{nullptr, nullptr, nullptr};
+            GSB_CUDA_TRY(cudaEventCreate(&i.e0)); GSB_CUDA_TRY(cudaEventCreate(&i.e1));
+            free_.push_back(i);
+        }
+        cur_ = free_.back(); free_.pop_back();
+        GSB_CUDA_TRY(cudaEventRecord(cur_.e0, s));
+    }
     void stop(double& acc_ms) {
-        GSB_CUDA_TRY(cudaEventRecord(e1, s));
-        GSB_CUDA_TRY(cudaEventSynchronize(e1));
-        float ms = 0;
-        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-        acc_ms += ms;
+        GSB_CUDA_TRY(cudaEventRecord(cur_.e1, s));
+        cur_.acc = &acc_ms;
+        open_.push_back(cur_);
+    }
+    // adds every finished interval to its accumulator (waits for the last recorded event)
+    void resolve() {
+        for (auto& i : open_) {
+            float ms = 0;
+            if (cudaEventSynchronize(i.e1) == cudaSuccess && cudaEventElapsedTime(&ms, i.e0, i.e1) == cudaSuccess) *i.acc += ms;
+            else cudaGetLastError();
+            free_.push_back(i);
+        }
+        open_.clear();
     }
 };
 
@@ -207,7 +232,7 @@ void reset_batch(gsb_ctx* c) {
     cudaStream_t s = c->ws.stream;
     GSB_CUDA_TRY(cudaMemsetAsync(c->cursor.p, 0, 8, s));
     GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), s));
-    c->hist_valid = c->comm == nullptr;                        // with a communicator the extraction takes no histograms
+    c->hist_valid = c->mix || c->comm == nullptr;              // legacy counting with a communicator: the histograms are taken after the exchange
     c->n_keys = 0;
 }
 
@@ -249,13 +274,14 @@ void sort_run(gsb_ctx* c, ReducedRun& run) {
 }
 
 // count the buffered instance keys; fold the result into the accumulated run
-void flush_batch(gsb_ctx* c, bool final_and_only) {
-    if (c->n_keys == 0) return;
+// pre / pre_plan: the batch has been through the multi-GPU exchange already (level 0 of the partition counting)
+void flush_batch(gsb_ctx* c, bool final_and_only, PartitionInput* pre = nullptr, const PartitionPlan* pre_plan = nullptr) {
+    if (c->n_keys == 0 && !pre) return;
     Workspace& ws = c->ws;
     const int kb = c->key_bytes;
-    ensure_alt(c, c->n_keys);
+    ensure_alt(c, pre ? std::max<u64>(pre->n_cap, c->n_keys) : c->n_keys);
     DevBuf<u8>& alt = c->alt;
-    u8* const src = c->batch_src ? c->batch_src : c->keys.p;
+    u8* const src = pre ? (u8*)pre->keys : (c->batch_src ? c->batch_src : c->keys.p);
     c->batch_src = nullptr;
     int passes_run = 0;
     ReducedRun run; u64 distinct = 0, n_self_rc = 0;
@@ -271,10 +297,21 @@ void flush_batch(gsb_ctx* c, bool final_and_only) {
     int where = 0;
     bool reduced = false;
     if (c->mix) {
-        // the fused top-byte histogram describes exactly this batch only if it came straight out of the extraction
-        const u64* hist_top = (c->comm || !c->hist_valid) ? nullptr : c->hist.p;
         PartitionTiming pt;
-        reduced = count_partitioned(ws, kb, c->key_bits, src, alt.p, c->n_keys, min_count, fold_w, hist_top, run, &distinct, &n_self_rc, &where, &pt);
+        PartitionInput in;
+        PartitionPlan plan;
+        if (pre) {
+            in = std::move(*pre);
+            in.scratch = alt.p;
+            plan = *pre_plan;
+        } else {
+            in.keys = src; in.scratch = alt.p; in.n = c->n_keys;
+            // the fused top-bit histogram describes exactly this batch only if it came straight out of the extraction
+            in.hist_top = (c->hist_valid && !c->exchanged_instances) ? c->hist.p : nullptr;
+            plan = partition_plan(kb, c->n_keys);
+        }
+        reduced = count_partitioned(ws, kb, c->key_bits, in, plan, min_count, fold_w, run, &distinct, &n_self_rc, &where, &pt);
+        if (pre && !reduced) c->n_keys = exchange_partition_received(c->comm);   // rare: the full sort below needs the exact number of keys that arrived
         c->stats.ms_sort += pt.ms_partition;
         c->stats.ms_reduce += pt.ms_count;
         c->stats.ms_sort_sweeps += pt.ms_scatter;
@@ -397,7 +434,7 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     // K3: windows -> keys (+ fused digit histograms)
     // (with a communicator attached the instances are exchanged before the sort and the digit histograms are taken from
     // what arrives, so the fused histograms -- the dominant cost of the kernel -- are switched off)
-    ingest_extract(c->cfg.kind, c->key_bytes, codes.p, valid.p, 64 + n_carry, n_sym_total, c->window, c->comm ? 0 : (c->mix ? -1 : c->passes), c->mix ? 1 : 0,
+    ingest_extract(c->cfg.kind, c->key_bytes, codes.p, valid.p, 64 + n_carry, n_sym_total, c->window, c->mix ? -1 : (c->comm ? 0 : c->passes), c->mix ? 1 : 0,
                    c->keys.p, c->cursor.p, c->keys_cap, c->hist.p, c->status.p, ws.sm_count, s, &ws.launches);
     u64 cur = 0;
     GSB_CUDA_TRY(cudaMemcpyAsync(&cur, c->cursor.p, 8, cudaMemcpyDeviceToHost, s));
@@ -500,7 +537,7 @@ void init_ctx(gsb_ctx* c) {
     c->key_bytes = c->key_bits <= 64 ? 8 : 16;
     c->passes = (c->key_bits + 7) / 8;
     c->cursor.reset(&c->ws, 1);
-    c->hist.reset(&c->ws, (size_t)c->passes * 256);
+    c->hist.reset(&c->ws, std::max<size_t>((size_t)c->passes * 256, (size_t)1 << kTopHistBits));
     c->status.reset(&c->ws, 1);
     c->carry.reset(&c->ws, 64);
     size_t free_b = 0, total_b = 0;
@@ -639,43 +676,80 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
             // Every rank must take the same sequence of collectives: whether ANY rank has flushed a batch already (then all
             // ranks merge runs instead of exchanging raw instances) and whether any rank saw a self-complementary window are
             // agreed on first.
-            u64 spilled = c->have_acc ? 1 : 0, self_rc_all = c->self_rc_windows;
+            u64 spilled = c->have_acc ? 1 : 0, self_rc_all = c->self_rc_windows, n_total = c->n_keys;
             if (c->comm) {
-                const u64 mine[2] = {spilled, self_rc_all};
+                const u64 mine[3] = {spilled, self_rc_all, c->n_keys};
                 std::vector<u64> all;
-                exchange_allgather_u64(c->comm, c->ws, mine, 2, all);
-                spilled = 0; self_rc_all = 0;
-                for (int r = 0; r < exchange_size(c->comm); ++r) { spilled += all[2 * r]; self_rc_all += all[2 * r + 1]; }
+                exchange_allgather_u64(c->comm, c->ws, mine, 3, all);
+                spilled = 0; self_rc_all = 0; n_total = 0;
+                for (int r = 0; r < exchange_size(c->comm); ++r) { spilled += all[3 * r]; self_rc_all += all[3 * r + 1]; n_total += all[3 * r + 2]; }
             }
             const bool single = spilled == 0;
             c->any_self_rc = self_rc_all > 0;
-            bool exchanged_instances = false;
+            bool exchanged_instances = false, counted_batch = false;
             if (c->comm && single) {
                 // Multi-GPU, everything still buffered as raw instances: route each instance to the rank that owns its key
                 // range FIRST (one all-to-all of raw keys over NVLink), then count locally exactly as on one GPU.
                 const u64 local_instances = c->n_keys;
-                c->timer.start();
-                u64 n_recv = 0;
-                ExchangeTiming et;
-                ensure_alt(c, c->n_keys);
-                u8* recv_ptr = nullptr;
-                exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &recv_ptr, &n_recv, &et, nullptr);
-                c->stats.ms_all_to_all += et.ms_all_to_all;
-                c->stats.exchange_bytes_sent += et.bytes_sent_remote;
-                c->stats.exchange_peer_memory = et.used_peer_memory ? 1 : 0;
-                c->batch_src = recv_ptr;                           // the received instances are the batch to count
-                c->n_keys = n_recv;
-                if (!c->mix) {                                     // legacy LSD counting wants the digit histograms of what arrived
-                    GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), c->ws.stream));
-                    sort_digit_hist(c->key_bytes, recv_ptr, c->n_keys, c->passes, c->hist.p, c->ws.sm_count, c->ws.stream, &c->ws.launches);
-                    c->hist_valid = true;
-                }
-                c->timer.stop(c->stats.ms_exchange);
-                exchanged_instances = true;
                 c->instances_before_exchange = local_instances;
+                if (c->mix) {
+                    // the exchange IS the first pass of the partition counting: children of the top bits of the mixed key are
+                    // stored straight into their owners' windows; no sampling, no host round trip (exchange.cu)
+                    int min_bits = 0;
+                    while ((1 << min_bits) < exchange_size(c->comm)) ++min_bits;
+                    PartitionPlan plan = partition_plan(c->key_bytes, n_total);
+                    if (plan.levels == 0) { plan.levels = 1; plan.bits[0] = min_bits; plan.total_bits = min_bits; }
+                    else if (plan.bits[0] < min_bits) { plan.total_bits += min_bits - plan.bits[0]; plan.bits[0] = min_bits; }
+                    PartitionedInstances pi;
+                    c->timer.start();
+                    const bool fast = exchange_partition_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->hist.p, n_total, plan.bits[0], &pi);
+                    c->timer.stop(c->stats.ms_exchange);
+                    if (fast) {
+                        PartitionInput in;
+                        in.keys = pi.recv; in.cstart = std::move(pi.cstart); in.n_parents = pi.n_parents; in.n_cap = pi.n_cap; in.consumed_bits = pi.bits;
+                        c->exchanged_instances = true;
+                        flush_batch(c, true, &in, &plan);              // synchronises with the stream
+                        if (exchange_partition_aborted(c->comm)) {
+                            // some rank's window was too small for its share (a massively repeated k-mer): nothing was moved and
+                            // nothing counted, on every rank alike; take the sampled exchange below instead
+                            c->log(1, "partition exchange declined (a receive window would overflow): using the sampled exchange");
+                            c->acc.keys.free(); c->acc.counts.free(); c->acc.m = 0; c->have_acc = false; c->acc_unsorted = false;
+                            c->counts.n_instances = 0; c->counts.n_distinct = 0;
+                            c->stats.n_batches -= 1; c->stats.n_sorted_keys = 0; c->stats.sort_passes_model -= c->passes;
+                            c->n_keys = local_instances;
+                            c->exchanged_instances = false;
+                        } else {
+                            c->stats.ms_all_to_all += exchange_partition_scatter_ms(c->comm);
+                            c->stats.exchange_bytes_sent += exchange_partition_bytes_sent(c->comm);
+                            c->stats.exchange_peer_memory = 1;
+                            exchanged_instances = true;
+                            counted_batch = true;
+                        }
+                    }
+                }
+                if (!exchanged_instances) {
+                    c->timer.start();
+                    u64 n_recv = 0;
+                    ExchangeTiming et;
+                    ensure_alt(c, c->n_keys);
+                    u8* recv_ptr = nullptr;
+                    exchange_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->alt.p, c->third, &c->third_cap, &recv_ptr, &n_recv, &et, nullptr);
+                    c->stats.ms_all_to_all += et.ms_all_to_all;
+                    c->stats.exchange_bytes_sent += et.bytes_sent_remote;
+                    c->stats.exchange_peer_memory = et.used_peer_memory ? 1 : 0;
+                    c->batch_src = recv_ptr;                           // the received instances are the batch to count
+                    c->n_keys = n_recv;
+                    if (!c->mix) {                                     // legacy LSD counting wants the digit histograms of what arrived
+                        GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), c->ws.stream));
+                        sort_digit_hist(c->key_bytes, recv_ptr, c->n_keys, c->passes, c->hist.p, c->ws.sm_count, c->ws.stream, &c->ws.launches);
+                        c->hist_valid = true;
+                    }
+                    c->timer.stop(c->stats.ms_exchange);
+                    exchanged_instances = true;
+                }
             }
             c->exchanged_instances = exchanged_instances;
-            flush_batch(c, single);
+            if (!counted_batch) flush_batch(c, single);
             if (!c->have_acc) { c->acc.keys.reset(&c->ws, 0); c->acc.counts.reset(&c->ws, 0); c->acc.m = 0; c->have_acc = true; }
             if (c->comm && !exchanged_instances) {
                 c->timer.start();
@@ -857,8 +931,11 @@ int gsb_host_alloc(size_t nbytes, void** out) {
 
 void gsb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-int gsb_get_stats(const gsb_ctx* c, gsb_stats* out) {
-    if (!c || !out) return GSB_EINVAL;
+int gsb_get_stats(const gsb_ctx* cc, gsb_stats* out) {
+    if (!cc || !out) return GSB_EINVAL;
+    gsb_ctx* c = const_cast<gsb_ctx*>(cc);
+    cudaSetDevice(c->ws.device);
+    c->timer.resolve();
     *out = c->stats;
     out->kernel_launches = c->ws.launches;
     out->hbm_peak_bytes = c->ws.peak_bytes;
@@ -879,6 +956,7 @@ int gsb_reset(gsb_ctx* c) {
         c->n_carry = 0;
         memset(&c->counts, 0, sizeof(c->counts));
         const u64 launches = c->ws.launches;
+        c->timer.resolve();                                    // accumulators of the step that ends here
         memset(&c->stats, 0, sizeof(c->stats));
         c->stats.sort_key_bytes = c->key_bytes;
         c->ws.launches = launches;
@@ -898,7 +976,7 @@ int gsb_comm_attach(gsb_ctx* c, const void* id, int n_ranks, int rank) {
         if (n_ranks > kMaxRanks) throw StatusError{GSB_EINVAL, "at most " + std::to_string(kMaxRanks) + " ranks are supported"};
         if (c->n_keys || c->have_acc) throw StatusError{GSB_EINVAL, "gsb_comm_attach after input has been pushed (attach first, or gsb_reset)"};
         c->comm = exchange_create(id, n_ranks, rank, c->ws);
-        c->hist_valid = false;
+        c->hist_valid = c->mix;
     });
 }
 

@@ -385,7 +385,7 @@ static const int kExThreads = 256;
 static const int kExItems = 4;                                  // stream positions per thread per iteration
 
 // PASSES > 0 unrolls the histogram update (7 = k 25, 8 = k 31, 14 = k 55); 0 = run-time count; -1 = ONE histogram, of
-// the top byte of the low key word (what the first partition pass of partition.cu splits by).
+// the top kTopHistBits bits of the low key word (the first partition pass of partition.cu splits by those or fewer bits).
 template <typename K, int MODE, int PASSES>
 __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restrict__ codes, const u32* __restrict__ valid,
                                                              u64 p_begin, u64 p_end, int w, int passes_rt, int mix,
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
                                                              u64* __restrict__ digit_hist /* [passes][256] */, IngestStatus* st) {
     typedef KeyOps<K> KO;
     typedef WindowOps<K> WO;
-    const int passes = PASSES > 0 ? PASSES : (PASSES < 0 ? 1 : passes_rt);
-    extern __shared__ u32 hist_s[];                            // [passes][256]
+    const int passes = PASSES > 0 ? PASSES : (PASSES < 0 ? (1 << kTopHistBits) / 256 : passes_rt);
+    extern __shared__ u32 hist_s[];                            // [passes][256] (PASSES < 0: [2^kTopHistBits])
     __shared__ u32 warp_cnt[kExThreads / 32];
     __shared__ u64 base_s;
     for (int i = threadIdx.x; i < passes * 256; i += kExThreads) hist_s[i] = 0;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
                 if (idx < capacity) out[idx] = x[it];
                 else st->error = GSB_PE_KEY_OVERFLOW;
                 if (PASSES < 0) {
-                    atomicAdd(&hist_s[(u32)(KO::lo(x[it]) >> 56)], 1u);
+                    atomicAdd(&hist_s[(u32)(KO::lo(x[it]) >> (64 - kTopHistBits))], 1u);
                 } else if (PASSES > 0) {
 #pragma unroll
                     for (int d = 0; d < (PASSES > 0 ? PASSES : 1); ++d) atomicAdd(&hist_s[d * 256 + KO::digit(x[it], 8 * d)], 1u);
@@ -553,7 +553,7 @@ static void launch_extract_p(int kind, const u64* codes, const u32* valid, u64 p
     const u64 span = (u64)kExThreads * kExItems;
     u64 tiles = (p_end - p_begin + span - 1) / span;
     int grid = (int)(tiles < (u64)sm_count * 8 ? tiles : (u64)sm_count * 8);
-    size_t smem = (size_t)(passes < 0 ? 1 : passes) * 256 * sizeof(u32);
+    size_t smem = (size_t)(passes < 0 ? (1 << kTopHistBits) / 256 : passes) * 256 * sizeof(u32);
     if (kind == GSB_KIND_GRAPH)
         extract_kernel<K, GSB_KIND_GRAPH, PASSES><<<grid, kExThreads, smem, s>>>(codes, valid, p_begin, p_end, w, passes, mix, out, cursor, capacity, digit_hist, st);
     else

@@ -141,19 +141,28 @@ bool reduce_groups(Workspace& ws, int key_bytes, int key_bits, const void* group
 void sort_desc_total(const ulonglong2* desc, u64 n_desc, u64* total_dev, cudaStream_t s, u64* launches);
 
 // ---- partition.cu ------------------------------------------------------------------------------
+static const int kMaxRanks = 32;
+static const int kTopHistBits = 10;        // the extraction kernel histograms the top 10 bits of the low (mixed) key word
 struct PartitionPlan { int total_bits = 0, levels = 0; int bits[8] = {0, 0, 0, 0, 0, 0, 0, 0}; u32 max_slots = 0; };
-PartitionPlan partition_plan(int key_bytes, u64 n);
+PartitionPlan partition_plan(int key_bytes, u64 n_all_ranks);
 u32 partition_tile_keys(int key_bytes);
 void partition_set_debug(u32 max_slots, int total_bits);          // test-only geometry overrides (0 = default)
 struct PartitionTiming { double ms_partition = 0, ms_count = 0, ms_scatter = 0; int levels = 0, total_bits = 0; u64 scatter_launches = 0, n_overflow_keys = 0; };
-// Counting by partitioning (partition.cu): n bit-MIXED keys in `a` (`b`: scratch of the same size, both overwritten; both
-// need 16 bytes of slack behind the n-th key) -> every distinct key (un-mixed) with final count >= min_count, in
-// ARBITRARY order.  fold_w as in reduce_sorted.  hist_top: optional [256] histogram of the top byte of the low key word.
-// key_bits: significant bits of the REAL key.  Returns false (nothing produced) when min_count > 1 and the survivors do
-// not fit the output buffers (hardly any duplication): the caller then sorts by the full key; *where_keys says whether the
-// (still mixed, permuted) keys are in a (0) or b (1).
-bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64 n, u64 min_count, int fold_w, const u64* hist_top,
+struct PartitionInput {
+    void* keys = nullptr; void* scratch = nullptr;
+    u64 n = 0;                       // one parent of n keys (host-known) ...
+    const u64* hist_top = nullptr;   // ... optionally with the [2^kTopHistBits] histogram of its top bits
+    DevBuf<u64> cstart;              // ... or parents made by earlier passes: [n_parents + 1] starts (device), taken over
+    u64 n_parents = 1, n_cap = 0;    //     n_cap: upper bound of the key count (allocation sizes)
+    int consumed_bits = 0;
+};
+// Counting by partitioning (partition.cu); see there for the contract.
+bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, PartitionInput& in, const PartitionPlan& plan, u64 min_count, int fold_w,
                        ReducedRun& out, u64* m_distinct, u64* n_self_rc, int* where_keys = nullptr, PartitionTiming* timing = nullptr);
+// first pass of a multi-GPU build: children stored straight into their owners' windows (exchange.cu)
+void partition_scatter_to_peers(Workspace& ws, int key_bytes, const void* in, u64 n, int bits, u64* cursor, u32 cstride,
+                                void* const* peer_base, int n_peers, const u32* abort_flag);
+void partition_fold_hist(Workspace& ws, const u64* hist_top, int bits, u64* out);
 
 // ---- fold.cu ---------------------------------------------------------------------------------
 // Strand folding (graph mode): instances are counted as min(x, rc x); these restore both strands.

@@ -21,6 +21,8 @@
 // run-length reduce of sort.cu, so the result never depends on the bucket geometry.
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
+#include <vector>
 
 #include "kernels.h"
 #include "scan.cuh"
@@ -31,6 +33,7 @@ namespace {
 
 static const int kPtThreads = 256;
 static const int kPtTileBytes = 32768;
+static const int kPtMaxBins = 1024;                                  // children per parent and pass: 2^10 at most
 
 // ---- mbarrier / bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk) ------------------------------------------
 __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -88,10 +91,15 @@ struct PartArgs {
     const u32* n_tiles_dev;    // nullptr = n_tiles
     u32 n_tiles;
     u64 n;
-    u64* cursor;               // [(parent << bits | digit) * cstride]: next free slot of the child (absolute index in out)
+    u64* cursor;               // [(parent << bits | digit) * cstride]: next free slot of the child (element index from its owner's base)
     u64* hist;                 // [parent << bits | digit]
     u32 cstride;
     int shift, bits;           // digit = (word >> shift) & (2^bits - 1), word = low 64 bits of the mixed key
+    // where the children live: child c of a single-parent pass belongs to peer (c * n_peers) >> bits (the multi-GPU
+    // exchange stores straight into the owners' windows over NVLink); one GPU: n_peers = 1, peer[0] = out
+    void* peer[kMaxRanks];
+    int n_peers;
+    const u32* abort;          // optional: non-zero = do nothing (the exchange found a window too small)
 };
 
 template <typename K> __device__ __forceinline__ u32 part_digit(const K& k, int shift, u32 mask) { return (u32)(KeyOps<K>::lo(k) >> shift) & mask; }
@@ -101,20 +109,22 @@ template <typename K>
 __global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
     constexpr int ITEMS = kPtTileBytes / (int)sizeof(K) / kPtThreads;
     constexpr u32 TILE = kPtThreads * ITEMS;
-    __shared__ u32 cnt_s[256];
+    __shared__ u32 cnt_s[kPtMaxBins];
     const int t = threadIdx.x;
     const K* __restrict__ in = (const K*)a.in;
     const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles;
     const u32 mul = perm_mul(n_tiles);
-    const u32 mask = (1u << a.bits) - 1;
-    cnt_s[t] = 0;
+    const u32 nbins = 1u << a.bits, mask = nbins - 1;
+    for (u32 i = t; i < nbins; i += kPtThreads) cnt_s[i] = 0;
     __syncthreads();
     u32 cur_parent = 0xffffffffu;
     auto flush = [&]() {
         __syncthreads();
-        const u32 c = cnt_s[t];
-        if (c) atomicAdd(&a.hist[((u64)cur_parent << a.bits) | (u32)t], (u64)c);
-        cnt_s[t] = 0;
+        for (u32 i = t; i < nbins; i += kPtThreads) {
+            const u32 c = cnt_s[i];
+            if (c) atomicAdd(&a.hist[((u64)cur_parent << a.bits) | i], (u64)c);
+            cnt_s[i] = 0;
+        }
         __syncthreads();
     };
     for (u32 it = blockIdx.x; it < n_tiles; it += gridDim.x) {
@@ -144,25 +154,29 @@ __global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
 //   the digit's counter returns -> [barrier] -> issue the bulk copy of the NEXT tile into the staging buffer, scan the 2^bits
 //   counts, reserve the tile's run in every child with one global atomicAdd per digit -> [barrier] -> keys into the exchange
 //   buffer grouped by digit -> [barrier] -> write-out, one contiguous run per digit.
-template <typename K>
-__global__ void __launch_bounds__(kPtThreads, 3) part_scatter_kernel(PartArgs a) {
+// BPT = bins per thread: 1 (up to 256 children per parent, 3 CTAs per SM) or 4 (up to 1024, 2 CTAs per SM)
+template <typename K, int BPT>
+__global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_kernel(PartArgs a) {
     constexpr int ITEMS = kPtTileBytes / (int)sizeof(K) / kPtThreads;
     constexpr u32 TILE = kPtThreads * ITEMS;
+    constexpr int MAXBINS = kPtThreads * BPT;
     extern __shared__ __align__(128) unsigned char part_smem[];
     K* stage = reinterpret_cast<K*>(part_smem);                               // TILE keys + 16 bytes (a 64-bit tile may start at an odd index)
     K* out_s = reinterpret_cast<K*>(part_smem + kPtTileBytes + 128);          // TILE keys
-    __shared__ u32 cnt_s[256], start_s[256];
-    __shared__ u64 gofs_s[256];
+    __shared__ __align__(16) u32 cnt_s[MAXBINS];
+    __shared__ u32 start_s[MAXBINS];
+    __shared__ u64 gaddr_s[MAXBINS];                                          // per digit: address of the tile's run minus its place in out_s
     __shared__ u32 scan_s[kPtThreads / 32 + 1];
     __shared__ __align__(8) u64 full_bar;
 
+    if (a.abort && *a.abort) return;
     const int t = threadIdx.x;
     const K* __restrict__ in = (const K*)a.in;
-    K* __restrict__ out = (K*)a.out;
     const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles;
     const u32 mul = perm_mul(n_tiles);
     const u32 mask = (1u << a.bits) - 1;
-    cnt_s[t] = 0;
+#pragma unroll
+    for (int j = 0; j < BPT; ++j) cnt_s[t * BPT + j] = 0;
     if (t == 0) mbar_init(&full_bar, 1);
     __syncthreads();
 
@@ -202,26 +216,52 @@ __global__ void __launch_bounds__(kPtThreads, 3) part_scatter_kernel(PartArgs a)
         }
         __syncthreads();                                                  // every key is in registers, every count is final
         if (t == 0 && nit < n_tiles) issue(nxt);
-        const u32 c = cnt_s[t];
-        const u32 ex = block_exclusive_scan<u32, kPtThreads>(c, (u32*)nullptr, scan_s);
-        u64 g = 0;
-        if (c) g = atomicAdd(&a.cursor[(((u64)cur.parent << a.bits) | (u32)t) * a.cstride], (u64)c);   // consumed after the scatter below
-        start_s[t] = ex;
-        cnt_s[t] = 0;
+        u32 c[BPT];
+        u32 sum = 0;
+        if (BPT == 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(&cnt_s[t * 4]);
+            c[0] = v.x; c[BPT > 1 ? 1 : 0] = v.y; c[BPT > 2 ? 2 : 0] = v.z; c[BPT > 3 ? 3 : 0] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < BPT; ++j) c[j] = cnt_s[t * BPT + j];
+        }
+#pragma unroll
+        for (int j = 0; j < BPT; ++j) sum += c[j];
+        const u32 ex = block_exclusive_scan<u32, kPtThreads>(sum, (u32*)nullptr, scan_s);
+        u64 g[BPT];
+#pragma unroll
+        for (int j = 0; j < BPT; ++j) {                                   // consumed after the scatter below
+            g[j] = 0;
+            if (c[j]) g[j] = atomicAdd(&a.cursor[(((u64)cur.parent << a.bits) | (u32)(t * BPT + j)) * a.cstride], (u64)c[j]);
+        }
+        {
+            u32 run = ex;
+#pragma unroll
+            for (int j = 0; j < BPT; ++j) { start_s[t * BPT + j] = run; run += c[j]; cnt_s[t * BPT + j] = 0; }
+        }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const u32 j = (u32)t + (u32)i * kPtThreads;
             if (j < cur.count) out_s[start_s[part_digit<K>(key[i], a.shift, mask)] + rank[i]] = key[i];
         }
-        gofs_s[t] = g - (u64)ex;
+        {
+            u32 run = ex;
+#pragma unroll
+            for (int j = 0; j < BPT; ++j) {
+                const u32 bin = (u32)(t * BPT + j);
+                const u32 owner = a.n_peers > 1 ? (u32)(((u64)(bin & mask) * (u32)a.n_peers) >> a.bits) : 0u;
+                gaddr_s[bin] = (u64)a.peer[owner] + (g[j] - (u64)run) * sizeof(K);
+                run += c[j];
+            }
+        }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const u32 j = (u32)t + (u32)i * kPtThreads;
             if (j < cur.count) {
                 const K k = out_s[j];
-                out[gofs_s[part_digit<K>(k, a.shift, mask)] + j] = k;
+                *reinterpret_cast<K*>(gaddr_s[part_digit<K>(k, a.shift, mask)] + (u64)j * sizeof(K)) = k;
             }
         }
         cur = nxt;
@@ -466,19 +506,37 @@ __global__ void __launch_bounds__(256) copy_overflow_kernel(const K* __restrict_
     }
 }
 
+// out[d] = sum of the 2^(from_bits - bits) bins of `in` that share the top `bits` bits d
+__global__ void fold_hist_kernel(const u64* __restrict__ in, int from_bits, int bits, u64* __restrict__ out) {
+    const u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= (1u << bits)) return;
+    const u32 w = 1u << (from_bits - bits);
+    u64 sum = 0;
+    for (u32 j = 0; j < w; ++j) sum += in[(d << (from_bits - bits)) + j];
+    out[d] = sum;
+}
+
 template <typename K>
 static void launch_hist(const PartArgs& a, int grid, cudaStream_t s) { part_hist_kernel<K><<<grid, kPtThreads, 0, s>>>(a); }
 
-template <typename K>
-static void launch_scatter(const PartArgs& a, int grid, int device, cudaStream_t s) {
+template <typename K, int BPT>
+static void launch_scatter_b(const PartArgs& a, int grid, int device, cudaStream_t s) {
     const size_t smem = 2 * (size_t)kPtTileBytes + 256;
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
-        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K, BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K, BPT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         if (device >= 0 && device < 64) configured[device] = true;
     }
-    part_scatter_kernel<K><<<grid, kPtThreads, smem, s>>>(a);
+    part_scatter_kernel<K, BPT><<<grid, kPtThreads, smem, s>>>(a);
+}
+
+static void launch_scatter(int key_bytes, const PartArgs& a, u64 tiles_ub, Workspace& ws) {
+    const bool wide = a.bits > 8;
+    const int grid = (int)std::min<u64>(tiles_ub, (u64)ws.sm_count * (wide ? 2 : 3));
+    if (key_bytes == 8) { if (wide) launch_scatter_b<u64, 4>(a, grid, ws.device, ws.stream); else launch_scatter_b<u64, 1>(a, grid, ws.device, ws.stream); }
+    else { if (wide) launch_scatter_b<Key128, 4>(a, grid, ws.device, ws.stream); else launch_scatter_b<Key128, 1>(a, grid, ws.device, ws.stream); }
+    ++ws.launches;
 }
 
 template <typename K>
@@ -514,7 +572,9 @@ static u32 g_force_max_slots = 0;
 static int g_force_total_bits = 0;
 void partition_set_debug(u32 max_slots, int total_bits) { g_force_max_slots = max_slots; g_force_total_bits = total_bits; }
 
-// Bits the partition passes consume for n keys, and how they are split over the passes.
+// Bits the partition passes consume for n keys (ALL keys that share the key space: the sum over the ranks of a multi-GPU
+// build), and how they are split over the passes: as few passes as 10 bits each allow, the earlier passes taking the
+// smaller share (the first pass of a multi-GPU build stores over NVLink, where longer runs per child matter most).
 PartitionPlan partition_plan(int key_bytes, u64 n) {
     PartitionPlan p;
     p.max_slots = key_bytes == 8 ? 8192u : 4096u;
@@ -526,101 +586,152 @@ PartitionPlan partition_plan(int key_bytes, u64 n) {
     if (g_force_total_bits > 0) bits = std::min(g_force_total_bits, 40);
     while (bits > 0 && (1ull << bits) > 64 * n + 256) --bits;          // never (many) more buckets than keys
     p.total_bits = bits;
-    p.levels = (bits + 7) / 8;
-    for (int l = 0; l < p.levels; ++l) p.bits[l] = bits / p.levels + (l < bits % p.levels ? 1 : 0);
+    p.levels = (bits + 9) / 10;
+    if (bits > 10 && bits <= 16) p.levels = 2;
+    for (int l = 0; l < p.levels; ++l) p.bits[l] = bits / p.levels + (l >= p.levels - bits % p.levels ? 1 : 0);
     return p;
 }
 
-// Count the n bit-mixed keys in `a` (b: scratch of the same size; both are overwritten).  Produces every distinct key
-// (un-mixed) whose final count is >= min_count, in ARBITRARY order, with its count; fold_w > 0 doubles the count of
-// self-complementary keys before the filter (fold.cu).  hist_top: optional [256] histogram of the top byte of the low key
-// word (fused into the extraction kernel), used when the first pass happens to split by exactly those 8 bits.
+namespace {
+
+struct LevelTiming { cudaEvent_t e0 = nullptr, e1 = nullptr; };
+
+// One pass over `cur` (parents given by cstart, or one parent [0, n) when cstart is empty) by `bits` more bits into `other`.
+// Produces the child starts.  hist_ready: optional histogram [n_parents << bits] that is already known.
+void run_level(Workspace& ws, int key_bytes, void* cur, void* other, u64 n, u64 n_cap, DevBuf<u64>& cstart, u64 n_parents, int consumed, int bits,
+               const u64* hist_ready, PartitionTiming* timing, std::vector<LevelTiming>& events) {
+    cudaStream_t s = ws.stream;
+    const u32 tile_keys = partition_tile_keys(key_bytes);
+    const u64 n_children = n_parents << bits;
+    const bool plain = cstart.p == nullptr;                          // one parent, its size known on the host
+    PartArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.in = cur; pa.out = other; pa.n = n;
+    pa.shift = 64 - consumed - bits; pa.bits = bits;
+    pa.peer[0] = other; pa.n_peers = 1; pa.abort = nullptr;
+    DevBuf<uint4> descs;
+    DevBuf<u32> tile_first, n_tiles_dev, scan_tmp32;
+    const u64 tiles_ub = plain ? (n + tile_keys - 1) / tile_keys : (n_cap + tile_keys - 1) / tile_keys + n_parents;
+    if (tiles_ub > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
+    pa.n_tiles = (u32)tiles_ub;
+    if (!plain) {
+        descs.reset(&ws, tiles_ub);
+        tile_first.reset(&ws, n_parents + 1);
+        n_tiles_dev.reset(&ws, 1);
+        scan_tmp32.reset(&ws, scan_tmp_elems(n_parents));
+        tiles_per_parent_kernel<<<(unsigned)((n_parents + 255) / 256), 256, 0, s>>>(cstart.p, (u32)n_parents, tile_keys, tile_first.p);
+        exclusive_scan<u32, u32>(tile_first.p, tile_first.p, n_parents, 0u, n_tiles_dev.p, scan_tmp32.p, s, &ws.launches);
+        fill_descs_kernel<<<(unsigned)((tiles_ub + 255) / 256), 256, 0, s>>>(cstart.p, tile_first.p, (u32)n_parents, n_tiles_dev.p, tile_keys, descs.p);
+        ws.launches += 2;
+        pa.descs = descs.p; pa.n_tiles_dev = n_tiles_dev.p;
+    }
+    // histogram of this level's digit per parent -> child starts
+    DevBuf<u64> hist(&ws, n_children), cnext(&ws, n_children + 1), scan_tmp(&ws, scan_tmp_elems(n_children));
+    const u64* hsrc = hist_ready;
+    if (!hsrc) {
+        GSB_CUDA_TRY(cudaMemsetAsync(hist.p, 0, n_children * 8, s));
+        pa.hist = hist.p;
+        const int grid_hist = (int)std::min<u64>(tiles_ub, (u64)ws.sm_count * 8);
+        if (key_bytes == 8) launch_hist<u64>(pa, grid_hist, s); else launch_hist<Key128>(pa, grid_hist, s);
+        ++ws.launches;
+        hsrc = hist.p;
+    }
+    exclusive_scan<u64, u64>(hsrc, cnext.p, n_children, 0ull, cnext.p + n_children, scan_tmp.p, s, &ws.launches);
+    // cursors: spread over distinct cache lines when there are few of them (every tile in flight hits all of them)
+    const u32 cstride = n_children <= 4096 ? 32u : 1u;
+    DevBuf<u64> cursor(&ws, n_children * cstride);
+    init_cursor_kernel<<<(unsigned)((n_children + 255) / 256), 256, 0, s>>>(cnext.p, cursor.p, n_children, cstride);
+    ++ws.launches;
+    pa.cursor = cursor.p; pa.cstride = cstride; pa.hist = nullptr;
+    LevelTiming lt;
+    if (timing) { GSB_CUDA_TRY(cudaEventCreate(&lt.e0)); GSB_CUDA_TRY(cudaEventCreate(&lt.e1)); GSB_CUDA_TRY(cudaEventRecord(lt.e0, s)); }
+    launch_scatter(key_bytes, pa, tiles_ub, ws);
+    if (timing) { GSB_CUDA_TRY(cudaEventRecord(lt.e1, s)); events.push_back(lt); }
+    cstart = std::move(cnext);
+}
+
+}  // namespace
+
+// level 0 of a multi-GPU build: this rank's n keys are split by their top `bits` bits and every child's run is stored
+// straight into its owner's window (peers.base[(child * n_ranks) >> bits], element offsets from cursor[child * cstride])
+void partition_scatter_to_peers(Workspace& ws, int key_bytes, const void* in, u64 n, int bits, u64* cursor, u32 cstride,
+                                void* const* peer_base, int n_peers, const u32* abort_flag) {
+    if (!n) return;
+    const u32 tile_keys = partition_tile_keys(key_bytes);
+    PartArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.in = in; pa.out = nullptr; pa.n = n;
+    pa.shift = 64 - bits; pa.bits = bits;
+    for (int r = 0; r < n_peers; ++r) pa.peer[r] = peer_base[r];
+    pa.n_peers = n_peers; pa.abort = abort_flag;
+    pa.cursor = cursor; pa.cstride = cstride;
+    const u64 tiles = (n + tile_keys - 1) / tile_keys;
+    if (tiles > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
+    pa.n_tiles = (u32)tiles;
+    launch_scatter(key_bytes, pa, tiles, ws);
+}
+
+void partition_fold_hist(Workspace& ws, const u64* hist_top, int bits, u64* out) {
+    fold_hist_kernel<<<((1u << bits) + 255) / 256, 256, 0, ws.stream>>>(hist_top, kTopHistBits, bits, out);
+    ++ws.launches;
+}
+
+// Count bit-mixed keys (see the file header).  in.keys holds them; in.scratch is a buffer of the same capacity; both are
+// overwritten and need 16 bytes of slack behind their last key.  Either one parent of in.n keys (host-known), or
+// in.cstart / in.n_parents / in.consumed_bits describe buckets that earlier passes (the multi-GPU exchange) have made, the
+// key count then being known only on the device (in.n_cap bounds it for allocations).
+// Produces every distinct key (un-mixed) whose final count is >= min_count, in ARBITRARY order, with its count; fold_w > 0
+// doubles the count of self-complementary keys before the filter (fold.cu).
 // Returns false (nothing produced) only when min_count > 1 and more keys survive than the output buffers hold -- the
-// caller then sorts by the full key instead.
-bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, void* a, void* b, u64 n, u64 min_count, int fold_w, const u64* hist_top,
+// caller then sorts by the full key instead; *where_keys: the (still mixed, permuted) keys are in keys (0) or scratch (1).
+bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, PartitionInput& in, const PartitionPlan& plan, u64 min_count, int fold_w,
                        ReducedRun& out, u64* m_distinct, u64* n_self_rc, int* where_keys, PartitionTiming* timing) {
     cudaStream_t s = ws.stream;
     out.m = 0;
     *m_distinct = 0; *n_self_rc = 0;
     if (where_keys) *where_keys = 0;
-    if (n == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return true; }
+    const bool plain = in.cstart.p == nullptr;
+    const u64 n_cap = plain ? in.n : in.n_cap;
+    if (n_cap == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return true; }
     if (min_count < 1) min_count = 1;
-    const PartitionPlan plan = partition_plan(key_bytes, n);
-    const u32 tile_keys = partition_tile_keys(key_bytes);
-    cudaEvent_t ev[24];
-    int n_ev = 0;
-    auto mark = [&]() { if (timing && n_ev < 24) { GSB_CUDA_TRY(cudaEventCreate(&ev[n_ev])); GSB_CUDA_TRY(cudaEventRecord(ev[n_ev], s)); ++n_ev; } };
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    auto mark = [&](int i) { if (timing) { GSB_CUDA_TRY(cudaEventCreate(&ev[i])); GSB_CUDA_TRY(cudaEventRecord(ev[i], s)); } };
+    std::vector<LevelTiming> levels_ev;
 
     // ---- partition passes ----
-    void* cur = a; void* other = b;
-    DevBuf<u64> cstart;                                                // child starts of the last pass run: [children + 1]
-    u64 n_parents = 1;
-    int consumed = 0;
-    mark();
-    for (int l = 0; l < plan.levels; ++l) {
-        const int bits = plan.bits[l];
-        const u64 n_children = n_parents << bits;
-        PartArgs pa;
-        pa.in = cur; pa.out = other; pa.n = n;
-        pa.shift = 64 - consumed - bits; pa.bits = bits;
-        DevBuf<uint4> descs;
-        DevBuf<u32> tile_first, n_tiles_dev, scan_tmp32;
-        u64 tiles_ub = (n + tile_keys - 1) / tile_keys + (l ? n_parents : 0);
-        if (tiles_ub > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
-        if (l == 0) {
-            pa.descs = nullptr; pa.n_tiles_dev = nullptr; pa.n_tiles = (u32)tiles_ub;
-        } else {
-            descs.reset(&ws, tiles_ub);
-            tile_first.reset(&ws, n_parents + 1);
-            n_tiles_dev.reset(&ws, 1);
-            scan_tmp32.reset(&ws, scan_tmp_elems(n_parents));
-            tiles_per_parent_kernel<<<(unsigned)((n_parents + 255) / 256), 256, 0, s>>>(cstart.p, (u32)n_parents, tile_keys, tile_first.p);
-            exclusive_scan<u32, u32>(tile_first.p, tile_first.p, n_parents, 0u, n_tiles_dev.p, scan_tmp32.p, s, &ws.launches);
-            fill_descs_kernel<<<(unsigned)((tiles_ub + 255) / 256), 256, 0, s>>>(cstart.p, tile_first.p, (u32)n_parents, n_tiles_dev.p, tile_keys, descs.p);
-            ws.launches += 2;
-            pa.descs = descs.p; pa.n_tiles_dev = n_tiles_dev.p; pa.n_tiles = (u32)tiles_ub;
+    void* cur = in.keys; void* other = in.scratch;
+    DevBuf<u64> cstart = std::move(in.cstart);                          // child starts of the last pass run: [children + 1]
+    u64 n_parents = plain ? 1 : in.n_parents;
+    int consumed = plain ? 0 : in.consumed_bits;
+    int level = 0, done_bits = 0;
+    while (level < plan.levels && done_bits < consumed) done_bits += plan.bits[level++];   // passes the caller has run already
+    mark(0);
+    DevBuf<u64> folded;
+    for (; level < plan.levels; ++level) {
+        const int bits = plan.bits[level];
+        const u64* hist_ready = nullptr;
+        if (plain && level == 0 && in.hist_top && bits <= kTopHistBits) {      // the extraction kernel counted the top bits already
+            folded.reset(&ws, (size_t)1 << bits);
+            partition_fold_hist(ws, in.hist_top, bits, folded.p);
+            hist_ready = folded.p;
         }
-        const int grid_hist = (int)std::min<u64>(tiles_ub, (u64)ws.sm_count * 8);
-        const int grid_scatter = (int)std::min<u64>(tiles_ub, (u64)ws.sm_count * 3);
-        // histogram of this level's digit per parent -> child starts
-        DevBuf<u64> hist(&ws, n_children), cnext(&ws, n_children + 1), scan_tmp(&ws, scan_tmp_elems(n_children));
-        const u64* hsrc = hist.p;
-        if (l == 0 && bits == 8 && hist_top) {
-            hsrc = hist_top;
-        } else {
-            GSB_CUDA_TRY(cudaMemsetAsync(hist.p, 0, n_children * 8, s));
-            pa.hist = hist.p;
-            if (key_bytes == 8) launch_hist<u64>(pa, grid_hist, s); else launch_hist<Key128>(pa, grid_hist, s);
-            ++ws.launches;
-        }
-        exclusive_scan<u64, u64>(hsrc, cnext.p, n_children, 0ull, cnext.p + n_children, scan_tmp.p, s, &ws.launches);
-        // cursors: spread over distinct cache lines when there are few of them (every tile in flight hits all of them)
-        const u32 cstride = n_children <= 4096 ? 32u : 1u;
-        DevBuf<u64> cursor(&ws, n_children * cstride);
-        init_cursor_kernel<<<(unsigned)((n_children + 255) / 256), 256, 0, s>>>(cnext.p, cursor.p, n_children, cstride);
-        ++ws.launches;
-        pa.cursor = cursor.p; pa.cstride = cstride; pa.hist = nullptr;
-        mark();
-        if (key_bytes == 8) launch_scatter<u64>(pa, grid_scatter, ws.device, s); else launch_scatter<Key128>(pa, grid_scatter, ws.device, s);
-        mark();
-        ++ws.launches;
+        run_level(ws, key_bytes, cur, other, in.n, n_cap, cstart, n_parents, consumed, bits, hist_ready, timing, levels_ev);
         std::swap(cur, other);
-        cstart = std::move(cnext);
-        n_parents = n_children;
+        n_parents <<= bits;
         consumed += bits;
     }
-    mark();
-    if (plan.levels == 0) {
+    mark(1);
+    if (cstart.p == nullptr) {                                          // no pass at all: one bucket
         cstart.reset(&ws, 2);
-        const u64 h[2] = {0, n};
+        const u64 h[2] = {0, in.n};
         GSB_CUDA_TRY(cudaMemcpyAsync(cstart.p, h, 16, cudaMemcpyHostToDevice, s));
         ws.sync();                                                     // h is on the stack
     }
 
     // ---- count every bucket ----
     const u64 n_buckets = n_parents;
-    const u64 out_cap = min_count > 1 ? n / 2 + 65536 : n;
-    const u64 ovf_cap = std::max<u64>(n_buckets, 1u << 16) + n / 1024;
+    const u64 out_cap = min_count > 1 ? n_cap / 2 + 65536 : n_cap;
+    const u64 ovf_cap = std::max<u64>(n_buckets, 1u << 16) + n_cap / 1024;
     DevBuf<u64> out_counts(&ws, out_cap), ctr(&ws, 8);
     DevBuf<ulonglong2> ovf(&ws, ovf_cap);
     GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 64, s));
@@ -632,21 +743,22 @@ bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, void* a, void
         launch_bucket_count<Key128>((const Key128*)cur, cstart.p, (u32)n_buckets, consumed, plan.max_slots, min_count, fold_w, (Key128*)other, out_counts.p, out_cap,
                                     ovf.p, ovf_cap, ctr.p, grid, ws.device, s);
     ++ws.launches;
-    mark();
+    mark(2);
     u64 h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     GSB_CUDA_TRY(cudaMemcpyAsync(h, ctr.p, 64, cudaMemcpyDeviceToHost, s));
     ws.sync();
-    if (where_keys) *where_keys = cur == a ? 0 : 1;
+    if (where_keys) *where_keys = cur == in.keys ? 0 : 1;
     if (timing) {
-        // events: [0] begin, then (before, after) per scatter launch, then end of the passes, then end of the bucket count
         float ms = 0;
-        const int e_part = 1 + 2 * plan.levels, e_count = e_part + 1;
-        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, ev[0], ev[e_part])); timing->ms_partition += ms;
-        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, ev[e_part], ev[e_count])); timing->ms_count += ms;
-        for (int l = 0; l < plan.levels; ++l) { GSB_CUDA_TRY(cudaEventElapsedTime(&ms, ev[1 + 2 * l], ev[2 + 2 * l])); timing->ms_scatter += ms; }
+        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, ev[0], ev[1])); timing->ms_partition += ms;
+        GSB_CUDA_TRY(cudaEventElapsedTime(&ms, ev[1], ev[2])); timing->ms_count += ms;
+        for (auto& lt : levels_ev) {
+            GSB_CUDA_TRY(cudaEventElapsedTime(&ms, lt.e0, lt.e1)); timing->ms_scatter += ms;
+            cudaEventDestroy(lt.e0); cudaEventDestroy(lt.e1);
+        }
         timing->levels = plan.levels; timing->total_bits = plan.total_bits;
-        timing->scatter_launches += plan.levels;
-        for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
+        timing->scatter_launches += levels_ev.size();
+        for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
     }
     if (h[0] > out_cap) return false;
     if (h[1] > ovf_cap) throw StatusError{GSB_EINVAL, "internal: overflow list of the bucket count exceeded"};

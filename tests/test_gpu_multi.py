@@ -17,9 +17,14 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _reads(rank, n=20_000):
+def _reads(rank, n=20_000, mode=""):
     g = S.genome(60_000, 42)
-    return bytes(S.reads_fastq(g, 100, n + 3000 * rank, err=0.01, seed=43 + rank))
+    text = bytes(S.reads_fastq(g, 100, n + 3000 * rank, err=0.01, seed=43 + rank))
+    if mode == "skew" and rank == 0:
+        # one k-mer repeated 1.5 M times on one rank: its owner's receive window cannot hold its share of a uniform split,
+        # the partition exchange must decline (on every rank alike) and the sampled exchange take over
+        text += b"".join(b"@p%d\n%s\n+\n%s\n" % (i, b"A" * 100, b"I" * 100) for i in range(22_000))
+    return text
 
 
 def _worker(rank, world, nccl_id, k, min_count, mode, out):
@@ -27,10 +32,11 @@ def _worker(rank, world, nccl_id, k, min_count, mode, out):
     sys.path.insert(0, os.path.dirname(HERE))
     import gossamer_b200 as G
     kind = G.KMERSET if mode == "kmerset" else G.GRAPH
-    b = G.Builder(kind, k, min_count=min_count, device=rank, max_batch_keys=400_000 if mode == "batches" else 0)
+    limited = mode == "batches" or (mode == "onespill" and rank == 0)       # onespill: only ONE rank ever flushes a batch early
+    b = G.Builder(kind, k, min_count=min_count, device=rank, max_batch_keys=400_000 if limited else 0)
     b.attach(nccl_id, world, rank)
-    text = _reads(rank)
-    if mode == "batches":                                  # several sort+reduce+merge rounds per rank before the exchange
+    text = _reads(rank, mode=mode)
+    if mode in ("batches", "onespill"):                                  # several sort+reduce+merge rounds per rank before the exchange
         recs = text.split(b"\n@r")
         chunks = [b"\n@r".join(recs[i:i + 4000]) for i in range(0, len(recs), 4000)]
         for i, ch in enumerate(chunks):
@@ -71,7 +77,8 @@ def _assemble(per_rank):
 
 
 @pytest.mark.parametrize("k,min_count,mode", [(25, 1, "dist"), (31, 2, "dist"), (55, 1, "dist"), (31, 3, "gather"), (27, 2, "batches"),
-                                              (5, 2, "dist"), (25, 1, "kmerset"), (40, 1, "kmerset")])
+                                              (5, 2, "dist"), (25, 1, "kmerset"), (40, 1, "kmerset"), (31, 2, "skew"), (25, 1, "onespill"),
+                                              (55, 2, "onespill")])
 def test_multi_gpu_build_bit_exact(k, min_count, mode):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
@@ -80,7 +87,7 @@ def test_multi_gpu_build_bit_exact(k, min_count, mode):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, nccl_id, k, min_count, mode, out), nprocs=world, join=True)
-    inputs = [(_reads(r), O.FASTQ) for r in range(world)]
+    inputs = [(_reads(r, mode=mode), O.FASTQ) for r in range(world)]
     if mode == "kmerset":
         want, ost = O.build_kmer_set(inputs, k, threads=4, base="graph")
     else:
