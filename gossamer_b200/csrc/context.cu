@@ -279,9 +279,9 @@ void flush_batch(gsb_ctx* c, bool final_and_only, PartitionInput* pre = nullptr,
     if (c->n_keys == 0 && !pre) return;
     Workspace& ws = c->ws;
     const int kb = c->key_bytes;
-    ensure_alt(c, pre ? std::max<u64>(pre->n_cap, c->n_keys) : c->n_keys);
-    DevBuf<u8>& alt = c->alt;
-    u8* const src = pre ? (u8*)pre->keys : (c->batch_src ? c->batch_src : c->keys.p);
+    if (!pre) ensure_alt(c, c->n_keys);
+    u8* const src = pre ? (u8*)pre->keys : (c->batch_src ? c->batch_src : c->keys.p);   // the batch
+    u8* const alt = pre ? (u8*)pre->scratch : c->alt.p;                                // scratch of the same capacity
     c->batch_src = nullptr;
     int passes_run = 0;
     ReducedRun run; u64 distinct = 0, n_self_rc = 0;
@@ -302,10 +302,9 @@ void flush_batch(gsb_ctx* c, bool final_and_only, PartitionInput* pre = nullptr,
         PartitionPlan plan;
         if (pre) {
             in = std::move(*pre);
-            in.scratch = alt.p;
             plan = *pre_plan;
         } else {
-            in.keys = src; in.scratch = alt.p; in.n = c->n_keys;
+            in.keys = src; in.scratch = alt; in.n = c->n_keys;
             // the fused top-bit histogram describes exactly this batch only if it came straight out of the extraction
             in.hist_top = (c->hist_valid && !c->exchanged_instances) ? c->hist.p : nullptr;
             plan = partition_plan(kb, c->n_keys);
@@ -330,8 +329,8 @@ void flush_batch(gsb_ctx* c, bool final_and_only, PartitionInput* pre = nullptr,
         }
     }
     if (!reduced) {
-        u8* const from = where ? alt.p : src;
-        u8* const other = where ? src : alt.p;
+        u8* const from = where ? alt : src;
+        u8* const other = where ? src : alt;
         const u64* hist = nullptr;
         c->timer.start();
         if (c->mix) sort_unmix_inplace(kb, from, c->n_keys, ws.sm_count, ws.stream, &ws.launches);   // real keys again
@@ -346,7 +345,7 @@ void flush_batch(gsb_ctx* c, bool final_and_only, PartitionInput* pre = nullptr,
     c->stats.n_batches += 1;
     if (!reduced) {
         c->timer.start();
-        reduce_sorted(ws, kb, where ? alt.p : src, nullptr, c->n_keys, min_count, run, &distinct, fold_w, &n_self_rc);
+        reduce_sorted(ws, kb, where ? alt : src, nullptr, c->n_keys, min_count, run, &distinct, fold_w, &n_self_rc);
         c->timer.stop(c->stats.ms_reduce);
     }
     c->counts.n_instances += c->n_keys * (c->fold_w ? 2 : 1);  // the reference counts both strands (src/ReverseComplementAdapter.hh:34-55)
@@ -677,12 +676,16 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
             // ranks merge runs instead of exchanging raw instances) and whether any rank saw a self-complementary window are
             // agreed on first.
             u64 spilled = c->have_acc ? 1 : 0, self_rc_all = c->self_rc_windows, n_total = c->n_keys;
+            std::vector<u64> n_keys_all;
             if (c->comm) {
                 const u64 mine[3] = {spilled, self_rc_all, c->n_keys};
                 std::vector<u64> all;
                 exchange_allgather_u64(c->comm, c->ws, mine, 3, all);
                 spilled = 0; self_rc_all = 0; n_total = 0;
-                for (int r = 0; r < exchange_size(c->comm); ++r) { spilled += all[3 * r]; self_rc_all += all[3 * r + 1]; n_total += all[3 * r + 2]; }
+                for (int r = 0; r < exchange_size(c->comm); ++r) {
+                    spilled += all[3 * r]; self_rc_all += all[3 * r + 1]; n_total += all[3 * r + 2];
+                    n_keys_all.push_back(all[3 * r + 2]);
+                }
             }
             const bool single = spilled == 0;
             c->any_self_rc = self_rc_all > 0;
@@ -695,18 +698,25 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                 if (c->mix) {
                     // the exchange IS the first pass of the partition counting: children of the top bits of the mixed key are
                     // stored straight into their owners' windows; no sampling, no host round trip (exchange.cu)
-                    int min_bits = 0;
+                    int min_bits = 1;
                     while ((1 << min_bits) < exchange_size(c->comm)) ++min_bits;
                     PartitionPlan plan = partition_plan(c->key_bytes, n_total);
                     if (plan.levels == 0) { plan.levels = 1; plan.bits[0] = min_bits; plan.total_bits = min_bits; }
                     else if (plan.bits[0] < min_bits) { plan.total_bits += min_bits - plan.bits[0]; plan.bits[0] = min_bits; }
+                    // this rank's share of a uniform split + 1/8 + a little (every rank computes the same figure)
+                    const u64 share = n_total / (u64)exchange_size(c->comm);
+                    const u64 out_cap = share + share / 8 + (1u << 16);
+                    ensure_alt(c, out_cap);
+                    if (out_cap > c->third_cap) { c->third.free(); c->third_cap = out_cap; c->third.reset(&c->ws, out_cap * c->key_bytes + 64); }
                     PartitionedInstances pi;
                     c->timer.start();
-                    const bool fast = exchange_partition_instances(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->hist.p, n_total, plan.bits[0], &pi);
+                    const bool fast = exchange_partition_pull(c->comm, c->ws, c->key_bytes, c->keys.p, c->n_keys, c->hist.p, n_keys_all, plan.bits[0],
+                                                              plan.levels > 1 ? plan.bits[1] : 0, c->alt.p, out_cap, &pi);
                     c->timer.stop(c->stats.ms_exchange);
                     if (fast) {
                         PartitionInput in;
-                        in.keys = pi.recv; in.cstart = std::move(pi.cstart); in.n_parents = pi.n_parents; in.n_cap = pi.n_cap; in.consumed_bits = pi.bits;
+                        in.keys = pi.recv; in.scratch = c->third.p; in.cstart = std::move(pi.cstart); in.n_parents = pi.n_parents; in.n_cap = pi.n_cap;
+                        in.consumed_bits = pi.bits;
                         c->exchanged_instances = true;
                         flush_batch(c, true, &in, &plan);              // synchronises with the stream
                         if (exchange_partition_aborted(c->comm)) {
@@ -720,6 +730,8 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                             c->exchanged_instances = false;
                         } else {
                             c->stats.ms_all_to_all += exchange_partition_scatter_ms(c->comm);
+                            c->stats.ms_sort_sweeps += exchange_partition_level0_ms(c->comm);   // the HBM-bound local pass
+                            c->stats.sort_passes += 1;
                             c->stats.exchange_bytes_sent += exchange_partition_bytes_sent(c->comm);
                             c->stats.exchange_peer_memory = 1;
                             exchanged_instances = true;

@@ -295,8 +295,9 @@ struct Exchange {
     bool p2p_usable = true;                        // cleared if IPC mapping fails: NCCL send/recv is used instead
     std::vector<u64> peer_cap;                     // [rank] capacity of that rank's window as of the last handshake (same on every rank)
     // partition exchange: results the host reads after its next synchronisation (pinned), events around the scatter
-    u64* host_slots = nullptr;                     // [0] abort flag, [1] bytes this rank stored into OTHER ranks' windows, [2] keys received
-    cudaEvent_t scatter_e0 = nullptr, scatter_e1 = nullptr;
+    u64* host_slots = nullptr;                     // [0] abort flag, [1] keys this rank pulled from OTHER ranks' windows, [2] keys received
+    u64 slot_bytes_scale = 1;
+    cudaEvent_t scatter_e0 = nullptr, scatter_e1 = nullptr, l0_e0 = nullptr, l0_e1 = nullptr;
 };
 
 void exchange_make_id(void* id_out) {
@@ -325,6 +326,8 @@ void exchange_destroy(Exchange* x) {
     if (x->host_slots) cudaFreeHost(x->host_slots);
     if (x->scatter_e0) cudaEventDestroy(x->scatter_e0);
     if (x->scatter_e1) cudaEventDestroy(x->scatter_e1);
+    if (x->l0_e0) cudaEventDestroy(x->l0_e0);
+    if (x->l0_e1) cudaEventDestroy(x->l0_e1);
     if (x->comm) nccl().CommDestroy(x->comm);
     delete x;
 }
@@ -537,7 +540,11 @@ static double host_now_ms() {
 
 void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, u8* parted_buf /* n_keys keys */,
                         DevBuf<u8>& recv, u64* recv_cap, u8** recv_ptr_out, u64* n_recv, ExchangeTiming* timing, u64* piggyback_sum) {
+#ifdef GSB_PROFILING
     const bool trace = getenv("GSB_TRACE_EXCHANGE") != nullptr;
+#else
+    const bool trace = false;
+#endif
     double t_prev = host_now_ms();
     auto lap = [&](const char* what) {
         if (!trace) return;
@@ -679,115 +686,77 @@ void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* k
     *n_recv = total;
 }
 
-// ---- instance exchange as level 0 of the partition counting ------------------------------------------------------
+// ---- instance exchange fused into the partition counting (PULL) --------------------------------------------------
 // The instances are bit-mixed, so equal shares of the mixed key space are equal shares of the instances whatever the
-// genome looks like: child c of the first partition pass (the top `bits` bits) belongs to rank (c * n) >> bits -- no
-// sampling, no splitters.  The extraction kernel has counted the top bits already; ONE device-side all-gather of those
-// histograms tells every rank where its run of every child starts inside the owner's window (children in order, sources
-// in rank order inside a child), and the ordinary partition kernel stores the runs there over NVLink.  The host takes
-// part in none of it: no readback between the all-gather and the local passes that follow.
-struct RankCaps { u64 keys[kMaxRanks]; };
-
-__global__ void __launch_bounds__(1024) exchange_offsets_kernel(const u64* __restrict__ all /* [n][C] */, int n, int bits, int rank, RankCaps caps,
-                                                                u32 cstride, u64* __restrict__ cursor /* [C * cstride] */,
-                                                                u64* __restrict__ cstart_mine /* [P_rank + 1] */, u32* __restrict__ flags /* [0] abort */,
-                                                                u64* __restrict__ sent_remote_bytes, u64* __restrict__ n_recv, int key_bytes) {
-    __shared__ u64 E[kPtExchangeMaxChildren + 1];
-    __shared__ u64 scan_s[1024 / 32 + 1];
-    __shared__ u32 abort_s;
-    const u32 C = 1u << bits;
-    const u32 c = threadIdx.x;
-    if (c == 0) abort_s = 0;
-    u64 tot = 0, before = 0, mine = 0;
-    if (c < C) {
-        for (int s = 0; s < n; ++s) {
-            const u64 v = all[(size_t)s * C + c];
-            tot += v;
-            if (s < rank) before += v;
-            if (s == rank) mine = v;
-        }
-    }
-    const u64 ex = block_exclusive_scan<u64, 1024>(tot, (u64*)nullptr, scan_s);
-    if (c < C) E[c] = ex;
-    if (c == C - 1) E[C] = ex + tot;
-    __syncthreads();
-    auto c_lo = [&](int r) -> u32 { return (u32)(((u64)r * C + (u32)n - 1) / (u32)n); };      // first child of rank r
-    if (c < (u32)n) {                                                    // does every window hold what it will receive?
-        const u64 recv = E[c_lo((int)c + 1)] - E[c_lo((int)c)];
-        if (recv > caps.keys[c]) atomicOr(&abort_s, 1u);
-    }
-    __syncthreads();
-    const bool abort = abort_s != 0;
-    const int owner = c < C ? (int)(((u64)c * (u32)n) >> bits) : 0;
-    if (c < C) cursor[(size_t)c * cstride] = E[c] - E[c_lo(owner)] + before;
-    const u32 lo = c_lo(rank), hi = c_lo(rank + 1);
-    if (c >= lo && c < hi) cstart_mine[c - lo] = abort ? 0ull : E[c] - E[lo];
-    if (c == 0) {
-        cstart_mine[hi - lo] = abort ? 0ull : E[hi] - E[lo];
-        flags[0] = abort ? 1u : 0u;
-        n_recv[0] = abort ? 0ull : E[hi] - E[lo];
-    }
-    // bytes this rank sends to others (for the NVLink figure)
-    u64 remote = (c < C && owner != rank) ? mine * (u64)key_bytes : 0ull;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) remote += __shfl_xor_sync(0xffffffffu, remote, o);
-    if ((c & 31) == 0 && remote) atomicAdd(sent_remote_bytes, remote);
-}
-
-bool exchange_partition_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, const u64* hist_top, u64 n_total, int bits,
-                                  PartitionedInstances* out) {
+// genome looks like: child c of the first partition pass (the top bits0 bits) belongs to rank (c * n) >> bits0 -- no
+// sampling, no splitters.
+//   1. every rank runs the first pass LOCALLY, into its peer-mapped window (HBM speed, long runs);
+//   2. it histograms the next bits1 bits of every child of its own output; one all-reduce of those histograms and one
+//      all-gather of the child starts (both device-side, no host round trip) tell every rank what it owns and where it lies;
+//   3. the SECOND pass of the owner reads its children tile by tile from wherever they are: the partition kernel's bulk
+//      copies (cp.async.bulk -> shared memory, one tile ahead) fetch 7/8 of them from the peers' windows over NVLink.
+// There is no separate transfer step and no staging copy: the exchange IS the read side of a pass that has to happen
+// anyway, and NVLink sees 32 KB bulk reads instead of short scattered stores.
+bool exchange_partition_pull(Exchange* x, Workspace& ws, int key_bytes, void* keys, u64 n_keys, const u64* hist_top, const std::vector<u64>& n_keys_all,
+                             int bits0, int bits1, void* out_local, u64 out_cap_keys, PartitionedInstances* out) {
     if (!x->p2p_usable) return false;
     const int n = x->n;
     cudaStream_t s = ws.stream;
     NcclApi& api = nccl();
-    if (bits > kTopHistBits || (1 << bits) < n) throw StatusError{GSB_EINVAL, "internal: bad first-level width for the exchange"};
-    const u32 C = 1u << bits;
-    // every window: its share of all instances + 1/8 + a little (all ranks compute the same figure)
-    const u64 need_keys = n_total / (u64)n + n_total / (u64)(8 * n) + (1u << 16);
-    std::vector<u64> need_all(n, need_keys * key_bytes + 64);
-    if (!ensure_windows(x, ws, need_all[0], &need_all)) { x->p2p_usable = false; return false; }
+    if (bits0 < 1 || bits0 > kTopHistBits || (1 << bits0) < n || bits1 < 0 || bits1 > 10) throw StatusError{GSB_EINVAL, "internal: bad pass widths for the exchange"};
+    const u32 C = 1u << bits0;
+    std::vector<u64> need_all(n);
+    for (int r = 0; r < n; ++r) need_all[r] = n_keys_all[r] * key_bytes + 64;
+    if (!ensure_windows(x, ws, need_all[x->rank], &need_all)) { x->p2p_usable = false; return false; }
     if (!x->host_slots) {
         GSB_CUDA_TRY(cudaMallocHost((void**)&x->host_slots, 64));
         GSB_CUDA_TRY(cudaEventCreate(&x->scatter_e0));
         GSB_CUDA_TRY(cudaEventCreate(&x->scatter_e1));
+        GSB_CUDA_TRY(cudaEventCreate(&x->l0_e0));
+        GSB_CUDA_TRY(cudaEventCreate(&x->l0_e1));
     }
-    DevBuf<u64> mine(&ws, C), all(&ws, (size_t)C * n);
-    partition_fold_hist(ws, hist_top, bits, mine.p);
-    check(api.AllGather(mine.p, all.p, C, ncclUint64, x->comm, s), "ncclAllGather(top-bit histograms)");
-    const u32 cstride = 32;
-    DevBuf<u64> cursor(&ws, (size_t)C * cstride), scalars(&ws, 4);
-    const u32 lo = (u32)(((u64)x->rank * C + n - 1) / n), hi = (u32)(((u64)(x->rank + 1) * C + n - 1) / n);
-    out->n_parents = hi - lo;
-    out->cstart.reset(&ws, (size_t)out->n_parents + 1);
+    // 1. first pass, local, into the window
+    DevBuf<u64> cstart0;
+    GSB_CUDA_TRY(cudaEventRecord(x->l0_e0, s));
+    partition_local_level0(ws, key_bytes, keys, x->recv_buf, n_keys, bits0, hist_top, cstart0);
+    GSB_CUDA_TRY(cudaEventRecord(x->l0_e1, s));
+    // 2. histograms of the next bits; all-reduce + all-gather
+    const size_t n_hist = (size_t)C << bits1;
+    DevBuf<u64> hist_all(&ws, n_hist), gathered(&ws, (size_t)(C + 1) * n), scalars(&ws, 4);
+    partition_next_hist(ws, key_bytes, x->recv_buf, cstart0.p, bits0, n_keys, bits1, hist_all.p);
+    check(api.AllGather(cstart0.p, gathered.p, C + 1, ncclUint64, x->comm, s), "ncclAllGather(child starts)");
+    check(api.AllReduce(hist_all.p, hist_all.p, n_hist, ncclUint64, ncclSum, x->comm, s), "ncclAllReduce(histograms)");
+    // (the collectives also order this rank's pull behind every peer's first pass)
     GSB_CUDA_TRY(cudaMemsetAsync(scalars.p, 0, 32, s));
-    RankCaps caps;
-    memset(&caps, 0, sizeof(caps));
-    for (int r = 0; r < n; ++r) caps.keys[r] = (x->peer_cap[r] - 64) / key_bytes;
-    exchange_offsets_kernel<<<1, 1024, 0, s>>>(all.p, n, bits, x->rank, caps, cstride, cursor.p, out->cstart.p, (u32*)scalars.p, scalars.p + 1, scalars.p + 2, key_bytes);
-    ++ws.launches;
+    partition_pull_check(ws, hist_all.p, gathered.p, bits0, bits1, n, x->rank, out_cap_keys, (u32*)scalars.p, scalars.p + 2, scalars.p + 1);
     GSB_CUDA_TRY(cudaMemcpyAsync(x->host_slots, scalars.p, 24, cudaMemcpyDeviceToHost, s));   // read by the host after its next synchronisation
-    void* bases[kMaxRanks];
+    // 3. second pass, pulling
+    const u32 lo = (u32)(((u64)x->rank * C + n - 1) / n), hi = (u32)(((u64)(x->rank + 1) * C + n - 1) / n);
+    const void* bases[kMaxRanks];
     for (int r = 0; r < n; ++r) bases[r] = x->peer_ptr[r];
-    GSB_CUDA_TRY(cudaEventRecord(x->scatter_e0, s));
-    partition_scatter_to_peers(ws, key_bytes, keys, n_keys, bits, cursor.p, cstride, bases, n, (const u32*)scalars.p);
-    // barrier, on the device only: the kernels enqueued behind this all-reduce start after every rank's scatter has finished
-    DevBuf<u64> flag(&ws, 2);
-    GSB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, 16, s));
-    check(api.AllReduce(flag.p, flag.p + 1, 1, ncclUint64, ncclSum, x->comm, s), "ncclAllReduce(barrier)");
-    GSB_CUDA_TRY(cudaEventRecord(x->scatter_e1, s));
-    out->recv = x->recv_buf;
-    out->n_cap = (x->recv_cap_bytes - 64) / key_bytes;
-    out->bits = bits;
+    partition_pull_level(ws, key_bytes, bases, n, gathered.p, bits0, lo, hi - lo, out_cap_keys, bits1, hist_all.p + ((size_t)lo << bits1), out_local,
+                         (const u32*)scalars.p, out->cstart, x->scatter_e0, x->scatter_e1);
+    out->recv = (u8*)out_local;
+    out->n_parents = (u64)(hi - lo) << bits1;
+    out->n_cap = out_cap_keys;
+    out->bits = bits0 + bits1;
+    x->slot_bytes_scale = (u64)key_bytes;
     return true;
 }
 
 // valid after the host has synchronised with the stream
 bool exchange_partition_aborted(const Exchange* x) { return x->host_slots && (u32)x->host_slots[0] != 0; }
-u64 exchange_partition_bytes_sent(const Exchange* x) { return x->host_slots ? x->host_slots[1] : 0; }
+u64 exchange_partition_bytes_sent(const Exchange* x) { return x->host_slots ? x->host_slots[1] * x->slot_bytes_scale : 0; }
 u64 exchange_partition_received(const Exchange* x) { return x->host_slots ? x->host_slots[2] : 0; }
 double exchange_partition_scatter_ms(const Exchange* x) {
     float ms = 0;
     if (x->scatter_e0 && cudaEventElapsedTime(&ms, x->scatter_e0, x->scatter_e1) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+    return ms;
+}
+
+double exchange_partition_level0_ms(const Exchange* x) {
+    float ms = 0;
+    if (x->l0_e0 && cudaEventElapsedTime(&ms, x->l0_e0, x->l0_e1) != cudaSuccess) { cudaGetLastError(); ms = 0; }
     return ms;
 }
 

@@ -36,17 +36,19 @@ struct ExchangeTiming { double ms_all_to_all = 0; u64 bytes_sent_remote = 0; boo
 void exchange_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, u8* parted_buf,
                         DevBuf<u8>& recv, u64* recv_cap, u8** recv_ptr_out, u64* n_recv, ExchangeTiming* timing,
                         u64* piggyback_sum = nullptr /* in: this rank's number, out: the sum over all ranks (rides on the sample all-gather) */);
-// Instance exchange as level 0 of the partition counting (exchange.cu): this rank's n_keys bit-mixed keys are split by
-// their top `bits` bits and stored straight into the owners' windows; rank r owns the children [ceil(r*2^bits/n),
-// ceil((r+1)*2^bits/n)).  Collective; no host synchronisation inside.  false (on every rank): peer memory unusable.
+// Instance exchange fused into the partition counting (exchange.cu): every rank runs the first pass (top bits0 bits of the
+// mixed key) locally into its peer-mapped window; rank r owns the children [ceil(r*2^bits0/n), ceil((r+1)*2^bits0/n)) and its
+// second pass (bits1 more bits) pulls them tile by tile out of all ranks' windows over NVLink into out_local (capacity
+// out_cap_keys).  Collective; no host synchronisation inside.  false (on every rank): peer memory unusable.
 struct PartitionedInstances { u8* recv = nullptr; DevBuf<u64> cstart; u64 n_parents = 0, n_cap = 0; int bits = 0; };
-bool exchange_partition_instances(Exchange* x, Workspace& ws, int key_bytes, const void* keys, u64 n_keys, const u64* hist_top, u64 n_total, int bits,
-                                  PartitionedInstances* out);
+bool exchange_partition_pull(Exchange* x, Workspace& ws, int key_bytes, void* keys, u64 n_keys, const u64* hist_top, const std::vector<u64>& n_keys_all,
+                             int bits0, int bits1, void* out_local, u64 out_cap_keys, PartitionedInstances* out);
 // the following are valid once the host has synchronised with the stream
-bool exchange_partition_aborted(const Exchange* x);      // some window was too small for what it would have received: nothing was moved
+bool exchange_partition_aborted(const Exchange* x);      // some rank's buffer was too small for its share: nothing was pulled
 u64 exchange_partition_bytes_sent(const Exchange* x);
 u64 exchange_partition_received(const Exchange* x);      // keys that arrived in this rank's window
-double exchange_partition_scatter_ms(const Exchange* x);
+double exchange_partition_scatter_ms(const Exchange* x);  // the pulling pass
+double exchange_partition_level0_ms(const Exchange* x);   // the local first pass (small kernels around it included)
 int exchange_rank(const Exchange* x);
 int exchange_size(const Exchange* x);
 // Collective.  Copies this rank's slice into its window and returns the global view; false if peer

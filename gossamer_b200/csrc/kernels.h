@@ -129,14 +129,6 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
 
 // keys[i] = key_unmix(keys[i])
 void sort_unmix_inplace(int key_bytes, void* keys, u64 n, int sm_count, cudaStream_t s, u64* launches);
-// Counting from a PARTIAL sort (sort.cu, "counting from a partial sort"): `grouped` holds bit-MIXED keys (key_mix)
-// that have been LSD-sorted on their low group_bits bits only; the outputs are the real keys.  Produces the min-count-filtered (key, count) pairs in ARBITRARY order (the caller sorts the
-// survivors by the full key); fold_w as in reduce_sorted.  out_keys_scratch: room for n keys.  Returns false, with
-// nothing produced, if too many groups hold several keys or too many keys survive -- the caller then finishes the
-// sort (digits group_bits/8 .. P) and uses reduce_sorted.
-bool reduce_groups(Workspace& ws, int key_bytes, int key_bits, const void* grouped, u64 n, int group_bits, u64 min_count, int fold_w,
-                   void* out_keys_scratch, ReducedRun& out, u64* m_distinct, u64* n_self_rc);
-
 // number of elements the descriptors {first index, length} cover -> *total_dev (sort.cu)
 void sort_desc_total(const ulonglong2* desc, u64 n_desc, u64* total_dev, cudaStream_t s, u64* launches);
 
@@ -163,6 +155,13 @@ bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, PartitionInpu
 void partition_scatter_to_peers(Workspace& ws, int key_bytes, const void* in, u64 n, int bits, u64* cursor, u32 cstride,
                                 void* const* peer_base, int n_peers, const u32* abort_flag);
 void partition_fold_hist(Workspace& ws, const u64* hist_top, int bits, u64* out);
+// pieces of the multi-GPU PULL exchange (partition.cu; orchestrated by exchange.cu)
+void partition_local_level0(Workspace& ws, int key_bytes, void* in, void* out, u64 n, int bits, const u64* hist_top, DevBuf<u64>& cstart_out);
+void partition_next_hist(Workspace& ws, int key_bytes, const void* keys, const u64* cstart, int bits0, u64 n, int bits, u64* hist);
+void partition_pull_check(Workspace& ws, u64* hist_all, const u64* gathered, int bits0, int bits1, int n_ranks, int rank, u64 cap_keys,
+                          u32* abort_flag, u64* n_recv, u64* n_remote);
+void partition_pull_level(Workspace& ws, int key_bytes, const void* const* src_base, int n_src, const u64* gathered, int bits0, u32 c_lo, u32 n_parents,
+                          u64 n_cap, int bits, const u64* hist_slice, void* out, const u32* abort_flag, DevBuf<u64>& cstart_out, cudaEvent_t e0, cudaEvent_t e1);
 
 // ---- fold.cu ---------------------------------------------------------------------------------
 // Strand folding (graph mode): instances are counted as min(x, rc x); these restore both strands.

@@ -57,19 +57,20 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
                  "WAIT_DONE:\n\t}" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
-struct TileRef { u64 begin; u32 count; u32 parent; };
+struct TileRef { u64 begin; u32 count; u32 parent; u32 src; };
 
-// descs == nullptr: one parent covering [0, n)
+// descs == nullptr: one parent covering [0, n).  A descriptor is {begin bits 0..31, begin bits 32..55 | source rank << 24,
+// count, parent}: the tile's keys are src_base[source rank][begin, begin + count).
 __device__ __forceinline__ TileRef tile_ref(const uint4* __restrict__ descs, u32 tile, u64 n, u32 tile_keys) {
     TileRef r;
     if (descs) {
         const uint4 d = descs[tile];
-        r.begin = (u64)d.x | ((u64)d.y << 32); r.count = d.z; r.parent = d.w;
+        r.begin = (u64)d.x | ((u64)(d.y & 0xFFFFFFu) << 32); r.src = d.y >> 24; r.count = d.z; r.parent = d.w;
     } else {
         r.begin = (u64)tile * tile_keys;
         const u64 rem = n - r.begin;
         r.count = rem < (u64)tile_keys ? (u32)rem : tile_keys;
-        r.parent = 0;
+        r.parent = 0; r.src = 0;
     }
     return r;
 }
@@ -85,7 +86,7 @@ __device__ __forceinline__ u32 perm_mul(u32 n_tiles) {
 __device__ __forceinline__ u32 perm_tile(u32 i, u32 mul, u32 n_tiles) { return (u32)(((u64)i * mul) % n_tiles); }
 
 struct PartArgs {
-    const void* in;
+    const void* src_base[kMaxRanks];   // where the tiles are read from: [0] = this GPU's buffer; others = peers' buffers (NVLink), pull exchange
     void* out;
     const uint4* descs;        // per-tile {begin lo, begin hi, count, parent}; nullptr = single parent [0, n)
     const u32* n_tiles_dev;    // nullptr = n_tiles
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
     constexpr u32 TILE = kPtThreads * ITEMS;
     __shared__ u32 cnt_s[kPtMaxBins];
     const int t = threadIdx.x;
-    const K* __restrict__ in = (const K*)a.in;
+    const K* __restrict__ in = (const K*)a.src_base[0];
     const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles;
     const u32 mul = perm_mul(n_tiles);
     const u32 nbins = 1u << a.bits, mask = nbins - 1;
@@ -171,7 +172,6 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
 
     if (a.abort && *a.abort) return;
     const int t = threadIdx.x;
-    const K* __restrict__ in = (const K*)a.in;
     const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles;
     const u32 mul = perm_mul(n_tiles);
     const u32 mask = (1u << a.bits) - 1;
@@ -184,11 +184,11 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
         const u32 skip = sizeof(K) == 8 ? (u32)(tr.begin & 1) : 0u;
         const u32 bytes = (((skip + tr.count) * (u32)sizeof(K)) + 15u) & ~15u;
         mbar_expect_tx(&full_bar, bytes);
-        bulk_load(stage, in + (tr.begin - skip), bytes, &full_bar);
+        bulk_load(stage, (const K*)a.src_base[tr.src] + (tr.begin - skip), bytes, &full_bar);   // local HBM, or a peer's buffer over NVLink
     };
 
     u32 it = blockIdx.x;
-    TileRef cur{0, 0, 0};
+    TileRef cur{0, 0, 0, 0};
     if (it < n_tiles) {
         cur = tile_ref(a.descs, perm_tile(it, mul, n_tiles), a.n, TILE);
         if (t == 0) issue(cur);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
     u32 parity = 0;
     for (; it < n_tiles; it += gridDim.x) {
         const u32 nit = it + gridDim.x;
-        TileRef nxt{0, 0, 0};
+        TileRef nxt{0, 0, 0, 0};
         if (nit < n_tiles) nxt = tile_ref(a.descs, perm_tile(nit, mul, n_tiles), a.n, TILE);
         mbar_wait(&full_bar, parity);
         parity ^= 1;
@@ -596,58 +596,142 @@ namespace {
 
 struct LevelTiming { cudaEvent_t e0 = nullptr, e1 = nullptr; };
 
-// One pass over `cur` (parents given by cstart, or one parent [0, n) when cstart is empty) by `bits` more bits into `other`.
-// Produces the child starts.  hist_ready: optional histogram [n_parents << bits] that is already known.
-void run_level(Workspace& ws, int key_bytes, void* cur, void* other, u64 n, u64 n_cap, DevBuf<u64>& cstart, u64 n_parents, int consumed, int bits,
-               const u64* hist_ready, PartitionTiming* timing, std::vector<LevelTiming>& events) {
+struct LevelTiles {
+    DevBuf<uint4> descs;
+    DevBuf<u32> n_tiles_dev;
+    u64 tiles_ub = 0;
+    void apply(PartArgs& pa) const { pa.descs = descs.p; pa.n_tiles_dev = descs.p ? n_tiles_dev.p : nullptr; pa.n_tiles = (u32)tiles_ub; }
+};
+
+// tiles over local parents given by cstart [n_parents + 1] (or one parent [0, n) when cstart is null)
+void build_tiles(Workspace& ws, int key_bytes, const u64* cstart, u64 n_parents, u64 n, u64 n_cap, LevelTiles& tiles) {
     cudaStream_t s = ws.stream;
     const u32 tile_keys = partition_tile_keys(key_bytes);
-    const u64 n_children = n_parents << bits;
-    const bool plain = cstart.p == nullptr;                          // one parent, its size known on the host
-    PartArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    pa.in = cur; pa.out = other; pa.n = n;
-    pa.shift = 64 - consumed - bits; pa.bits = bits;
-    pa.peer[0] = other; pa.n_peers = 1; pa.abort = nullptr;
-    DevBuf<uint4> descs;
-    DevBuf<u32> tile_first, n_tiles_dev, scan_tmp32;
-    const u64 tiles_ub = plain ? (n + tile_keys - 1) / tile_keys : (n_cap + tile_keys - 1) / tile_keys + n_parents;
-    if (tiles_ub > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
-    pa.n_tiles = (u32)tiles_ub;
-    if (!plain) {
-        descs.reset(&ws, tiles_ub);
-        tile_first.reset(&ws, n_parents + 1);
-        n_tiles_dev.reset(&ws, 1);
-        scan_tmp32.reset(&ws, scan_tmp_elems(n_parents));
-        tiles_per_parent_kernel<<<(unsigned)((n_parents + 255) / 256), 256, 0, s>>>(cstart.p, (u32)n_parents, tile_keys, tile_first.p);
-        exclusive_scan<u32, u32>(tile_first.p, tile_first.p, n_parents, 0u, n_tiles_dev.p, scan_tmp32.p, s, &ws.launches);
-        fill_descs_kernel<<<(unsigned)((tiles_ub + 255) / 256), 256, 0, s>>>(cstart.p, tile_first.p, (u32)n_parents, n_tiles_dev.p, tile_keys, descs.p);
-        ws.launches += 2;
-        pa.descs = descs.p; pa.n_tiles_dev = n_tiles_dev.p;
-    }
-    // histogram of this level's digit per parent -> child starts
-    DevBuf<u64> hist(&ws, n_children), cnext(&ws, n_children + 1), scan_tmp(&ws, scan_tmp_elems(n_children));
-    const u64* hsrc = hist_ready;
-    if (!hsrc) {
-        GSB_CUDA_TRY(cudaMemsetAsync(hist.p, 0, n_children * 8, s));
-        pa.hist = hist.p;
-        const int grid_hist = (int)std::min<u64>(tiles_ub, (u64)ws.sm_count * 8);
-        if (key_bytes == 8) launch_hist<u64>(pa, grid_hist, s); else launch_hist<Key128>(pa, grid_hist, s);
-        ++ws.launches;
-        hsrc = hist.p;
-    }
-    exclusive_scan<u64, u64>(hsrc, cnext.p, n_children, 0ull, cnext.p + n_children, scan_tmp.p, s, &ws.launches);
+    tiles.tiles_ub = cstart ? (n_cap + tile_keys - 1) / tile_keys + n_parents : (n + tile_keys - 1) / tile_keys;
+    if (tiles.tiles_ub > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
+    if (!cstart) return;
+    tiles.descs.reset(&ws, tiles.tiles_ub);
+    tiles.n_tiles_dev.reset(&ws, 1);
+    DevBuf<u32> tile_first(&ws, n_parents + 1), scan_tmp32(&ws, scan_tmp_elems(n_parents));
+    tiles_per_parent_kernel<<<(unsigned)((n_parents + 255) / 256), 256, 0, s>>>(cstart, (u32)n_parents, tile_keys, tile_first.p);
+    exclusive_scan<u32, u32>(tile_first.p, tile_first.p, n_parents, 0u, tiles.n_tiles_dev.p, scan_tmp32.p, s, &ws.launches);
+    fill_descs_kernel<<<(unsigned)((tiles.tiles_ub + 255) / 256), 256, 0, s>>>(cstart, tile_first.p, (u32)n_parents, tiles.n_tiles_dev.p, tile_keys, tiles.descs.p);
+    ws.launches += 2;
+}
+
+// hist[parent << bits | digit] += number of such keys (hist must be zeroed by the caller)
+void level_hist(Workspace& ws, int key_bytes, PartArgs pa, const LevelTiles& tiles, u64* hist) {
+    tiles.apply(pa);
+    pa.hist = hist;
+    const int grid = (int)std::min<u64>(tiles.tiles_ub, (u64)ws.sm_count * 8);
+    if (grid == 0) return;
+    if (key_bytes == 8) launch_hist<u64>(pa, grid, ws.stream); else launch_hist<Key128>(pa, grid, ws.stream);
+    ++ws.launches;
+}
+
+// child starts from the histogram, cursors, the scatter pass itself
+void level_scatter(Workspace& ws, int key_bytes, PartArgs pa, const LevelTiles& tiles, const u64* hist, u64 n_children, DevBuf<u64>& cstart_out,
+                   PartitionTiming* timing, std::vector<LevelTiming>& events) {
+    cudaStream_t s = ws.stream;
+    DevBuf<u64> cnext(&ws, n_children + 1), scan_tmp(&ws, scan_tmp_elems(n_children));
+    exclusive_scan<u64, u64>(hist, cnext.p, n_children, 0ull, cnext.p + n_children, scan_tmp.p, s, &ws.launches);
     // cursors: spread over distinct cache lines when there are few of them (every tile in flight hits all of them)
     const u32 cstride = n_children <= 4096 ? 32u : 1u;
     DevBuf<u64> cursor(&ws, n_children * cstride);
     init_cursor_kernel<<<(unsigned)((n_children + 255) / 256), 256, 0, s>>>(cnext.p, cursor.p, n_children, cstride);
     ++ws.launches;
+    tiles.apply(pa);
     pa.cursor = cursor.p; pa.cstride = cstride; pa.hist = nullptr;
     LevelTiming lt;
     if (timing) { GSB_CUDA_TRY(cudaEventCreate(&lt.e0)); GSB_CUDA_TRY(cudaEventCreate(&lt.e1)); GSB_CUDA_TRY(cudaEventRecord(lt.e0, s)); }
-    launch_scatter(key_bytes, pa, tiles_ub, ws);
+    if (tiles.tiles_ub) launch_scatter(key_bytes, pa, tiles.tiles_ub, ws);
     if (timing) { GSB_CUDA_TRY(cudaEventRecord(lt.e1, s)); events.push_back(lt); }
-    cstart = std::move(cnext);
+    cstart_out = std::move(cnext);
+}
+
+PartArgs local_args(const void* cur, void* other, u64 n, int consumed, int bits) {
+    PartArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.src_base[0] = cur; pa.out = other; pa.n = n;
+    pa.shift = 64 - consumed - bits; pa.bits = bits;
+    pa.peer[0] = other; pa.n_peers = 1; pa.abort = nullptr;
+    return pa;
+}
+
+// One pass over `cur` (parents given by cstart, or one parent [0, n) when cstart is empty) by `bits` more bits into `other`.
+// Produces the child starts.  hist_ready: optional histogram [n_parents << bits] that is already known.
+void run_level(Workspace& ws, int key_bytes, void* cur, void* other, u64 n, u64 n_cap, DevBuf<u64>& cstart, u64 n_parents, int consumed, int bits,
+               const u64* hist_ready, PartitionTiming* timing, std::vector<LevelTiming>& events) {
+    const u64 n_children = n_parents << bits;
+    PartArgs pa = local_args(cur, other, n, consumed, bits);
+    LevelTiles tiles;
+    build_tiles(ws, key_bytes, cstart.p, n_parents, n, n_cap, tiles);
+    DevBuf<u64> hist;
+    if (!hist_ready) {
+        hist.reset(&ws, n_children);
+        GSB_CUDA_TRY(cudaMemsetAsync(hist.p, 0, n_children * 8, ws.stream));
+        level_hist(ws, key_bytes, pa, tiles, hist.p);
+        hist_ready = hist.p;
+    }
+    level_scatter(ws, key_bytes, pa, tiles, hist_ready, n_children, cstart, timing, events);
+}
+
+// ---- pull exchange: tiles over the runs that every source rank holds of this rank's children ------------------------------
+// gathered[s * (C + 1) + c] = start of child c in source s's level-0 output; pair q = p * n_src + s (p: this rank's p-th child)
+__global__ void pull_tiles_per_pair_kernel(const u64* __restrict__ gathered, u32 C, u32 n_src, u32 c_lo, u32 n_pairs, u32 tile_keys, u32* __restrict__ tp) {
+    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pairs) return;
+    const u32 p = q / n_src, sr = q % n_src;
+    const u64* g = gathered + (size_t)sr * (C + 1) + c_lo + p;
+    tp[q] = (u32)((g[1] - g[0] + tile_keys - 1) / tile_keys);
+}
+
+__global__ void pull_fill_descs_kernel(const u64* __restrict__ gathered, u32 C, u32 n_src, u32 c_lo, u32 n_pairs, const u32* __restrict__ tile_first,
+                                       const u32* __restrict__ n_tiles_dev, u32 tile_keys, uint4* __restrict__ descs) {
+    const u32 tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= *n_tiles_dev) return;
+    u32 lo = 0, hi = n_pairs;
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (tile_first[mid] <= tile) lo = mid + 1; else hi = mid; }
+    const u32 q = lo - 1, p = q / n_src, sr = q % n_src;
+    const u64* g = gathered + (size_t)sr * (C + 1) + c_lo + p;
+    const u64 begin = g[0] + (u64)(tile - tile_first[q]) * tile_keys;
+    const u64 rem = g[1] - begin;
+    descs[tile] = make_uint4((u32)begin, (u32)((begin >> 32) & 0xFFFFFFu) | (sr << 24), rem < (u64)tile_keys ? (u32)rem : tile_keys, p);
+}
+
+// after the all-reduce of the next level's histograms: does this rank's share fit its buffer?  If not (on any rank: every
+// rank evaluates every rank), the flag is raised and this rank's slice of the histogram is zeroed, so that everything
+// downstream sees empty buckets.  Also: how many keys this rank will pull, and how many of those from other ranks.
+__global__ void __launch_bounds__(1024) pull_check_kernel(u64* __restrict__ hist_all /* [C << b1] */, const u64* __restrict__ gathered, u32 C, int b1, int n, int rank,
+                                                          u64 cap_keys, u32* __restrict__ abort_flag, u64* __restrict__ n_recv, u64* __restrict__ n_remote) {
+    __shared__ u64 tot_s[kMaxRanks];
+    __shared__ u32 abort_s;
+    const u32 t = threadIdx.x;
+    if (t < kMaxRanks) tot_s[t] = 0;
+    if (t == 0) abort_s = 0;
+    __syncthreads();
+    // per-rank totals from the level-0 child sizes (sum over sources)
+    for (u32 c = t; c < C; c += blockDim.x) {
+        u64 v = 0;
+        for (int sr = 0; sr < n; ++sr) { const u64* g = gathered + (size_t)sr * (C + 1) + c; v += g[1] - g[0]; }
+        atomicAdd(&tot_s[(u32)(((u64)c * (u32)n) / C)], v);
+    }
+    __syncthreads();
+    if (t < (u32)n && tot_s[t] > cap_keys) atomicOr(&abort_s, 1u);
+    __syncthreads();
+    const bool abort = abort_s != 0;
+    const u32 lo = (u32)(((u64)rank * C + n - 1) / n), hi = (u32)(((u64)(rank + 1) * C + n - 1) / n);
+    if (abort) {
+        const u64 a = (u64)lo << b1, b = (u64)hi << b1;
+        for (u64 i = a + t; i < b; i += blockDim.x) hist_all[i] = 0;
+    }
+    if (t == 0) {
+        *abort_flag = abort ? 1u : 0u;
+        u64 mine_local = 0;
+        for (u32 c = lo; c < hi; ++c) { const u64* g = gathered + (size_t)rank * (C + 1) + c; mine_local += g[1] - g[0]; }
+        *n_recv = abort ? 0ull : tot_s[rank];
+        *n_remote = abort ? 0ull : tot_s[rank] - mine_local;
+    }
 }
 
 }  // namespace
@@ -660,7 +744,7 @@ void partition_scatter_to_peers(Workspace& ws, int key_bytes, const void* in, u6
     const u32 tile_keys = partition_tile_keys(key_bytes);
     PartArgs pa;
     memset(&pa, 0, sizeof(pa));
-    pa.in = in; pa.out = nullptr; pa.n = n;
+    pa.src_base[0] = in; pa.out = nullptr; pa.n = n;
     pa.shift = 64 - bits; pa.bits = bits;
     for (int r = 0; r < n_peers; ++r) pa.peer[r] = peer_base[r];
     pa.n_peers = n_peers; pa.abort = abort_flag;
@@ -674,6 +758,67 @@ void partition_scatter_to_peers(Workspace& ws, int key_bytes, const void* in, u6
 void partition_fold_hist(Workspace& ws, const u64* hist_top, int bits, u64* out) {
     fold_hist_kernel<<<((1u << bits) + 255) / 256, 256, 0, ws.stream>>>(hist_top, kTopHistBits, bits, out);
     ++ws.launches;
+}
+
+// ---- pieces of the multi-GPU pull exchange (orchestrated by exchange.cu) -------------------------------------------------
+// level 0, local: this rank's n keys by their top `bits` bits into `out` (its peer-mapped window); cstart_out [2^bits + 1]
+void partition_local_level0(Workspace& ws, int key_bytes, void* in, void* out, u64 n, int bits, const u64* hist_top, DevBuf<u64>& cstart_out) {
+    std::vector<LevelTiming> ev;
+    DevBuf<u64> folded;
+    const u64* hist_ready = nullptr;
+    if (hist_top && bits <= kTopHistBits) {
+        folded.reset(&ws, (size_t)1 << bits);
+        partition_fold_hist(ws, hist_top, bits, folded.p);
+        hist_ready = folded.p;
+    }
+    DevBuf<u64> none;
+    run_level(ws, key_bytes, in, out, n, n, none, 1, 0, bits, hist_ready, nullptr, ev);
+    cstart_out = std::move(none);
+}
+
+// histogram of the NEXT `bits` bits of every level-0 child of this rank's own output: hist [2^(bits0 + bits)] (zeroed here)
+void partition_next_hist(Workspace& ws, int key_bytes, const void* keys, const u64* cstart, int bits0, u64 n, int bits, u64* hist) {
+    const u64 n_parents = 1ull << bits0;
+    GSB_CUDA_TRY(cudaMemsetAsync(hist, 0, (n_parents << bits) * 8, ws.stream));
+    PartArgs pa = local_args(keys, nullptr, n, bits0, bits);
+    LevelTiles tiles;
+    build_tiles(ws, key_bytes, cstart, n_parents, n, n, tiles);
+    level_hist(ws, key_bytes, pa, tiles, hist);
+}
+
+void partition_pull_check(Workspace& ws, u64* hist_all, const u64* gathered, int bits0, int bits1, int n_ranks, int rank, u64 cap_keys,
+                          u32* abort_flag, u64* n_recv, u64* n_remote) {
+    pull_check_kernel<<<1, 1024, 0, ws.stream>>>(hist_all, gathered, 1u << bits0, bits1, n_ranks, rank, cap_keys, abort_flag, n_recv, n_remote);
+    ++ws.launches;
+}
+
+// level 1 of a multi-GPU build, fused with the exchange: this rank's children [c_lo, c_lo + n_parents) are PULLED tile by
+// tile from wherever they lie -- src_base[s] is rank s's level-0 output, peer-mapped; the partition kernel's bulk copies
+// fetch them over NVLink -- and split by the next `bits` bits into `out` (local).  hist_slice [n_parents << bits]: the
+// all-reduced histogram of exactly these children.  cstart_out [(n_parents << bits) + 1].
+void partition_pull_level(Workspace& ws, int key_bytes, const void* const* src_base, int n_src, const u64* gathered, int bits0, u32 c_lo, u32 n_parents,
+                          u64 n_cap, int bits, const u64* hist_slice, void* out, const u32* abort_flag, DevBuf<u64>& cstart_out, cudaEvent_t e0, cudaEvent_t e1) {
+    cudaStream_t s = ws.stream;
+    const u32 tile_keys = partition_tile_keys(key_bytes);
+    const u32 C = 1u << bits0;
+    const u32 n_pairs = n_parents * (u32)n_src;
+    LevelTiles tiles;
+    tiles.tiles_ub = (n_cap + tile_keys - 1) / tile_keys + n_pairs;
+    if (tiles.tiles_ub > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
+    tiles.descs.reset(&ws, tiles.tiles_ub);
+    tiles.n_tiles_dev.reset(&ws, 1);
+    DevBuf<u32> tile_first(&ws, (size_t)n_pairs + 1), scan_tmp32(&ws, scan_tmp_elems(n_pairs));
+    pull_tiles_per_pair_kernel<<<(n_pairs + 255) / 256, 256, 0, s>>>(gathered, C, (u32)n_src, c_lo, n_pairs, tile_keys, tile_first.p);
+    exclusive_scan<u32, u32>(tile_first.p, tile_first.p, n_pairs, 0u, tiles.n_tiles_dev.p, scan_tmp32.p, s, &ws.launches);
+    pull_fill_descs_kernel<<<(unsigned)((tiles.tiles_ub + 255) / 256), 256, 0, s>>>(gathered, C, (u32)n_src, c_lo, n_pairs, tile_first.p, tiles.n_tiles_dev.p, tile_keys, tiles.descs.p);
+    ws.launches += 2;
+    PartArgs pa = local_args(nullptr, out, 0, bits0, bits);
+    for (int r = 0; r < n_src; ++r) pa.src_base[r] = src_base[r];
+    pa.abort = abort_flag;
+    std::vector<LevelTiming> ev;
+    if (e0) GSB_CUDA_TRY(cudaEventRecord(e0, s));
+    level_scatter(ws, key_bytes, pa, tiles, hist_slice, (u64)n_parents << bits, cstart_out, nullptr, ev);
+    if (e1) GSB_CUDA_TRY(cudaEventRecord(e1, s));
 }
 
 // Count bit-mixed keys (see the file header).  in.keys holds them; in.scratch is a buffer of the same capacity; both are

@@ -86,7 +86,13 @@ template <typename K, typename LB, int THREADS, int ITEMS, bool HAS_VALUES, int 
 __global__ void __launch_bounds__(THREADS, MINB) onesweep_kernel(const K* __restrict__ in, K* __restrict__ out,
                                                                  const u64* __restrict__ vin, u64* __restrict__ vout,
                                                                  u64 n, int shift, const u64* __restrict__ digit_base,
-                                                                 LB* lookback, u32* ticket, int ablate) {
+                                                                 LB* lookback, u32* ticket, int ablate_arg) {
+#ifdef GSB_PROFILING
+    const int ablate = ablate_arg;                              // profiling switches (wrong results by construction): -DGSB_PROFILING builds only
+#else
+    constexpr int ablate = 0;
+    (void)ablate_arg;
+#endif
     typedef KeyOps<K> KO;
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * ITEMS;
@@ -284,11 +290,7 @@ void sort_set_tuning(int id) {
 }
 
 // tile shape of the (key, payload) sweeps on 64-bit keys: 0 = 256 x 16 at 2 CTAs/SM, 1 = 256 x 8 at 4, 2 = 256 x 12 at 3
-static int pair_shape() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("GSB_PAIR_SHAPE"); v = e ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
-    return v;
-}
+static int pair_shape() { return 1; }
 
 u64 sort_tile_keys(int key_bytes, bool with_values) {
     if (key_bytes == 8 && with_values) { static const int items[3] = {16, 8, 12}; return 256ull * items[pair_shape()]; }
@@ -506,281 +508,6 @@ __global__ void __launch_bounds__(kRleThreads, 4) rle_emit_kernel(const K* __res
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// counting from a PARTIAL sort
-// ------------------------------------------------------------------------------------------
-// Equal keys agree in every digit, so after LSD sweeps over only the low `gb` bits all instances of a key
-// are already contiguous -- inside the "group" of keys that share those bits.  With gb >= log2(n) + 4 a
-// group mostly holds ONE distinct key (a key meets another one in its group with probability D / 2^gb); then the
-// group is a run and its length is the count, exactly as after a full sort, and the remaining sweeps over
-// n instances are not needed: only the survivors of the min-count filter (a few % of the instances when
-// sequencing errors dominate the distinct keys) are sorted by the full key afterwards, together with their
-// reverse complements (fold.cu).  Groups that do hold different keys are copied out whole and go through
-// the full sort + run-length reduce ("impure" path), so the result never depends on the choice of gb.
-//
-// The instances are stored bit-MIXED (key_mix, common.cuh) when this path is taken, so that the low bits depend
-// on the whole window: with the raw key, a true k-mer and its error variants whose error lies in the high bases
-// share their low bits and nearly every group holds several keys.  Outputs are un-mixed.
-//
-// One streaming pass, output order arbitrary (warp-aggregated appends): the full-key sort that follows
-// makes the final order deterministic because the surviving keys are distinct.
-template <typename K> __device__ __forceinline__ bool same_group(const K& a, const K& b, int gb);
-template <> __device__ __forceinline__ bool same_group<u64>(const u64& a, const u64& b, int gb) {
-    return gb >= 64 ? a == b : ((a ^ b) << (64 - gb)) == 0;
-}
-template <> __device__ __forceinline__ bool same_group<Key128>(const Key128& a, const Key128& b, int gb) {
-    if (gb <= 64) return gb == 64 ? a.lo == b.lo : ((a.lo ^ b.lo) << (64 - gb)) == 0;
-    return a.lo == b.lo && (gb >= 128 ? a.hi == b.hi : ((a.hi ^ b.hi) << (128 - gb)) == 0);
-}
-
-// first index after the group of keys[known] (keys[known] is in the group of `key`): gallop, then bisect
-template <typename K>
-__device__ __forceinline__ u64 group_end(const K* __restrict__ keys, u64 n, u64 known, const K& key, int gb) {
-    u64 a = known, step = 1;
-    while (a + step < n && same_group<K>(keys[a + step], key, gb)) { a += step; step <<= 1; }
-    u64 lo = a + 1, hi = a + step < n ? a + step : n;
-    while (lo < hi) { const u64 mid = lo + ((hi - lo) >> 1); if (same_group<K>(keys[mid], key, gb)) lo = mid + 1; else hi = mid; }
-    return lo;
-}
-
-// any set bit at tile-relative positions [a, b) of a bit vector
-__device__ __forceinline__ bool bits_any(const u32* bits, u32 a, u32 b) {
-    if (a >= b) return false;
-    const u32 wa = a >> 5, wb = (b - 1) >> 5;
-    for (u32 w = wa; w <= wb; ++w) {
-        u32 mask = 0xffffffffu;
-        if (w == wa) mask &= 0xffffffffu << (a & 31);
-        if (w == wb && (b & 31)) mask &= (1u << (b & 31)) - 1;
-        if (bits[w] & mask) return true;
-    }
-    return false;
-}
-
-// ctr[0] survivors appended, ctr[1] impure groups recorded (descriptors {first index, length}; their elements are
-// copied out by copy_groups_kernel), ctr[2] pure groups (= distinct keys in them), ctr[3] pure groups whose key is its
-// own reverse complement.  Appends beyond a capacity are dropped (the counters still advance): the host then falls
-// back to the full sort.
-//
-// Blocked arrangement: a thread owns 8 CONSECUTIVE keys, so group heads and "differs from its predecessor" flags
-// come from register compares, and only a thread's LAST group needs the other threads (two 256-bit vectors in shared
-// memory: which threads contain a head, which have a differing key before their first head).  The first, warp-striped
-// version executed 1.43 G warp instructions for 198 M keys (ncu: XU pipe saturated by the per-item bit searches,
-// 23 % of the stall samples at the barrier) and took 1.8 ms.
-static const int kGrpThreads = 256;
-static const int kGrpItems = 8;
-
-template <typename K>
-__global__ void __launch_bounds__(kGrpThreads, 3) rle_groups_kernel(const K* __restrict__ keys, u64 n, int gb, u64 min_count, int fold_w,
-                                                                    K* __restrict__ out_keys, u64* __restrict__ out_counts, u64 out_cap,
-                                                                    ulonglong2* __restrict__ imp_desc, u64 desc_cap, u64* __restrict__ ctr) {
-    typedef KeyOps<K> KO;
-    constexpr int TILE = kGrpThreads * kGrpItems;
-    constexpr int WORDS = kGrpThreads / 32;
-    __shared__ u32 head_thr[WORDS], preimp_thr[WORDS];
-    __shared__ u8 first_head_s[kGrpThreads];
-    __shared__ u32 keep_warp[WORDS], imp_warp[WORDS], stat_s[2];
-    __shared__ u32 halo_head_s, halo_imp_s;
-    __shared__ u64 keep_base_s, imp_base_s;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const u64 tbase = (u64)blockIdx.x * TILE;
-    const u64 base = tbase + (u64)t * kGrpItems;
-    const u64 tile_end = tbase + TILE < n ? tbase + TILE : n;
-    // Halo: heads / differing keys among the 32 keys that FOLLOW the tile, loaded together with the tile.  The last
-    // group of a tile nearly always ends there; searching for its end with dependent loads instead (gallop + bisect)
-    // kept every tile's 255 other threads waiting at the barrier for ~5 us (1.6 ms for 198 M keys).
-    if (warp == WORDS - 1) {
-        const u64 p = tile_end + lane;                             // p - 1 >= 0: the tile is not empty
-        bool h = false, im = false;
-        if (tile_end < n) {
-            if (p >= n) {
-                h = p == n;                                        // the end of the input closes the last group
-            } else {
-                const K a = keys[p], b = keys[p - 1];
-                h = !same_group<K>(a, b, gb);
-                im = !h && !KO::eq(a, b);
-            }
-        }
-        const u32 hh = __ballot_sync(0xffffffffu, h), hi = __ballot_sync(0xffffffffu, im);
-        if (lane == 0) { halo_head_s = hh; halo_imp_s = hi; }
-    }
-    const int nv = base >= n ? 0 : (int)(n - base < (u64)kGrpItems ? n - base : (u64)kGrpItems);
-    K k[kGrpItems];
-    if (sizeof(K) == 8 && nv == kGrpItems) {                       // 64 contiguous bytes per thread: four 128-bit loads
-        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(keys + base);
-#pragma unroll
-        for (int q = 0; q < kGrpItems / 2; ++q) {
-            const ulonglong2 v = p[q];
-            k[2 * q] = KO::make(v.x, 0); k[2 * q + 1] = KO::make(v.y, 0);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kGrpItems; ++j) k[j] = j < nv ? keys[base + j] : KO::make(0, 0);
-    }
-    K prev = KO::make(0, 0);
-    if (base > 0 && nv > 0) prev = keys[base - 1];
-    u32 headm = 0, impm = 0;
-#pragma unroll
-    for (int j = 0; j < kGrpItems; ++j) {
-        if (j < nv) {
-            const K& p = j ? k[j ? j - 1 : 0] : prev;
-            const bool h = (base + j == 0) || !same_group<K>(k[j], p, gb);
-            const bool im = !h && !KO::eq(k[j], p);                // a different key inside a group
-            headm |= (h ? 1u : 0u) << j;
-            impm |= (im ? 1u : 0u) << j;
-        }
-    }
-    const int first_head = headm ? __ffs(headm) - 1 : kGrpItems;
-    const bool pre_imp = (impm & ((1u << first_head) - 1)) != 0;
-    const u32 b1 = __ballot_sync(0xffffffffu, headm != 0), b2 = __ballot_sync(0xffffffffu, pre_imp);
-    if (lane == 0) { head_thr[warp] = b1; preimp_thr[warp] = b2; }
-    first_head_s[t] = (u8)first_head;
-    if (t < 2) stat_s[t] = 0;
-    __syncthreads();
-
-    u64 cnt[kGrpItems];                                            // pure group: its count; impure group: its length
-    u32 keepm = 0, impgm = 0, pure_groups = 0, self_groups = 0;
-    // groups that start AND end inside this thread's keys: everything is in registers
-#pragma unroll
-    for (int j = 0; j < kGrpItems; ++j) {
-        cnt[j] = 0;
-        const u32 after = ~((2u << j) - 1);
-        const u32 later = headm & after;
-        if (((headm >> j) & 1u) && later) {
-            const int j2 = __ffs(later) - 1;
-            const bool impure = (impm & after & ((1u << j2) - 1)) != 0;
-            const u64 len = (u64)(j2 - j);
-            k[j] = key_unmix(k[j]);                                 // the real key from here on
-            if (impure) {
-                impgm |= 1u << j;
-                cnt[j] = len;
-            } else {
-                ++pure_groups;
-                const bool self_rc = fold_w && KO::eq(key_rc(k[j], fold_w), k[j]);
-                self_groups += self_rc ? 1u : 0u;
-                cnt[j] = self_rc ? 2 * len : len;                   // both strands of a self-complementary key are this key
-                if (cnt[j] >= min_count) keepm |= 1u << j;
-            }
-        }
-    }
-    // the thread's LAST group ends in another thread, in the halo, or further on: handled once, outside the unrolled
-    // loop (inside it, the divergent search code ran for every j that is some lane's last head -- i.e. 8 times)
-    const int jl = headm ? 31 - __clz(headm) : -1;
-    K last_key = KO::make(0, 0);
-    u64 last_cnt = 0;
-    if (jl >= 0) {
-#pragma unroll
-        for (int j = 0; j < kGrpItems; ++j) if (j == jl) last_key = k[j];
-        bool impure = (impm & ~((2u << jl) - 1)) != 0;
-        u64 end;
-        int w = warp;
-        u32 m = lane == 31 ? 0u : (head_thr[w] & ~((2u << lane) - 1));
-        while (!m && ++w < WORDS) m = head_thr[w];
-        if (m) {                                                    // next head: in thread t2 of this tile
-            const u32 t2 = (u32)w * 32 + (__ffs(m) - 1);
-            end = tbase + (u64)t2 * kGrpItems + first_head_s[t2];
-            impure = impure || bits_any(preimp_thr, (u32)t + 1, t2 + 1);
-        } else {                                                    // the group runs to the end of the tile, maybe beyond
-            impure = impure || bits_any(preimp_thr, (u32)t + 1, (u32)kGrpThreads);
-            if (tile_end < n) {
-                const u32 hm = halo_head_s;
-                if (hm) {                                           // ends within the 32 keys after the tile
-                    const int p = __ffs(hm) - 1;
-                    end = tile_end + p;
-                    impure = impure || (halo_imp_s & ((1u << p) - 1)) != 0;
-                } else {                                            // a long group: search for its end
-                    impure = impure || halo_imp_s != 0;
-                    end = group_end<K>(keys, n, tile_end + 31, last_key, gb);
-                    for (u64 q = tile_end + 32; !impure && q < end; ++q) impure = !KO::eq(keys[q], last_key);
-                }
-            } else {
-                end = n;
-            }
-        }
-        const u64 len = end - (base + jl);
-        last_key = key_unmix(last_key);
-        if (impure) {
-            impgm |= 1u << jl;
-            last_cnt = len;
-        } else {
-            ++pure_groups;
-            const bool self_rc = fold_w && KO::eq(key_rc(last_key, fold_w), last_key);
-            self_groups += self_rc ? 1u : 0u;
-            last_cnt = self_rc ? 2 * len : len;
-            if (last_cnt >= min_count) keepm |= 1u << jl;
-        }
-    }
-    // ONE append per tile and cursor (a warp-level atomic on the single cursor serialised the whole kernel)
-    const u32 my_keep = __popc(keepm), my_imp = __popc(impgm);
-    u32 keep_inc = my_keep, imp_inc = my_imp;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 a = __shfl_up_sync(0xffffffffu, keep_inc, o), b = __shfl_up_sync(0xffffffffu, imp_inc, o);
-        if (lane >= o) { keep_inc += a; imp_inc += b; }
-    }
-    if (lane == 31) { keep_warp[warp] = keep_inc; imp_warp[warp] = imp_inc; }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        pure_groups += __shfl_xor_sync(0xffffffffu, pure_groups, o);
-        self_groups += __shfl_xor_sync(0xffffffffu, self_groups, o);
-    }
-    if (lane == 0) {
-        if (pure_groups) atomicAdd(&stat_s[0], pure_groups);
-        if (self_groups) atomicAdd(&stat_s[1], self_groups);
-    }
-    __syncthreads();
-    if (t == 0) {
-        u32 kt = 0, it = 0;
-#pragma unroll
-        for (int w = 0; w < WORDS; ++w) {
-            const u32 a = keep_warp[w], b = imp_warp[w];
-            keep_warp[w] = kt; imp_warp[w] = it;
-            kt += a; it += b;
-        }
-        keep_base_s = kt ? atomicAdd(&ctr[0], (u64)kt) : 0;
-        imp_base_s = it ? atomicAdd(&ctr[1], (u64)it) : 0;
-        if (stat_s[0]) atomicAdd(&ctr[2], (u64)stat_s[0]);
-        if (stat_s[1]) atomicAdd(&ctr[3], (u64)stat_s[1]);
-    }
-    __syncthreads();
-    u64 ko = keep_base_s + keep_warp[warp] + (keep_inc - my_keep);
-    u64 io = imp_base_s + imp_warp[warp] + (imp_inc - my_imp);
-#pragma unroll
-    for (int j = 0; j < kGrpItems; ++j) {
-        const bool is_last = j == jl;
-        const u64 c = is_last ? last_cnt : cnt[j];
-        if ((keepm >> j) & 1u) {
-            if (ko < out_cap) { out_keys[ko] = is_last ? last_key : k[j]; out_counts[ko] = c; }
-            ++ko;
-        }
-        if ((impgm >> j) & 1u) {
-            if (io < desc_cap) imp_desc[io] = make_ulonglong2(base + j, c);
-            ++io;
-        }
-    }
-}
-
-// one thread per impure group: copies its elements, un-mixed, to `out` (one atomic per warp for the positions)
-template <typename K>
-__global__ void __launch_bounds__(256) copy_groups_kernel(const K* __restrict__ keys, const ulonglong2* __restrict__ desc, u64 n_desc,
-                                                          K* __restrict__ out, u64 out_cap, u64* __restrict__ cursor) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    u64 idx = 0, len = 0;
-    if (i < n_desc) { const ulonglong2 d = desc[i]; idx = d.x; len = d.y; }
-    u64 inc = len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    u64 base = 0;
-    if (lane == 31 && inc) base = atomicAdd(cursor, inc);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    const u64 pos = base + inc - len;
-    for (u64 q = 0; q < len; ++q)
-        if (pos + q < out_cap) out[pos + q] = key_unmix(keys[idx + q]);
-}
-
 __global__ void desc_total_kernel(const ulonglong2* __restrict__ desc, u64 n_desc, u64* __restrict__ total) {
     u64 mine = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_desc; i += (u64)gridDim.x * blockDim.x) mine += desc[i].y;
@@ -970,7 +697,11 @@ void reduce_sorted(Workspace& ws, int key_bytes, const void* sorted, const u64* 
     if (weights && fold_w) throw StatusError{GSB_EINVAL, "internal: strand folding is finished by fold_finalize for merged runs"};
     if (n == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return; }
     if (min_count < 1) min_count = 1;
+#ifdef GSB_PROFILING
     const bool trace = getenv("GSB_TRACE_REDUCE") != nullptr;
+#else
+    const bool trace = false;
+#endif
     struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
     auto lap = [&](const char* what) {
         if (!trace) return;
@@ -1034,79 +765,6 @@ void sort_unmix_inplace(int key_bytes, void* keys, u64 n, int sm_count, cudaStre
     if (key_bytes == 8) unmix_kernel<u64><<<grid, 256, 0, s>>>((u64*)keys, n);
     else unmix_kernel<Key128><<<grid, 256, 0, s>>>((Key128*)keys, n);
     ++*launches;
-}
-
-bool reduce_groups(Workspace& ws, int key_bytes, int key_bits, const void* grouped, u64 n, int group_bits, u64 min_count, int fold_w,
-                   void* out_keys_scratch, ReducedRun& out, u64* m_distinct, u64* n_self_rc) {
-    cudaStream_t s = ws.stream;
-    out.m = 0;
-    *m_distinct = 0; *n_self_rc = 0;
-    if (n == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return true; }
-    if (min_count < 1) min_count = 1;
-    const bool trace = getenv("GSB_TRACE_REDUCE") != nullptr;
-    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
-    auto lap = [&](const char* what, u64 v) {
-        if (!trace) return;
-        cudaStreamSynchronize(s);
-        struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
-        fprintf(stderr, "[reduce_groups] %-22s %8.3f ms (%llu)\n", what, (t.tv_sec - ts0.tv_sec) * 1e3 + (t.tv_nsec - ts0.tv_nsec) * 1e-6, v);
-        ts0 = t;
-    };
-    const u64 out_cap = n / 4 + (1u << 16), imp_cap = n / 8 + (1u << 16), desc_cap = n / 16 + (1u << 16);
-    DevBuf<u64> out_counts(&ws, out_cap), ctr(&ws, 8);
-    DevBuf<ulonglong2> desc(&ws, desc_cap);
-    GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 64, s));
-    DevBuf<u8> imp(&ws, imp_cap * key_bytes);
-    const unsigned tiles = (unsigned)((n + kGrpThreads * kGrpItems - 1) / (kGrpThreads * kGrpItems));
-    if (key_bytes == 8)
-        rle_groups_kernel<u64><<<tiles, kGrpThreads, 0, s>>>((const u64*)grouped, n, group_bits, min_count, fold_w, (u64*)out_keys_scratch, out_counts.p, out_cap,
-                                                              desc.p, desc_cap, ctr.p);
-    else
-        rle_groups_kernel<Key128><<<tiles, kGrpThreads, 0, s>>>((const Key128*)grouped, n, group_bits, min_count, fold_w, (Key128*)out_keys_scratch, out_counts.p, out_cap,
-                                                                 desc.p, desc_cap, ctr.p);
-    ++ws.launches;
-    u64 h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    GSB_CUDA_TRY(cudaMemcpyAsync(h, ctr.p, 64, cudaMemcpyDeviceToHost, s));
-    ws.sync();
-    lap("groups kernel", h[1]);
-    // the low bits group badly / little duplication: the caller sorts by the full key instead
-    if (h[0] > out_cap || h[1] > desc_cap) return false;
-    if (h[1]) {
-        const unsigned blocks = (unsigned)((h[1] + 255) / 256);
-        if (key_bytes == 8) copy_groups_kernel<u64><<<blocks, 256, 0, s>>>((const u64*)grouped, desc.p, h[1], (u64*)imp.p, imp_cap, ctr.p + 5);
-        else copy_groups_kernel<Key128><<<blocks, 256, 0, s>>>((const Key128*)grouped, desc.p, h[1], (Key128*)imp.p, imp_cap, ctr.p + 5);
-        ++ws.launches;
-        GSB_CUDA_TRY(cudaMemcpyAsync(&h[1], ctr.p + 5, 8, cudaMemcpyDeviceToHost, s));
-        ws.sync();
-        if (h[1] > imp_cap) return false;
-    }
-    // h[1] = number of elements on the impure path from here on
-    ReducedRun slow; u64 d2 = 0, self2 = 0;
-    if (h[1]) {
-        // Groups holding several keys (a few per cent of the instances at most, chance collisions of the mixed low
-        // bits): their elements were copied out un-mixed and go through the ordinary full sort + run-length reduce.
-        DevBuf<u8> alt(&ws, h[1] * key_bytes);
-        const int where = sort_keys(ws, key_bytes, key_bits, imp.p, alt.p, nullptr, nullptr, h[1], nullptr, nullptr);
-        reduce_sorted(ws, key_bytes, where ? alt.p : imp.p, nullptr, h[1], min_count, slow, &d2, fold_w, &self2);
-    }
-    lap("impure groups: sort+rle", slow.m);
-    const u64 m = h[0] + slow.m;
-    out.keys.reset(&ws, m * key_bytes);
-    out.counts.reset(&ws, m);
-    if (h[0]) {
-        GSB_CUDA_TRY(cudaMemcpyAsync(out.keys.p, out_keys_scratch, h[0] * key_bytes, cudaMemcpyDeviceToDevice, s));
-        GSB_CUDA_TRY(cudaMemcpyAsync(out.counts.p, out_counts.p, h[0] * 8, cudaMemcpyDeviceToDevice, s));
-    }
-    if (slow.m) {
-        GSB_CUDA_TRY(cudaMemcpyAsync(out.keys.p + h[0] * key_bytes, slow.keys.p, slow.m * key_bytes, cudaMemcpyDeviceToDevice, s));
-        GSB_CUDA_TRY(cudaMemcpyAsync(out.counts.p + h[0], slow.counts.p, slow.m * 8, cudaMemcpyDeviceToDevice, s));
-    }
-    out.m = m;
-    *m_distinct = h[2] + d2;
-    *n_self_rc = h[3] + self2;
-    ws.sync();
-    lap("copies", m);
-    return true;
 }
 
 }  // namespace gsb
