@@ -65,7 +65,19 @@ class Sink(C.Structure):
     _fields_ = [("user", C.c_void_p), ("open", _OPEN_FN), ("pwrite", _PWRITE_FN), ("close", _CLOSE_FN)]
 
 
-EXPORTS = ["gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
+_SIZE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64))
+_PREAD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64)
+
+
+class Source(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("size", _SIZE_FN), ("pread", _PREAD_FN)]
+
+
+class GraphInfo(C.Structure):
+    _fields_ = [("version", C.c_uint64), ("k", C.c_uint64), ("flags", C.c_uint64), ("n_items", C.c_uint64)]
+
+
+EXPORTS = ["gsb_graph_peek", "gsb_graph_load", "gsb_graph_load_pairs", "gsb_graph_finish", "gsb_graph_dump", "gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
            "gsb_emit", "gsb_timer_begin", "gsb_timer_end", "gsb_host_alloc", "gsb_host_free", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root", "gsb_plan_splitters", "gsb_samples_per_rank",
            "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_sort_bench", "gsb_debug_set_tuning", "gsb_debug_set_partition", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
            "gsb_debug_extract"]
@@ -96,6 +108,11 @@ def lib():
         L.gsb_comm_make_id.argtypes = [C.c_void_p]
         L.gsb_comm_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.gsb_gather_to_root.argtypes = [C.c_void_p]
+        L.gsb_graph_peek.argtypes = [C.c_char_p, C.POINTER(Source), C.c_int, C.POINTER(GraphInfo), C.c_char_p, C.c_size_t]
+        L.gsb_graph_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Source)]
+        L.gsb_graph_load_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.gsb_graph_finish.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Counts)]
+        L.gsb_graph_dump.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Sink)]
         L.gsb_debug_copy_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.gsb_debug_copy_counts.restype = C.c_int64
         L.gsb_debug_sort_keys.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
@@ -157,6 +174,57 @@ class MemorySink:
 
     def as_bytes(self):
         return {k: bytes(v) for k, v in self.files.items()}
+
+
+class MemorySource:
+    """{name: bytes} behind the gsb_source callbacks (the StringFileFactory analogue for reading)."""
+
+    def __init__(self, files):
+        self.files = {k: bytes(v) for k, v in files.items()}
+
+        def _size(user, name, out):
+            b = self.files.get(name.decode())
+            if b is None:
+                return 1
+            out[0] = len(b)
+            return 0
+
+        def _pread(user, name, offset, dst, length):
+            b = self.files.get(name.decode())
+            if b is None or offset + length > len(b):
+                return 1
+            C.memmove(dst, b[offset:offset + length], length)
+            return 0
+
+        self._cbs = (_SIZE_FN(_size), _PREAD_FN(_pread))
+        self.c = Source(None, *self._cbs)
+
+
+class DirectorySource:
+    """Real files (names are paths)."""
+
+    def __init__(self):
+        def _size(user, name, out):
+            try:
+                out[0] = os.path.getsize(name.decode())
+                return 0
+            except OSError:
+                return 1
+
+        def _pread(user, name, offset, dst, length):
+            try:
+                with open(name.decode(), "rb") as f:
+                    f.seek(offset)
+                    b = f.read(length)
+                if len(b) != length:
+                    return 1
+                C.memmove(dst, b, length)
+                return 0
+            except OSError:
+                return 1
+
+        self._cbs = (_SIZE_FN(_size), _PREAD_FN(_pread))
+        self.c = Source(None, *self._cbs)
 
 
 class DirectorySink:
@@ -266,6 +334,25 @@ class Builder:
     def reset(self):
         self._check(lib().gsb_reset(self.h))
 
+    # ---- existing file sets: trim / merge / dump / restore ----
+    def load(self, prefix, source):
+        """Decode the file set `prefix` on the device and merge it into the run (counts of equal keys are summed)."""
+        self._check(lib().gsb_graph_load(self.h, prefix.encode(), C.byref(source.c)))
+
+    def load_pairs(self, lo, hi, counts):
+        lo = np.ascontiguousarray(lo, np.uint64)
+        hi = None if hi is None else np.ascontiguousarray(hi, np.uint64)
+        counts = np.ascontiguousarray(counts, np.uint64)
+        self._check(lib().gsb_graph_load_pairs(self.h, _ptr(lo), _ptr(hi), _ptr(counts), lo.size))
+
+    def finish_loaded(self, cutoff=0, m_est=0):
+        c = Counts()
+        self._check(lib().gsb_graph_finish(self.h, cutoff, m_est, C.byref(c)))
+        return c
+
+    def dump(self, name, sink):
+        self._check(lib().gsb_graph_dump(self.h, name.encode(), C.byref(sink.c)))
+
     def attach(self, nccl_id, n_ranks, rank):
         self._check(lib().gsb_comm_attach(self.h, nccl_id, n_ranks, rank))
 
@@ -309,6 +396,64 @@ def make_nccl_id():
     if rc != 0:
         raise GossamerError(rc, lib().gsb_last_error(None).decode())
     return buf.raw
+
+
+def graph_peek(prefix, source, kind=GRAPH):
+    info, err = GraphInfo(), C.create_string_buffer(512)
+    rc = lib().gsb_graph_peek(prefix.encode(), C.byref(source.c), kind, C.byref(info), err, 512)
+    if rc != 0:
+        raise GossamerError(rc, err.value.decode())
+    return info
+
+
+def trim_graph(files, src_prefix, dst_prefix, cutoff, device=0):
+    """`goss trim-graph -C cutoff` on a file set held in memory (src/GossCmdTrimGraph.cc:27-127).  Returns {name: bytes}."""
+    source = MemorySource(files)
+    info = graph_peek(src_prefix, source)
+    b = Builder(GRAPH, int(info.k), device=device)
+    try:
+        b.load(src_prefix, source)
+        b.finish_loaded(cutoff=cutoff, m_est=0)            # the reference passes the exact kept count
+        sink = MemorySink()
+        b.emit(dst_prefix, sink)
+        return sink.as_bytes()
+    finally:
+        b.close()
+
+
+def merge_file_sets(files, prefixes, dst_prefix, kind=GRAPH, max_merge=8, device=0):
+    """`goss merge-graphs` / `merge-kmer-sets` (src/GossCmdMerge.tcc:148-296), including its grouping into temporary
+    file sets when there are more than max_merge inputs (the size estimate of the last merge depends on it)."""
+    files = dict(files)
+    todo = [(p, False) for p in prefixes]
+    tmp_n = 0
+
+    def merge(ins, out):
+        source = MemorySource(files)
+        infos = [graph_peek(p, source, kind) for p in ins]
+        for p, i in zip(ins, infos):
+            if i.k != infos[0].k:
+                raise GossamerError(-1, "all graphs involved in a merge must have the same kmer-size.\n"
+                                        f"{ins[0]} has k={infos[0].k}.\n{p} has k={i.k}.\n")
+        tot = sum(int(i.n_items) for i in infos)
+        b = Builder(kind, int(infos[0].k), device=device)
+        try:
+            for p in ins:
+                b.load(p, source)
+            b.finish_loaded(cutoff=0, m_est=tot)
+            sink = MemorySink()
+            b.emit(out, sink)
+            return sink.as_bytes()
+        finally:
+            b.close()
+
+    while len(todo) > max_merge:
+        group, todo = todo[:max_merge], todo[max_merge:]
+        out = f"__tmp{tmp_n}"
+        tmp_n += 1
+        files.update(merge([p for p, _ in group], out))
+        todo.append((out, True))
+    return merge([p for p, _ in todo], dst_prefix)
 
 
 def build_graph(inputs, k, min_count=1, prefix="graph", sink=None, device=0):

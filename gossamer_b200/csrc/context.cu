@@ -181,6 +181,8 @@ struct gsb_ctx {
     bool dist_ready = false;       // ... is valid: gsb_emit writes this rank's byte ranges of every file
     bool acc_unsorted = false;     // acc came out of reduce_groups: folded, filtered, final counts, arbitrary order
     bool gathered = false;         // gsb_gather_to_root was called: rank 0 holds and emits everything
+    u64 m_est = 0;                 // size estimate the builders are parameterised with (0 = the number of items emitted)
+    u64 loaded_items = 0;          // gsb_graph_load: sum of the sizes of the file sets loaded so far
 
     void log(int sev, const std::string& m) { if (cfg.log) cfg.log(cfg.log_user, sev, m.c_str()); }
 };
@@ -236,22 +238,20 @@ void reset_batch(gsb_ctx* c) {
     c->n_keys = 0;
 }
 
-// merge two reduced runs: concatenate, sort by key carrying the counts, sum equal keys
+// merge two sorted reduced runs (merge path, fold.cu), then sum the counts of equal keys -- what AsyncMerge / PairMerge
+// do one item at a time (src/AsyncMerge.tcc:267-324, src/GossCmdMerge.tcc:84-145).  Linear in the sizes of the runs.
 void merge_runs(gsb_ctx* c, ReducedRun& into, ReducedRun& other) {
     Workspace& ws = c->ws;
-    cudaStream_t s = ws.stream;
     const u64 n = into.m + other.m;
     const int kb = c->key_bytes;
-    DevBuf<u8> ka(&ws, n * kb), kbuf(&ws, n * kb);
-    DevBuf<u64> va(&ws, n), vb(&ws, n);
-    GSB_CUDA_TRY(cudaMemcpyAsync(ka.p, into.keys.p, into.m * kb, cudaMemcpyDeviceToDevice, s));
-    GSB_CUDA_TRY(cudaMemcpyAsync(ka.p + into.m * kb, other.keys.p, other.m * kb, cudaMemcpyDeviceToDevice, s));
-    GSB_CUDA_TRY(cudaMemcpyAsync(va.p, into.counts.p, into.m * 8, cudaMemcpyDeviceToDevice, s));
-    GSB_CUDA_TRY(cudaMemcpyAsync(va.p + into.m, other.counts.p, other.m * 8, cudaMemcpyDeviceToDevice, s));
+    if (other.m == 0) return;
+    if (into.m == 0) { into = std::move(other); other.m = 0; return; }
+    DevBuf<u8> mk(&ws, n * kb);
+    DevBuf<u64> mc(&ws, n);
+    merge_disjoint_runs(ws, kb, into.keys.p, into.counts.p, into.m, other.keys.p, other.counts.p, other.m, mk.p, mc.p);
     into.keys.free(); into.counts.free(); other.keys.free(); other.counts.free();
-    int where = sort_keys(ws, kb, c->key_bits, ka.p, kbuf.p, va.p, vb.p, n, nullptr, nullptr);
     ReducedRun merged; u64 distinct = 0;
-    reduce_sorted(ws, kb, where ? kbuf.p : ka.p, where ? vb.p : va.p, n, 1, merged, &distinct);
+    reduce_sorted(ws, kb, mk.p, mc.p, n, 1, merged, &distinct);
     into = std::move(merged);
     other.m = 0;
 }
@@ -457,13 +457,14 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
 void write_graph_files(gsb_ctx* c, Emitter& em, const std::string& prefix) {
     const u64 k = (u64)c->cfg.k;
     const u64 m = c->acc.m;
+    const u64 m_est = c->m_est ? c->m_est : m;           // pNumEdges of Graph::Builder (src/Graph.cc:145-158)
     // Graph::Builder ctor writes the header first (src/Graph.cc:159-166)
     u64 header[3] = {2011101014ull, k, 0};
     em.put_host(prefix + ".header", header, sizeof(header));
     const unsigned rho2 = 2 * (unsigned)(k + 1);
     U128 universe = rho2 < 64 ? U128{1ull << rho2, 0} : U128{0, 1ull << (rho2 - 64)};
-    emit_sparse_array(em, c->key_bytes, c->acc.keys.p, m, universe, m, universe, prefix + "-edges");
-    emit_counts(em, c->acc.counts.p, m, m, prefix + "-counts");
+    emit_sparse_array(em, c->key_bytes, c->acc.keys.p, m, universe, m_est, universe, prefix + "-edges");
+    emit_counts(em, c->acc.counts.p, m, m_est, prefix + "-counts");
     emit_count_histogram(em, c->acc.counts.p, m, prefix + "-counts-hist.txt");
 }
 
@@ -472,7 +473,7 @@ void write_kmer_set_files(gsb_ctx* c, Emitter& em, const std::string& prefix) {
     const u64 m = c->acc.m;
     const unsigned bits = 2 * (unsigned)k;
     U128 universe = bits < 64 ? U128{1ull << bits, 0} : U128{0, 1ull << (bits - 64)};
-    emit_sparse_array(em, c->key_bytes, c->acc.keys.p, m, universe, m, universe, prefix + ".kmers");
+    emit_sparse_array(em, c->key_bytes, c->acc.keys.p, m, universe, c->m_est ? c->m_est : m, universe, prefix + ".kmers");
     u64 header[3] = {2011101701ull, k, m};             // KmerSet::Builder::end, src/KmerSet.hh:76-83
     em.put_host(prefix + ".header", header, sizeof(header));
 }
@@ -916,6 +917,157 @@ int gsb_emit(gsb_ctx* c, const char* prefix, const gsb_sink* sink) {
     });
 }
 
+// ---- existing file sets ---------------------------------------------------------------------------------------------
+static void read_host_file(const gsb_source* src, const std::string& name, std::vector<u8>& out) {
+    uint64_t size = 0;
+    if (src->size(src->user, name.c_str(), &size) != 0) throw StatusError{GSB_EIO, "cannot open " + name};
+    out.resize(size);
+    if (size && src->pread(src->user, name.c_str(), 0, out.data(), size) != 0) throw StatusError{GSB_EIO, "read failed for " + name};
+}
+
+static void peek_graph(const std::string& prefix, const gsb_source* src, int kind, gsb_graph_info* out) {
+    std::vector<u8> h, sa;
+    read_host_file(src, prefix + ".header", h);
+    if (h.size() < 24) throw StatusError{GSB_EIO, prefix + ".header is truncated"};
+    u64 w[3];
+    memcpy(w, h.data(), 24);
+    const u64 want = kind == GSB_KIND_GRAPH ? 2011101014ull : 2011101701ull;
+    if (w[0] != want) throw StatusError{GSB_EINVAL, prefix + ": version mismatch " + std::to_string(w[0]) + " vs " + std::to_string(want)};
+    read_host_file(src, prefix + (kind == GSB_KIND_GRAPH ? "-edges.header" : ".kmers.header"), sa);
+    if (sa.size() < 64) throw StatusError{GSB_EIO, prefix + ": SparseArray header is truncated"};
+    u64 count = 0;
+    memcpy(&count, sa.data() + 56, 8);
+    out->version = w[0]; out->k = w[1]; out->flags = w[2]; out->n_items = count;
+}
+
+int gsb_graph_peek(const char* prefix, const gsb_source* src, int kind, gsb_graph_info* out, char* err, size_t errcap) {
+    if (!prefix || !src || !src->size || !src->pread || !out) return GSB_EINVAL;
+    int rc = guarded(nullptr, [&] { peek_graph(prefix, src, kind, out); });
+    if (rc != GSB_OK && err && errcap) { strncpy(err, g_create_error.c_str(), errcap - 1); err[errcap - 1] = 0; }
+    return rc;
+}
+
+static void absorb_run(gsb_ctx* c, ReducedRun& run) {
+    if (c->have_acc) {
+        c->timer.start();
+        merge_runs(c, c->acc, run);
+        c->timer.stop(c->stats.ms_merge);
+    } else {
+        c->acc = std::move(run);
+        c->have_acc = true;
+    }
+}
+
+int gsb_graph_load(gsb_ctx* c, const char* prefix, const gsb_source* src) {
+    if (!c || !prefix || !src || !src->size || !src->pread) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (c->counted) throw StatusError{GSB_EINVAL, "gsb_graph_load after the run was finished (call gsb_reset first)"};
+        if (c->comm) throw StatusError{GSB_EINVAL, "gsb_graph_load is a single-GPU operation"};
+        if (c->n_keys) throw StatusError{GSB_EINVAL, "gsb_graph_load cannot be mixed with gsb_push_block in one build"};
+        gsb_graph_info info;
+        peek_graph(prefix, src, c->cfg.kind, &info);
+        if ((int)info.k != c->cfg.k) throw StatusError{GSB_EINVAL, std::string(prefix) + " has k=" + std::to_string(info.k) + ", this context was created for k=" + std::to_string(c->cfg.k)};
+        if (c->cfg.kind == GSB_KIND_GRAPH && (info.flags & 1)) throw StatusError{GSB_EINVAL, "Asymmetric graphs not yet handled"};
+        ReducedRun run;
+        c->timer.start();
+        const std::string p(prefix);
+        read_sparse_array(c->ws, src, p + (c->cfg.kind == GSB_KIND_GRAPH ? "-edges" : ".kmers"), c->key_bytes, c->pinned, c->pinned_bytes, run.keys, &run.m);
+        if (c->cfg.kind == GSB_KIND_GRAPH) read_counts(c->ws, src, p + "-counts", run.m, c->pinned, c->pinned_bytes, run.counts);
+        else { run.counts.reset(&c->ws, run.m); fill_ones(c->ws, run.counts.p, run.m); }
+        c->timer.stop(c->stats.ms_scan);
+        c->loaded_items += run.m;
+        absorb_run(c, run);
+    });
+}
+
+int gsb_graph_load_pairs(gsb_ctx* c, const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* counts, uint64_t m) {
+    if (!c || (m && (!key_lo || !counts))) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (c->counted) throw StatusError{GSB_EINVAL, "gsb_graph_load_pairs after the run was finished (call gsb_reset first)"};
+        ReducedRun raw, run;
+        Workspace& ws = c->ws;
+        const int kb = c->key_bytes;
+        raw.keys.reset(&ws, m * kb);
+        raw.counts.reset(&ws, m);
+        if (m) {
+            if (kb == 8) {
+                GSB_CUDA_TRY(cudaMemcpyAsync(raw.keys.p, key_lo, m * 8, cudaMemcpyHostToDevice, ws.stream));
+            } else {
+                std::vector<u64> inter(2 * m);
+                for (u64 i = 0; i < m; ++i) { inter[2 * i] = key_lo[i]; inter[2 * i + 1] = key_hi ? key_hi[i] : 0; }
+                GSB_CUDA_TRY(cudaMemcpyAsync(raw.keys.p, inter.data(), m * 16, cudaMemcpyHostToDevice, ws.stream));
+                ws.sync();
+            }
+            GSB_CUDA_TRY(cudaMemcpyAsync(raw.counts.p, counts, m * 8, cudaMemcpyHostToDevice, ws.stream));
+            ws.sync();
+        }
+        raw.m = m;
+        // any order, possibly repeated keys: sort by key, sum equal keys
+        DevBuf<u8> kalt(&ws, m * kb);
+        DevBuf<u64> calt(&ws, m);
+        const int where = sort_keys(ws, kb, c->key_bits, raw.keys.p, kalt.p, raw.counts.p, calt.p, m, nullptr, nullptr);
+        u64 distinct = 0;
+        reduce_sorted(ws, kb, where ? kalt.p : raw.keys.p, where ? calt.p : raw.counts.p, m, 1, run, &distinct);
+        c->loaded_items += m;
+        absorb_run(c, run);
+    });
+}
+
+int gsb_graph_finish(gsb_ctx* c, uint64_t cutoff, uint64_t m_est, gsb_counts* out) {
+    if (!c) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (c->counted) throw StatusError{GSB_EINVAL, "the run is finished already"};
+        if (c->n_keys) throw StatusError{GSB_EINVAL, "gsb_graph_finish cannot be mixed with gsb_push_block in one build"};
+        if (!c->have_acc) { c->acc.keys.reset(&c->ws, 0); c->acc.counts.reset(&c->ws, 0); c->acc.m = 0; c->have_acc = true; }
+        c->counts.n_distinct = c->acc.m;
+        if (cutoff > 0 && c->acc.m) {
+            c->timer.start();
+            DevBuf<u8> fk(&c->ws, c->acc.m * c->key_bytes);
+            DevBuf<u64> fc(&c->ws, c->acc.m), total(&c->ws, 1);
+            DevBuf<u8> lb(&c->ws, rle_lookback_bytes(c->acc.m));
+            sort_filter(c->key_bytes, c->acc.keys.p, c->acc.counts.p, nullptr, c->acc.m, cutoff + 1, fk.p, fc.p, lb.p, total.p, c->ws.stream, &c->ws.launches);
+            u64 kept = 0;
+            GSB_CUDA_TRY(cudaMemcpyAsync(&kept, total.p, 8, cudaMemcpyDeviceToHost, c->ws.stream));
+            c->ws.sync();
+            c->acc.keys = std::move(fk); c->acc.counts = std::move(fc); c->acc.m = kept;
+            c->timer.stop(c->stats.ms_reduce);
+        }
+        c->counts.n_kept = c->acc.m;
+        c->counts.n_instances = c->loaded_items;
+        c->m_est = m_est;
+        c->acc_unsorted = false;
+        c->counted = true;
+        if (out) *out = c->counts;
+    });
+}
+
+int gsb_graph_dump(gsb_ctx* c, const char* name, const gsb_sink* sink) {
+    if (!c || !name || !sink || !sink->open || !sink->pwrite || !sink->close) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_graph_dump before the run was finished"};
+        if (c->cfg.kind != GSB_KIND_GRAPH) throw StatusError{GSB_EINVAL, "dump-graph wants a graph"};
+        Emitter em;
+        em.ws = &c->ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
+        DevBuf<u8> text;
+        u64 bytes = 0;
+        dump_text(c->ws, c->key_bytes, c->acc.keys.p, c->acc.counts.p, c->acc.m, c->cfg.k + 1, text, &bytes);
+        // '#' version, then K <tab> count <tab> flags (src/GossCmdDumpGraph.cc:49-50)
+        const std::string head = "#2011101014\n" + std::to_string(c->cfg.k) + "\t" + std::to_string(c->acc.m) + "\t0\n";
+        void* h = nullptr;
+        const std::string nm(name);
+        if (sink->open(sink->user, name, head.size() + bytes, &h) != 0) throw StatusError{GSB_EIO, "open failed for " + nm};
+        if (sink->pwrite(sink->user, h, 0, head.data(), head.size()) != 0) throw StatusError{GSB_EIO, "pwrite failed for " + nm};
+        for (u64 off = 0; off < bytes; off += c->pinned_bytes) {
+            const u64 chunk = std::min<u64>(c->pinned_bytes, bytes - off);
+            GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, text.p + off, chunk, cudaMemcpyDeviceToHost, c->ws.stream));
+            c->ws.sync();
+            if (sink->pwrite(sink->user, h, head.size() + off, c->pinned, chunk) != 0) throw StatusError{GSB_EIO, "pwrite failed for " + nm};
+        }
+        if (sink->close(sink->user, h) != 0) throw StatusError{GSB_EIO, "close failed for " + nm};
+        c->stats.bytes_out += head.size() + bytes;
+    });
+}
+
 int gsb_timer_begin(gsb_ctx* c) {
     if (!c) return GSB_EINVAL;
     return guarded(c, [&] { GSB_CUDA_TRY(cudaEventRecord(c->user_e0, c->ws.stream)); });
@@ -962,6 +1114,7 @@ int gsb_reset(gsb_ctx* c) {
         c->have_acc = false; c->counted = false;
         c->dist_ready = false; c->gathered = false;
         c->self_rc_windows = 0; c->any_self_rc = true;
+        c->m_est = 0; c->loaded_items = 0;
         c->exchanged_instances = false; c->batch_src = nullptr; c->acc_unsorted = false;
         if (c->pending.valid) { GSB_CUDA_TRY(cudaStreamSynchronize(c->copy_stream)); c->pending.valid = false; }
         for (int f = 0; f < 3; ++f) { c->file_open[f] = false; c->line_base[f] = 0; }

@@ -209,6 +209,13 @@ void emit_counts(Emitter& em, const u64* counts, u64 m, u64 m_est, const std::st
 // "count\tfrequency\n" lines in ascending count order (src/Graph.cc:127-133)
 void emit_count_histogram(Emitter& em, const u64* counts, u64 m, const std::string& name);
 
+// ---- reader.cu -------------------------------------------------------------------------------
+void read_sparse_array(Workspace& ws, const gsb_source* src, const std::string& base, int key_bytes, u8* pinned, size_t pinned_bytes,
+                       DevBuf<u8>& keys_out, u64* m_out);
+void read_counts(Workspace& ws, const gsb_source* src, const std::string& base, u64 m, u8* pinned, size_t pinned_bytes, DevBuf<u64>& counts_out);
+void fill_ones(Workspace& ws, u64* counts, u64 m);
+void dump_text(Workspace& ws, int key_bytes, const void* keys, const u64* counts, u64 m, int w, DevBuf<u8>& text_out, u64* bytes_out);
+
 struct ParseFailure { int code; u64 line; };
 struct StatusError { int status; std::string message; };
 

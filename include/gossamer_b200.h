@@ -142,6 +142,37 @@ int gsb_finish_counting(gsb_ctx* ctx, gsb_counts* out);
 int gsb_emit(gsb_ctx* ctx, const char* prefix, const gsb_sink* sink);
 /* sink == NULL builds every file in device memory and drops it (device-only timing; bytes_out still counts). */
 
+/* ---- existing file sets: trim-graph, merge-graphs / merge-kmer-sets, dump-graph, restore-graph ------------------------
+ * Input seam: the FileFactory::in analogue (src/FileFactory.hh:80-164).  size() returns 0 and the size if the file exists. */
+typedef struct gsb_source {
+    void* user;
+    int (*size)(void* user, const char* name, uint64_t* size_out);
+    int (*pread)(void* user, const char* name, uint64_t offset, void* dst, uint64_t len);
+} gsb_source;
+
+typedef struct gsb_graph_info {
+    uint64_t version;   /* 2011101014 (Graph, src/Graph.hh:73-83) or 2011101701 (KmerSet, src/KmerSet.hh:32-43) */
+    uint64_t k;
+    uint64_t flags;     /* Graph: bit 0 = asymmetric; KmerSet: the stored count */
+    uint64_t n_items;   /* edges / k-mers in the set (the SparseArray header's count) */
+} gsb_graph_info;
+
+/* Host only: what `prefix` holds (kind: gsb_kind).  Replaces Graph::LazyIterator's header checks (src/Graph.cc:195-216). */
+int gsb_graph_peek(const char* prefix, const gsb_source* src, int kind, gsb_graph_info* out, char* err, size_t errcap);
+/* Decodes the file set `prefix` (Elias-Fano edges / k-mers, VariableByteArray counts) into a sorted (key, count) run on the
+ * device and merges it into the context's run, summing the counts of equal keys -- the read side of
+ * Graph::LazyIterator / CursorMerge / PairMerge (src/GossCmdMerge.tcc:29-145).  The context's k must match the file's. */
+int gsb_graph_load(gsb_ctx* ctx, const char* prefix, const gsb_source* src);
+/* Same, from host arrays (restore-graph's parsed lines, src/GossCmdRestoreGraph.cc:70-128); any order. */
+int gsb_graph_load_pairs(gsb_ctx* ctx, const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* counts, uint64_t m);
+/* Ends loading: keeps the items with count > cutoff (trim-graph's predicate, src/GossCmdTrimGraph.cc:119; 0 keeps all) and
+ * fixes the size estimate the builders are parameterised with: m_est = 0 means "the number kept" (trim-graph passes the
+ * exact n), merge passes the sum of the inputs' sizes (src/GossCmdMerge.tcc:224-263,296), restore the header's n.
+ * gsb_emit then writes the file set. */
+int gsb_graph_finish(gsb_ctx* ctx, uint64_t cutoff, uint64_t m_est, gsb_counts* out);
+/* dump-graph's text (src/GossCmdDumpGraph.cc:31-60) of the finished run, formatted on the device, as one file `name`. */
+int gsb_graph_dump(gsb_ctx* ctx, const char* name, const gsb_sink* sink);
+
 /* Device-side stopwatch on the library's stream (CUDA events): begin records, end records +
  * synchronises and returns the elapsed milliseconds between the two. */
 int gsb_timer_begin(gsb_ctx* ctx);

@@ -13,6 +13,10 @@
 #include "GossCmdBuildGraph.hh"
 #include "GossCmdBuildKmerSet.hh"
 #include "GossCmdTrimGraph.hh"
+#include "GossCmdMergeGraphs.hh"
+#include "GossCmdMergeKmerSets.hh"
+#include "GossCmdDumpGraph.hh"
+#include "GossCmdRestoreGraph.hh"
 #include "Graph.hh"
 #include "KmerSet.hh"
 #include "Logger.hh"
@@ -175,6 +179,51 @@ int ref_trim_graph(void* sv, const char* in, const char* out, uint64_t c, char* 
         GossCmdTrimGraph cmd(in, out, c, false, false, boost::optional<uint64_t>());
         boost::program_options::variables_map opts;
         GossCmdContext cxt(s->fac, log, "trim-graph", opts);
+        cmd(cxt);
+        return 0;
+    REF_CATCH
+}
+
+// merge-graphs / merge-kmer-sets (src/GossCmdMerge.tcc:148-296)
+int ref_merge_graphs(void* sv, const char** ins, int n_ins, uint64_t max_merge, const char* out, int kmer_sets, char* err, int errcap) {
+    REF_TRY
+        Store* s = (Store*)sv;
+        Logger log("log.txt", s->fac);
+        std::vector<std::string> in(ins, ins + n_ins);
+        boost::program_options::variables_map opts;
+        if (kmer_sets) {
+            GossCmdMergeKmerSets cmd(in, max_merge, out);
+            GossCmdContext cxt(s->fac, log, "merge-kmer-sets", opts);
+            cmd(cxt);
+        } else {
+            GossCmdMergeGraphs cmd(in, max_merge, out);
+            GossCmdContext cxt(s->fac, log, "merge-graphs", opts);
+            cmd(cxt);
+        }
+        return 0;
+    REF_CATCH
+}
+
+// dump-graph (src/GossCmdDumpGraph.cc:31-60) and restore-graph (src/GossCmdRestoreGraph.cc:70-128)
+int ref_dump_graph(void* sv, const char* in, const char* out_file, char* err, int errcap) {
+    REF_TRY
+        Store* s = (Store*)sv;
+        Logger log("log.txt", s->fac);
+        GossCmdDumpGraph cmd(in, out_file);
+        boost::program_options::variables_map opts;
+        GossCmdContext cxt(s->fac, log, "dump-graph", opts);
+        cmd(cxt);
+        return 0;
+    REF_CATCH
+}
+
+int ref_restore_graph(void* sv, const char* in_file, const char* out, char* err, int errcap) {
+    REF_TRY
+        Store* s = (Store*)sv;
+        Logger log("log.txt", s->fac);
+        GossCmdRestoreGraph cmd(in_file, out);
+        boost::program_options::variables_map opts;
+        GossCmdContext cxt(s->fac, log, "restore-graph", opts);
         cmd(cxt);
         return 0;
     REF_CATCH

@@ -177,3 +177,24 @@ def read_graph(files, base="graph"):
     lo, hi, cn = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint32)
     _check(lib().ref_read_graph(st.h, base.encode(), _p(lo), _p(hi), _p(cn), C.c_uint64(n), C.byref(k), err, 512), err)
     return k.value, lo, hi, cn
+
+
+def merge_graphs(store, ins, out, max_merge=8, kmer_sets=False):
+    """The reference's own merge-graphs / merge-kmer-sets on file sets already in `store`."""
+    err = C.create_string_buffer(1024)
+    arr, n = _names(list(ins))
+    _check(lib().ref_merge_graphs(store.h, arr, n, C.c_uint64(max_merge), out.encode(), 1 if kmer_sets else 0, err, 1024), err)
+    return store.files(kmer_set_names(out) if kmer_sets else graph_names(out))
+
+
+def dump_graph(store, src, out_file="dump.txt"):
+    err = C.create_string_buffer(512)
+    _check(lib().ref_dump_graph(store.h, src.encode(), out_file.encode(), err, 512), err)
+    return store.files([out_file])[out_file]
+
+
+def restore_graph(store, text, out, in_file="restore.txt"):
+    err = C.create_string_buffer(512)
+    store.put_all({in_file: bytes(text)})
+    _check(lib().ref_restore_graph(store.h, in_file.encode(), out.encode(), err, 512), err)
+    return store.files(graph_names(out))
