@@ -1,6 +1,9 @@
 // file_io.cc -- see file_io.hh
 #include "file_io.hh"
 
+#include <dirent.h>
+#include <sys/stat.h>
+
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -119,7 +122,7 @@ bool BlockReader::next(const uint8_t*& data, size_t& size, bool& last) {
     }
 }
 
-OutputFiles::OutputFiles() {
+OutputFiles::OutputFiles(bool shared) : shared_(shared) {
     sink_.user = this;
     sink_.open = &OutputFiles::s_open;
     sink_.pwrite = &OutputFiles::s_pwrite;
@@ -128,9 +131,9 @@ OutputFiles::OutputFiles() {
 
 int OutputFiles::s_open(void* user, const char* name, uint64_t size_hint, void** handle) {
     OutputFiles* self = (OutputFiles*)user;
-    int fd = ::open(name, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    int fd = ::open(name, O_WRONLY | O_CREAT | (self->shared_ ? 0 : O_TRUNC), 0644);
     if (fd < 0) return -1;
-    if (size_hint) { if (ftruncate(fd, (off_t)size_hint) != 0) { /* best effort */ } }
+    if (size_hint || self->shared_) { if (ftruncate(fd, (off_t)size_hint) != 0) { /* best effort */ } }
     self->names_.push_back(name);
     *handle = (void*)(intptr_t)(fd + 1);
     return 0;
@@ -152,6 +155,48 @@ int OutputFiles::s_pwrite(void* user, void* handle, uint64_t offset, const void*
 int OutputFiles::s_close(void*, void* handle) {
     int fd = (int)(intptr_t)handle - 1;
     return ::close(fd) == 0 ? 0 : -1;
+}
+
+InputFiles::InputFiles() {
+    src_.user = this;
+    src_.size = &InputFiles::s_size;
+    src_.pread = &InputFiles::s_pread;
+}
+
+int InputFiles::s_size(void*, const char* name, uint64_t* size_out) {
+    struct stat st;
+    if (::stat(name, &st) != 0 || !S_ISREG(st.st_mode)) return -1;
+    *size_out = (uint64_t)st.st_size;
+    return 0;
+}
+
+int InputFiles::s_pread(void*, const char* name, uint64_t offset, void* dst, uint64_t len) {
+    int fd = ::open(name, O_RDONLY);
+    if (fd < 0) return -1;
+    uint64_t done = 0;
+    while (done < len) {
+        ssize_t r = ::pread(fd, (char*)dst + done, len - done, (off_t)(offset + done));
+        if (r < 0) { if (errno == EINTR) continue; ::close(fd); return -1; }
+        if (r == 0) { ::close(fd); return -1; }
+        done += (uint64_t)r;
+    }
+    ::close(fd);
+    return 0;
+}
+
+void remove_file_set(const std::string& prefix) {
+    const size_t slash = prefix.rfind('/');
+    const std::string dir = slash == std::string::npos ? "." : prefix.substr(0, slash == 0 ? 1 : slash);
+    const std::string stem = slash == std::string::npos ? prefix : prefix.substr(slash + 1);
+    DIR* d = ::opendir(dir.c_str());
+    if (!d) return;
+    std::vector<std::string> victims;
+    while (struct dirent* e = ::readdir(d)) {
+        const std::string n = e->d_name;
+        if (n.size() > stem.size() && n.compare(0, stem.size(), stem) == 0 && (n[stem.size()] == '.' || n[stem.size()] == '-')) victims.push_back(dir + "/" + n);
+    }
+    ::closedir(d);
+    for (const std::string& v : victims) ::unlink(v.c_str());
 }
 
 void check_output_prefix(const std::string& prefix) {

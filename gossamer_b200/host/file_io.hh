@@ -58,7 +58,9 @@ private:
 // Output files under a prefix, written with pwrite (PhysicalFileFactory::out).
 class OutputFiles {
 public:
-    OutputFiles();
+    // shared = true: several worker processes write their own pieces of the same files (multi-GPU emission): the files
+    // are created without truncation and sized with ftruncate; the launcher removes stale files beforehand
+    explicit OutputFiles(bool shared = false);
     gsb_sink* sink() { return &sink_; }
     uint64_t bytes_written() const { return bytes_; }
     std::vector<std::string> names() const { return names_; }
@@ -69,7 +71,23 @@ private:
     gsb_sink sink_;
     uint64_t bytes_ = 0;
     std::vector<std::string> names_;
+    bool shared_ = false;
 };
+
+// Existing files behind the gsb_source callbacks (PhysicalFileFactory::in for the readers of a file set).
+class InputFiles {
+public:
+    InputFiles();
+    gsb_source* source() { return &src_; }
+private:
+    static int s_size(void* user, const char* name, uint64_t* size_out);
+    static int s_pread(void* user, const char* name, uint64_t offset, void* dst, uint64_t len);
+    gsb_source src_;
+};
+
+// removes every file `<prefix>.*` / `<prefix>-*` in the prefix's directory (Graph::remove, src/Graph.cc:380-387, widened to
+// whatever an earlier run left under the prefix)
+void remove_file_set(const std::string& prefix);
 
 // "-O prefix" check: create and remove <prefix>.test (src/GossOptionChecker.hh:80-105)
 void check_output_prefix(const std::string& prefix);

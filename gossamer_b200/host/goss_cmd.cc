@@ -7,6 +7,10 @@
 #include <ctime>
 #include <sstream>
 
+#include <signal.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
 namespace goss {
 
 void Logger::operator()(Severity s, const std::string& msg) {
@@ -33,7 +37,160 @@ struct Ctx {
     throw Error{m + "\n"};
 }
 
+// ---- several GPUs: one worker PROCESS per device -----------------------------------------------------------------------------
+// The seam is the body of GossCmdBuildGraph::operator() (src/GossCmdBuildGraph.cc:270-426); the reference has no distributed
+// mode.  The launcher forks one worker per device before anything touches CUDA; worker 0 makes the NCCL id and the launcher
+// relays it over pipes; every worker attaches, pushes its share of the input (FASTQ / line files: every n-th block, cut at
+// record boundaries; FASTA files: whole files, because a record may straddle blocks), and after the collective finish /
+// emit writes ITS byte ranges of every output file with pwrite into the shared files.
+bool read_all(int fd, void* dst, size_t n) {
+    size_t done = 0;
+    while (done < n) {
+        ssize_t r = ::read(fd, (char*)dst + done, n - done);
+        if (r < 0) { if (errno == EINTR) continue; return false; }
+        if (r == 0) return false;
+        done += (size_t)r;
+    }
+    return true;
+}
+bool write_all(int fd, const void* src, size_t n) {
+    size_t done = 0;
+    while (done < n) {
+        ssize_t w = ::write(fd, (const char*)src + done, n - done);
+        if (w < 0) { if (errno == EINTR) continue; return false; }
+        done += (size_t)w;
+    }
+    return true;
+}
+
+int build_worker(const BuildOptions& opt, const GossCmdContext& cxt, int kind, int rank, int n, int id_in_fd, int id_out_fd) {
+    Logger& log = cxt.log;
+    try {
+        auto t0 = std::chrono::steady_clock::now();
+        unsigned char id[GSB_NCCL_ID_BYTES];
+        if (rank == 0) {
+            if (gsb_comm_make_id(id) != GSB_OK) throw Error{std::string(gsb_last_error(nullptr)) + "\n"};
+            if (!write_all(id_out_fd, id, sizeof(id))) throw Error{"cannot hand the communicator id to the launcher\n"};
+        } else if (!read_all(id_in_fd, id, sizeof(id))) {
+            throw Error{"no communicator id from the launcher\n"};
+        }
+        gsb_config cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.abi_version = GSB_ABI_VERSION;
+        cfg.kind = kind;
+        cfg.k = (int32_t)opt.K;
+        cfg.device = opt.devices[rank];
+        cfg.min_count = kind == GSB_KIND_GRAPH ? opt.min_count : 1;
+        cfg.log = &library_log;
+        cfg.log_user = &log;
+        Ctx h;
+        int rc = gsb_create(&cfg, &h.c);
+        if (rc != GSB_OK) throw Error{std::string(gsb_last_error(nullptr)) + "\n"};
+        rc = gsb_comm_attach(h.c, id, n, rank);
+        if (rc != GSB_OK) fail_from_library(h.c, rc, opt.out);
+        struct Item { const std::vector<std::string>* names; int format; };
+        const Item items[3] = {{&opt.lines, GSB_FMT_LINE}, {&opt.fastas, GSB_FMT_FASTA}, {&opt.fastqs, GSB_FMT_FASTQ}};
+        uint64_t n_files = 0, block_no = 0, fasta_no = 0;
+        for (const Item& it : items)
+            for (const std::string& name : *it.names) {
+                ++n_files;
+                if (it.format == GSB_FMT_FASTA) {                       // whole FASTA files, round robin
+                    if ((int)(fasta_no++ % (uint64_t)n) != rank) continue;
+                    if (rank == 0 || opt.fastas.size() > 1) log(info, "reading " + name);
+                    BlockReader rd(name, it.format, (size_t)opt.block_mb << 20);
+                    const uint8_t* data; size_t size; bool last;
+                    while (rd.next(data, size, last)) {
+                        rc = gsb_push_block(h.c, data, size, it.format, last ? GSB_BLOCK_LAST_OF_FILE : GSB_BLOCK_ASYNC);
+                        if (rc != GSB_OK) fail_from_library(h.c, rc, name);
+                    }
+                    continue;
+                }
+                if (rank == 0) log(info, "reading " + name);
+                BlockReader rd(name, it.format, (size_t)opt.block_mb << 20);
+                const uint8_t* data; size_t size; bool last;
+                while (rd.next(data, size, last)) {                     // every worker scans the file; block b belongs to worker b mod n
+                    if ((int)(block_no++ % (uint64_t)n) != rank) continue;
+                    rc = gsb_push_block(h.c, data, size, it.format, GSB_BLOCK_LAST_OF_FILE | (last ? 0u : GSB_BLOCK_ASYNC));
+                    if (rc != GSB_OK) fail_from_library(h.c, rc, name);
+                }
+            }
+        if (n_files == 0) throw Error{"No valid reads.\n"};
+        gsb_counts counts;
+        if (rank == 0) log(info, "sorting and counting...");
+        rc = gsb_finish_counting(h.c, &counts);
+        if (rc != GSB_OK) fail_from_library(h.c, rc, opt.out);
+        if (counts.n_instances == 0 && kind == GSB_KIND_GRAPH) throw Error{"No valid reads.\n"};
+        OutputFiles files(true);
+        rc = gsb_emit(h.c, opt.out.c_str(), files.sink());
+        if (rc != GSB_OK) {
+            if (rc == GSB_EIO) throw Error{"\tcannot write to '" + opt.out + "'\n"};
+            fail_from_library(h.c, rc, opt.out);
+        }
+        if (rank == 0) {
+            gsb_stats st;
+            gsb_get_stats(h.c, &st);
+            std::ostringstream os;
+            os << n << " GPUs: " << counts.n_instances << " instances, " << counts.n_distinct << " distinct, " << counts.n_kept
+               << " kept; rank 0 device ms: scan " << st.ms_scan << " extract " << st.ms_extract << " exchange " << st.ms_exchange << " count " << st.ms_reduce
+               << " emit " << st.ms_emit;
+            log(info, os.str());
+            log(info, "total build time: " + std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
+        }
+        return 0;
+    } catch (const Error& e) {
+        std::cerr << "error performing " << cxt.cmdName << " (worker " << rank << ", device " << opt.devices[rank] << "):\n" << e.text;
+        return 1;
+    } catch (const std::exception& e) {
+        std::cerr << "caught unexpected exception in worker " << rank << ": " << e.what() << std::endl;
+        return 1;
+    }
+}
+
+void run_build_multi(const BuildOptions& opt, const GossCmdContext& cxt, int kind) {
+    const int n = (int)opt.devices.size();
+    remove_file_set(opt.out);                                          // shared files are opened without truncation
+    int up[2];
+    if (pipe(up) != 0) throw Error{"pipe failed\n"};
+    std::vector<int> down_r(n, -1), down_w(n, -1);
+    std::vector<pid_t> pids(n, -1);
+    for (int r = 1; r < n; ++r) { int p[2]; if (pipe(p) != 0) throw Error{"pipe failed\n"}; down_r[r] = p[0]; down_w[r] = p[1]; }
+    fflush(nullptr);
+    for (int r = 0; r < n; ++r) {
+        pid_t pid = fork();
+        if (pid < 0) throw Error{"fork failed\n"};
+        if (pid == 0) {
+            close(up[0]);
+            for (int q = 1; q < n; ++q) { close(down_w[q]); if (q != r) close(down_r[q]); }
+            const int rc = build_worker(opt, cxt, kind, r, n, down_r[r], up[1]);
+            fflush(nullptr);
+            _exit(rc);
+        }
+        pids[r] = pid;
+    }
+    close(up[1]);
+    for (int r = 1; r < n; ++r) close(down_r[r]);
+    unsigned char id[GSB_NCCL_ID_BYTES];
+    const bool have_id = read_all(up[0], id, sizeof(id));
+    close(up[0]);
+    for (int r = 1; r < n; ++r) { if (have_id) write_all(down_w[r], id, sizeof(id)); close(down_w[r]); }
+    bool failed = !have_id;
+    int left = n;
+    while (left > 0) {
+        int status = 0;
+        pid_t done = wait(&status);
+        if (done < 0) { if (errno == EINTR) continue; break; }
+        --left;
+        const bool ok = WIFEXITED(status) && WEXITSTATUS(status) == 0;
+        if (!ok && !failed) {                                          // one worker failed: the others would wait in a collective for ever
+            failed = true;
+            for (int r = 0; r < n; ++r) if (pids[r] != done) kill(pids[r], SIGTERM);
+        }
+    }
+    if (failed) throw Error{"a worker process failed (see above)\n"};
+}
+
 void run_build(const BuildOptions& opt, const GossCmdContext& cxt, int kind) {
+    if (opt.devices.size() > 1) { run_build_multi(opt, cxt, kind); return; }
     Logger& log = cxt.log;
     auto t0 = std::chrono::steady_clock::now();
     gsb_config cfg;
@@ -41,7 +198,7 @@ void run_build(const BuildOptions& opt, const GossCmdContext& cxt, int kind) {
     cfg.abi_version = GSB_ABI_VERSION;
     cfg.kind = kind;
     cfg.k = (int32_t)opt.K;
-    cfg.device = opt.device;
+    cfg.device = opt.devices.size() == 1 ? opt.devices[0] : opt.device;
     cfg.min_count = kind == GSB_KIND_GRAPH ? opt.min_count : 1;
     cfg.max_batch_keys = 0;
     cfg.log = &library_log;
@@ -123,6 +280,7 @@ std::string usage_text(const std::string& cmd) {
     if (cmd == "build-graph") os << "  -m, --min-count arg        keep edges seen at least this often (== trim-graph -C m-1)\n";
     if (cmd == "build-kmer-set") os << "  -S, --log-hash-slots arg   accepted for compatibility\n";
     os << "      --device arg           CUDA device ordinal (default 0)\n"
+       << "      --devices arg          several GPUs, one worker process each: 0,1,2,3 or 0-7\n"
        << "      --block-mb arg         input block size in MiB (default 256, at most 1024)\n"
        << "  -v, --verbose              show progress messages\n"
        << "  -l, --log-file arg         place to write messages\n"
@@ -169,6 +327,20 @@ ParsedArgs parse_build_args(const std::string& cmd, int argc, char** argv, uint6
         else if ((a == "-m" || a == "--min-count") && cmd == "build-graph") o.min_count = parse_u64(a, need().c_str());
         else if ((a == "-S" || a == "--log-hash-slots") && cmd == "build-kmer-set") (void)parse_u64(a, need().c_str());
         else if (a == "--device") o.device = (int)parse_u64(a, need().c_str());
+        else if (a == "--devices") {                                                   // 0,1,2 or 0-7
+            const std::string v = need();
+            const size_t dash = v.find('-');
+            if (dash != std::string::npos && v.find(',') == std::string::npos) {
+                const int lo = (int)parse_u64(a, v.substr(0, dash).c_str()), hi = (int)parse_u64(a, v.substr(dash + 1).c_str());
+                if (hi < lo) throw usage("the argument ('" + v + "') for option '--devices' is invalid\n");
+                for (int d = lo; d <= hi; ++d) o.devices.push_back(d);
+            } else {
+                std::stringstream ss(v);
+                std::string tok;
+                while (std::getline(ss, tok, ',')) o.devices.push_back((int)parse_u64(a, tok.c_str()));
+            }
+            if (o.devices.empty() || o.devices.size() > 32) throw usage("the argument ('" + v + "') for option '--devices' is invalid\n");
+        }
         else if (a == "--block-mb") o.block_mb = parse_u64(a, need().c_str());
         else if (a == "-l" || a == "--log-file") pa.log_file = need();
         else if (a == "--tmp-dir" || a == "-D" || a == "--debug") (void)need();

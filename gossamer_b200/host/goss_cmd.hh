@@ -36,6 +36,8 @@ struct BuildOptions {
     uint64_t T = 4;               // accepted and ignored: the work runs on the GPU
     uint64_t min_count = 1;       // -m / --min-count (addition; == build-graph then trim-graph -C m-1)
     int device = 0;
+    std::vector<int> devices;     // --devices a,b,c | a-b: one worker process per GPU (src/GossCmdBuildGraph.cc:270-426 is the seam;
+                                  // the reference itself has no distributed mode)
     uint64_t block_mb = 256;
     std::string out;
     std::vector<std::string> fastas, fastqs, lines;
@@ -56,6 +58,26 @@ public:
 private:
     BuildOptions opt_;
 };
+
+// trim-graph (src/GossCmdTrimGraph.cc), merge-graphs / merge-kmer-sets (src/GossCmdMerge.tcc), dump-graph
+// (src/GossCmdDumpGraph.cc), restore-graph (src/GossCmdRestoreGraph.cc): existing file sets in, a new file set (or text) out
+struct RewriteOptions {
+    std::vector<std::string> ins;     // -G / --graph-in (repeatable), --graphs-in <list>
+    std::string out;                  // -O / --graph-out
+    std::string text_file = "-";      // dump-graph -o / restore-graph -f
+    uint64_t cutoff = 0;              // trim-graph -C
+    bool have_cutoff = false;
+    uint64_t max_merge = 8;           // merge: --max-merge
+    int device = 0;
+    bool verbose = false, help = false;
+    std::string log_file;
+};
+RewriteOptions parse_rewrite_args(const std::string& cmd, int argc, char** argv);
+std::string rewrite_usage_text(const std::string& cmd);
+void run_trim_graph(const RewriteOptions& o, const GossCmdContext& cxt);
+void run_merge(const RewriteOptions& o, const GossCmdContext& cxt, bool kmer_sets);
+void run_dump_graph(const RewriteOptions& o, const GossCmdContext& cxt);
+void run_restore_graph(const RewriteOptions& o, const GossCmdContext& cxt);
 
 struct ParsedArgs {
     BuildOptions opt;

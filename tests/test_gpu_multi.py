@@ -110,3 +110,46 @@ def test_multi_gpu_build_bit_exact(k, min_count, mode):
         if n:
             assert first > last
             last = final
+
+
+def test_goss_cli_builds_on_several_gpus(tmp_path):
+    """The C++ host drives the multi-GPU build: `goss build-graph --devices 0,1[,2,3]` forks one worker process per GPU (NCCL id
+    over pipes), every worker pwrites its own byte ranges into the shared output files; the result is compared with the
+    single-process oracle, byte for byte."""
+    import subprocess
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    goss = os.path.join(os.path.dirname(HERE), "gossamer_b200", "goss")
+    g = S.genome(200_000, 77)
+    text = bytes(S.reads_fastq(g, 100, 60_000, err=0.01, seed=78))               # ~13 MB -> 13 blocks of 1 MiB over the workers
+    fasta = (">c1\n" + "\n".join(bytes(g[i:i + 70]).decode() for i in range(0, 40_000, 70)) + "\n").encode()
+    (tmp_path / "reads.fq").write_bytes(text)
+    (tmp_path / "ref.fa").write_bytes(fasta)
+    devices = ",".join(str(d) for d in range(world))
+
+    def files(prefix):
+        return {p.name: p.read_bytes() for p in tmp_path.iterdir() if p.name.startswith(prefix + ".") or p.name.startswith(prefix + "-")}
+
+    for k, m in ((27, 2), (55, 1)):
+        want, _ = O.build_graph([(fasta, O.FASTA), (text, O.FASTQ)], k, min_count=m, threads=4, base="g%d" % k)
+        # a stale, larger file under the prefix must not leak into the result
+        (tmp_path / ("g%d-edges.high-bits" % k)).write_bytes(b"\xff" * 10_000_000)
+        r = subprocess.run([goss, "build-graph", "-k", str(k), "-m", str(m), "-i", "reads.fq", "-I", "ref.fa", "-O", "g%d" % k, "--block-mb", "1",
+                            "--devices", devices, "-v"], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 0, r.stderr
+        got, ref = files("g%d" % k), want.files()
+        assert set(got) == set(ref)
+        assert not [n for n in ref if got[n] != ref[n]]
+    want, _ = O.build_kmer_set([(fasta, O.FASTA), (text, O.FASTQ)], 25, threads=4, base="ks")
+    r = subprocess.run([goss, "build-kmer-set", "-k", "25", "-i", "reads.fq", "-I", "ref.fa", "-O", "ks", "--block-mb", "1", "--devices", "0-%d" % (world - 1)],
+                       capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    got, ref = files("ks"), want.files()
+    assert set(got) == set(ref) and not [n for n in ref if got[n] != ref[n]]
+    # a parse error in one worker's block: every worker stops, exit code 1
+    cut = text.index(b"\n", len(text) // 2) + 1
+    (tmp_path / "bad.fq").write_bytes(text[:cut] + b"oops\n" + text[cut:])
+    r = subprocess.run([goss, "build-graph", "-k", "27", "-i", "bad.fq", "-O", "b", "--block-mb", "1", "--devices", devices], capture_output=True, text=True,
+                       cwd=tmp_path, timeout=120)
+    assert r.returncode == 1 and "bad.fq" in r.stderr

@@ -117,3 +117,54 @@ def test_dump_and_restore_match_reference(k):
     b.close()
     assert not _diff(sink.as_bytes(), want)
     assert c.n_kept == n
+
+
+def test_goss_cli_rewrite_commands(tmp_path):
+    """The C++ host: `goss trim-graph / merge-graphs / dump-graph / restore-graph` on real files, against the reference's
+    own commands run on the same file sets."""
+    import os
+    import subprocess
+    goss = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gossamer_b200", "goss")
+    k = 27
+    store = None
+    for i in range(3):
+        text = _reads(140 + i, 20_000, 4_000, 100)
+        st, f = _ref_graph(text, k, f"in{i}")
+        if store is None:
+            store = st
+        else:
+            store.put_all(f)
+        for n, v in f.items():
+            (tmp_path / n).write_bytes(v)
+
+    def files(prefix):
+        return {p.name: p.read_bytes() for p in tmp_path.iterdir() if p.name.startswith(prefix + ".") or p.name.startswith(prefix + "-")}
+
+    def run(*args):
+        r = subprocess.run([goss, *args], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 0, r.stderr
+        return r
+
+    run("trim-graph", "-G", "in0", "-O", "t", "-C", "2", "-v")
+    assert not _diff(files("t"), R.trim_graph(store, "in0", "t", 2))
+    run("merge-graphs", "-G", "in0", "-G", "in1", "-G", "in2", "-O", "m")
+    assert not _diff(files("m"), R.merge_graphs(store, ["in0", "in1", "in2"], "m"))
+    run("merge-graphs", "-G", "in0", "-G", "in1", "-G", "in2", "--max-merge", "2", "-O", "m2")
+    assert not _diff(files("m2"), R.merge_graphs(store, ["in0", "in1", "in2"], "m2", max_merge=2))
+    run("dump-graph", "-G", "in1", "-o", "dump.txt")
+    want_text = R.dump_graph(store, "in1", "dump.txt")
+    assert (tmp_path / "dump.txt").read_bytes() == want_text
+    r = subprocess.run([goss, "dump-graph", "-G", "in1"], capture_output=True, cwd=tmp_path)
+    assert r.returncode == 0 and r.stdout == want_text
+    run("restore-graph", "-f", "dump.txt", "-O", "r")
+    assert not _diff(files("r"), R.restore_graph(store, want_text, "r"))
+    # errors: unknown input, missing cutoff, k mismatch in a merge
+    r = subprocess.run([goss, "trim-graph", "-G", "nope", "-O", "x", "-C", "1"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "error performing trim-graph" in r.stderr
+    r = subprocess.run([goss, "trim-graph", "-G", "in0", "-O", "x"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "--cutoff" in r.stderr
+    st2, f2 = _ref_graph(_reads(150, 20_000, 1_000, 100), 25, "other")
+    for n, v in f2.items():
+        (tmp_path / n).write_bytes(v)
+    r = subprocess.run([goss, "merge-graphs", "-G", "in0", "-G", "other", "-O", "x"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "same kmer-size" in r.stderr
