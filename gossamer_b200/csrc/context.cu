@@ -267,6 +267,10 @@ void ensure_alt(gsb_ctx* c, u64 n) {
 void sort_run(gsb_ctx* c, ReducedRun& run) {
     if (run.m < 2) return;
     Workspace& ws = c->ws;
+    {
+        ReducedRun sorted;
+        if (sort_pairs_msd(ws, c->key_bytes, c->key_bits, run.keys.p, run.counts.p, run.m, 0, sorted)) { run = std::move(sorted); return; }
+    }
     DevBuf<u8> kalt(&ws, run.m * c->key_bytes);
     DevBuf<u64> calt(&ws, run.m);
     const int where = sort_keys(ws, c->key_bytes, c->key_bits, run.keys.p, kalt.p, run.counts.p, calt.p, run.m, nullptr, nullptr);
@@ -830,15 +834,23 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                     uk.free(); uc.free();
                     const u64 mine = totals[exchange_rank(c->comm)];
                     c->timer.start();
-                    DevBuf<u8> bk(&c->ws, mine * kb);
-                    DevBuf<u64> bc(&c->ws, mine);
-                    const int where = sort_keys(c->ws, kb, c->key_bits, rk, bk.p, rc, bc.p, mine, nullptr, nullptr);
-                    if (mine) {                              // keep one copy in the window (for the peers) and one as acc
-                        const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
-                        GSB_CUDA_TRY(cudaMemcpyAsync(where ? (void*)rk : (void*)bk.p, where ? (void*)bk.p : (void*)rk, mine * kb, d2d, c->ws.stream));
-                        GSB_CUDA_TRY(cudaMemcpyAsync(where ? rc : bc.p, where ? bc.p : rc, mine * 8, d2d, c->ws.stream));
+                    const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+                    ReducedRun sorted;
+                    if (mine && sort_pairs_msd(c->ws, kb, c->key_bits, rk, rc, mine, 0, sorted)) {
+                        // one copy stays in the window (for the peers), one is acc
+                        GSB_CUDA_TRY(cudaMemcpyAsync(rk, sorted.keys.p, mine * kb, d2d, c->ws.stream));
+                        GSB_CUDA_TRY(cudaMemcpyAsync(rc, sorted.counts.p, mine * 8, d2d, c->ws.stream));
+                        c->acc = std::move(sorted);
+                    } else {
+                        DevBuf<u8> bk(&c->ws, mine * kb);
+                        DevBuf<u64> bc(&c->ws, mine);
+                        const int where = sort_keys(c->ws, kb, c->key_bits, rk, bk.p, rc, bc.p, mine, nullptr, nullptr);
+                        if (mine) {
+                            GSB_CUDA_TRY(cudaMemcpyAsync(where ? (void*)rk : (void*)bk.p, where ? (void*)bk.p : (void*)rk, mine * kb, d2d, c->ws.stream));
+                            GSB_CUDA_TRY(cudaMemcpyAsync(where ? rc : bc.p, where ? bc.p : rc, mine * 8, d2d, c->ws.stream));
+                        }
+                        c->acc.keys = std::move(bk); c->acc.counts = std::move(bc); c->acc.m = mine;
                     }
-                    c->acc.keys = std::move(bk); c->acc.counts = std::move(bc); c->acc.m = mine;
                     c->timer.stop(c->stats.ms_unfold);
                     c->timer.start();
                     exchange_view(c->comm, kb, totals, &c->dist);
@@ -1311,6 +1323,8 @@ int gsb_debug_sort_bench(int device, uint64_t n, int key_bits, int iters, int tu
 }
 
 int gsb_debug_set_partition(int max_slots, int total_bits) { partition_set_debug((u32)(max_slots < 0 ? 0 : max_slots), total_bits); return GSB_OK; }
+
+int gsb_debug_set_pairsort(int cap, int bits) { pairsort_set_debug((u32)(cap < 0 ? 0 : cap), bits); return GSB_OK; }
 
 int gsb_debug_set_tuning(int id) { g_legacy_counting = (id >> 16) & 1; sort_set_tuning(id & 0xFFFF); return GSB_OK; }
 

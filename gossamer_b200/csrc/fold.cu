@@ -190,6 +190,12 @@ void unfold_run(Workspace& ws, int key_bytes, int key_bits, int w, ReducedRun& r
     if (!m) return;
     cudaStream_t s = ws.stream;
     if (!sorted_input) {
+        // U = run ++ rc(run) ordered by the full key: most-significant-digit passes + a shared-memory sort per bucket
+        // (partition.cu); only data that defeat the bucket geometry take the radix sort below
+        {
+            ReducedRun sorted;
+            if (sort_pairs_msd(ws, key_bytes, key_bits, run.keys.p, run.counts.p, m, w, sorted)) { run = std::move(sorted); return; }
+        }
         // U = run ++ rc(run), then one radix sort of the pairs by the full key
         DevBuf<u8> uk(&ws, 2 * m * key_bytes), uk_alt(&ws, 2 * m * key_bytes);
         DevBuf<u64> uc(&ws, 2 * m), uc_alt(&ws, 2 * m);

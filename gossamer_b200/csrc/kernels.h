@@ -139,6 +139,7 @@ struct PartitionPlan { int total_bits = 0, levels = 0; int bits[8] = {0, 0, 0, 0
 PartitionPlan partition_plan(int key_bytes, u64 n_all_ranks);
 u32 partition_tile_keys(int key_bytes);
 void partition_set_debug(u32 max_slots, int total_bits);          // test-only geometry overrides (0 = default)
+void pairsort_set_debug(u32 cap, int bits);                       // test-only: bucket capacity (0 = default), partition bits (< 0 = default)
 struct PartitionTiming { double ms_partition = 0, ms_count = 0, ms_scatter = 0; int levels = 0, total_bits = 0; u64 scatter_launches = 0, n_overflow_keys = 0; };
 struct PartitionInput {
     void* keys = nullptr; void* scratch = nullptr;
@@ -162,6 +163,10 @@ void partition_pull_check(Workspace& ws, u64* hist_all, const u64* gathered, int
                           u32* abort_flag, u64* n_recv, u64* n_remote);
 void partition_pull_level(Workspace& ws, int key_bytes, const void* const* src_base, int n_src, const u64* gathered, int bits0, u32 c_lo, u32 n_parents,
                           u64 n_cap, int bits, const u64* hist_slice, void* out, const u32* abort_flag, DevBuf<u64>& cstart_out, cudaEvent_t e0, cudaEvent_t e1);
+
+// (key, count) pairs with distinct keys, arbitrary order -> ordered by key (most-significant-digit passes + a shared-memory
+// sort per bucket, partition.cu); fold_w > 0: the reverse complements join the set first.  false = declined, radix-sort instead.
+bool sort_pairs_msd(Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w, ReducedRun& out);
 
 // ---- fold.cu ---------------------------------------------------------------------------------
 // Strand folding (graph mode): instances are counted as min(x, rc x); these restore both strands.

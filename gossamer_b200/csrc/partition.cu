@@ -92,6 +92,7 @@ struct PartArgs {
     const u32* n_tiles_dev;    // nullptr = n_tiles
     u32 n_tiles;
     u64 n;
+    const u64* n_dev;          // optional: the key count of a single-parent pass, known only on the device (n_tiles is then an upper bound)
     u64* cursor;               // [(parent << bits | digit) * cstride]: next free slot of the child (element index from its owner's base)
     u64* hist;                 // [parent << bits | digit]
     u32 cstride;
@@ -103,17 +104,32 @@ struct PartArgs {
     const u32* abort;          // optional: non-zero = do nothing (the exchange found a window too small)
 };
 
-template <typename K> __device__ __forceinline__ u32 part_digit(const K& k, int shift, u32 mask) { return (u32)(KeyOps<K>::lo(k) >> shift) & mask; }
+// What a pass moves and which bits it splits by.
+//   MixedDigit: bare instance keys, bit-mixed; the digit comes from the low (mixed) 64-bit word.
+//   RealDigit : (key, count) pairs ordered by the REAL key (pairsort below); shift counts from bit 0 of the whole key.
+struct __align__(16) Pair64 { u64 key; u64 count; };
+struct __align__(16) Pair128 { u64 lo, hi; u64 count; u64 pad; };
+struct MixedDigit {
+    template <typename K> static __device__ __forceinline__ u32 digit(const K& k, int shift, u32 mask) { return (u32)(KeyOps<K>::lo(k) >> shift) & mask; }
+};
+struct RealDigit {
+    static __device__ __forceinline__ u32 digit(const Pair64& e, int shift, u32 mask) { return (u32)(e.key >> shift) & mask; }
+    static __device__ __forceinline__ u32 digit(const Pair128& e, int shift, u32 mask) {
+        Key128 k; k.lo = e.lo; k.hi = e.hi;
+        return (u32)KeyOps<Key128>::shr64(k, shift) & mask;
+    }
+};
 
 // ---- digit histogram of one level ----------------------------------------------------------------------------------
-template <typename K>
+template <typename K, typename D>
 __global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
     constexpr int ITEMS = kPtTileBytes / (int)sizeof(K) / kPtThreads;
     constexpr u32 TILE = kPtThreads * ITEMS;
     __shared__ u32 cnt_s[kPtMaxBins];
     const int t = threadIdx.x;
     const K* __restrict__ in = (const K*)a.src_base[0];
-    const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles;
+    const u64 n_keys = a.n_dev ? *a.n_dev : a.n;
+    const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : (a.n_dev ? (u32)((n_keys + TILE - 1) / TILE) : a.n_tiles);
     const u32 mul = perm_mul(n_tiles);
     const u32 nbins = 1u << a.bits, mask = nbins - 1;
     for (u32 i = t; i < nbins; i += kPtThreads) cnt_s[i] = 0;
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
         __syncthreads();
     };
     for (u32 it = blockIdx.x; it < n_tiles; it += gridDim.x) {
-        const TileRef tr = tile_ref(a.descs, perm_tile(it, mul, n_tiles), a.n, TILE);
+        const TileRef tr = tile_ref(a.descs, perm_tile(it, mul, n_tiles), n_keys, TILE);
         if (tr.parent != cur_parent) {                               // uniform over the CTA
             if (cur_parent != 0xffffffffu) flush();
             cur_parent = tr.parent;
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const u32 j = (u32)t + (u32)i * kPtThreads;
-            if (j < tr.count) atomicAdd(&cnt_s[part_digit<K>(key[i], a.shift, mask)], 1u);
+            if (j < tr.count) atomicAdd(&cnt_s[D::digit(key[i], a.shift, mask)], 1u);
         }
     }
     if (cur_parent != 0xffffffffu) flush();
@@ -156,7 +172,7 @@ __global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
 //   counts, reserve the tile's run in every child with one global atomicAdd per digit -> [barrier] -> keys into the exchange
 //   buffer grouped by digit -> [barrier] -> write-out, one contiguous run per digit.
 // BPT = bins per thread: 1 (up to 256 children per parent, 3 CTAs per SM) or 4 (up to 1024, 2 CTAs per SM)
-template <typename K, int BPT>
+template <typename K, typename D, int BPT>
 __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_kernel(PartArgs a) {
     constexpr int ITEMS = kPtTileBytes / (int)sizeof(K) / kPtThreads;
     constexpr u32 TILE = kPtThreads * ITEMS;
@@ -172,7 +188,8 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
 
     if (a.abort && *a.abort) return;
     const int t = threadIdx.x;
-    const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : a.n_tiles;
+    const u64 n_keys = a.n_dev ? *a.n_dev : a.n;
+    const u32 n_tiles = a.n_tiles_dev ? *a.n_tiles_dev : (a.n_dev ? (u32)((n_keys + TILE - 1) / TILE) : a.n_tiles);
     const u32 mul = perm_mul(n_tiles);
     const u32 mask = (1u << a.bits) - 1;
 #pragma unroll
@@ -190,14 +207,14 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
     u32 it = blockIdx.x;
     TileRef cur{0, 0, 0, 0};
     if (it < n_tiles) {
-        cur = tile_ref(a.descs, perm_tile(it, mul, n_tiles), a.n, TILE);
+        cur = tile_ref(a.descs, perm_tile(it, mul, n_tiles), n_keys, TILE);
         if (t == 0) issue(cur);
     }
     u32 parity = 0;
     for (; it < n_tiles; it += gridDim.x) {
         const u32 nit = it + gridDim.x;
         TileRef nxt{0, 0, 0, 0};
-        if (nit < n_tiles) nxt = tile_ref(a.descs, perm_tile(nit, mul, n_tiles), a.n, TILE);
+        if (nit < n_tiles) nxt = tile_ref(a.descs, perm_tile(nit, mul, n_tiles), n_keys, TILE);
         mbar_wait(&full_bar, parity);
         parity ^= 1;
         const u32 skip = sizeof(K) == 8 ? (u32)(cur.begin & 1) : 0u;
@@ -212,7 +229,7 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
         for (int i = 0; i < ITEMS; ++i) {
             const u32 j = (u32)t + (u32)i * kPtThreads;
             rank[i] = 0;
-            if (j < cur.count) rank[i] = atomicAdd(&cnt_s[part_digit<K>(key[i], a.shift, mask)], 1u);
+            if (j < cur.count) rank[i] = atomicAdd(&cnt_s[D::digit(key[i], a.shift, mask)], 1u);
         }
         __syncthreads();                                                  // every key is in registers, every count is final
         if (t == 0 && nit < n_tiles) issue(nxt);
@@ -243,7 +260,7 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const u32 j = (u32)t + (u32)i * kPtThreads;
-            if (j < cur.count) out_s[start_s[part_digit<K>(key[i], a.shift, mask)] + rank[i]] = key[i];
+            if (j < cur.count) out_s[start_s[D::digit(key[i], a.shift, mask)] + rank[i]] = key[i];
         }
         {
             u32 run = ex;
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
             const u32 j = (u32)t + (u32)i * kPtThreads;
             if (j < cur.count) {
                 const K k = out_s[j];
-                *reinterpret_cast<K*>(gaddr_s[part_digit<K>(k, a.shift, mask)] + (u64)j * sizeof(K)) = k;
+                *reinterpret_cast<K*>(gaddr_s[D::digit(k, a.shift, mask)] + (u64)j * sizeof(K)) = k;
             }
         }
         cur = nxt;
@@ -516,26 +533,48 @@ __global__ void fold_hist_kernel(const u64* __restrict__ in, int from_bits, int 
     out[d] = sum;
 }
 
-template <typename K>
-static void launch_hist(const PartArgs& a, int grid, cudaStream_t s) { part_hist_kernel<K><<<grid, kPtThreads, 0, s>>>(a); }
+// what a pass moves (element size; which digit functor)
+enum ElemKind { EK_KEY64, EK_KEY128, EK_PAIR64, EK_PAIR128 };
+static inline ElemKind mixed_kind(int key_bytes) { return key_bytes == 8 ? EK_KEY64 : EK_KEY128; }
+static inline ElemKind pair_kind(int key_bytes) { return key_bytes == 8 ? EK_PAIR64 : EK_PAIR128; }
+static inline u32 elem_bytes(ElemKind ek) { return ek == EK_KEY64 ? 8u : ek == EK_PAIR128 ? 32u : 16u; }
+static inline u32 tile_elems(ElemKind ek) { return (u32)kPtTileBytes / elem_bytes(ek); }
 
-template <typename K, int BPT>
+static void launch_hist(ElemKind ek, const PartArgs& a, int grid, cudaStream_t s) {
+    switch (ek) {
+        case EK_KEY64: part_hist_kernel<u64, MixedDigit><<<grid, kPtThreads, 0, s>>>(a); break;
+        case EK_KEY128: part_hist_kernel<Key128, MixedDigit><<<grid, kPtThreads, 0, s>>>(a); break;
+        case EK_PAIR64: part_hist_kernel<Pair64, RealDigit><<<grid, kPtThreads, 0, s>>>(a); break;
+        case EK_PAIR128: part_hist_kernel<Pair128, RealDigit><<<grid, kPtThreads, 0, s>>>(a); break;
+    }
+}
+
+template <typename K, typename D, int BPT>
 static void launch_scatter_b(const PartArgs& a, int grid, int device, cudaStream_t s) {
     const size_t smem = 2 * (size_t)kPtTileBytes + 256;
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
-        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K, BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K, BPT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K, D, BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel<K, D, BPT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         if (device >= 0 && device < 64) configured[device] = true;
     }
-    part_scatter_kernel<K, BPT><<<grid, kPtThreads, smem, s>>>(a);
+    part_scatter_kernel<K, D, BPT><<<grid, kPtThreads, smem, s>>>(a);
 }
 
-static void launch_scatter(int key_bytes, const PartArgs& a, u64 tiles_ub, Workspace& ws) {
+template <typename K, typename D>
+static void launch_scatter_w(bool wide, const PartArgs& a, int grid, int device, cudaStream_t s) {
+    if (wide) launch_scatter_b<K, D, 4>(a, grid, device, s); else launch_scatter_b<K, D, 1>(a, grid, device, s);
+}
+
+static void launch_scatter(ElemKind ek, const PartArgs& a, u64 tiles_ub, Workspace& ws) {
     const bool wide = a.bits > 8;
     const int grid = (int)std::min<u64>(tiles_ub, (u64)ws.sm_count * (wide ? 2 : 3));
-    if (key_bytes == 8) { if (wide) launch_scatter_b<u64, 4>(a, grid, ws.device, ws.stream); else launch_scatter_b<u64, 1>(a, grid, ws.device, ws.stream); }
-    else { if (wide) launch_scatter_b<Key128, 4>(a, grid, ws.device, ws.stream); else launch_scatter_b<Key128, 1>(a, grid, ws.device, ws.stream); }
+    switch (ek) {
+        case EK_KEY64: launch_scatter_w<u64, MixedDigit>(wide, a, grid, ws.device, ws.stream); break;
+        case EK_KEY128: launch_scatter_w<Key128, MixedDigit>(wide, a, grid, ws.device, ws.stream); break;
+        case EK_PAIR64: launch_scatter_w<Pair64, RealDigit>(wide, a, grid, ws.device, ws.stream); break;
+        case EK_PAIR128: launch_scatter_w<Pair128, RealDigit>(wide, a, grid, ws.device, ws.stream); break;
+    }
     ++ws.launches;
 }
 
@@ -571,6 +610,10 @@ u32 partition_tile_keys(int key_bytes) { return (u32)(kPtTileBytes / key_bytes);
 static u32 g_force_max_slots = 0;
 static int g_force_total_bits = 0;
 void partition_set_debug(u32 max_slots, int total_bits) { g_force_max_slots = max_slots; g_force_total_bits = total_bits; }
+// the same for the pair sort: bucket capacity (0 = default) and partition bits (< 0 = default)
+static u32 g_force_pair_cap = 0;
+static int g_force_pair_bits = -1;
+void pairsort_set_debug(u32 cap, int bits) { g_force_pair_cap = cap; g_force_pair_bits = bits; }
 
 // Bits the partition passes consume for n keys (ALL keys that share the key space: the sum over the ranks of a multi-GPU
 // build), and how they are split over the passes: as few passes as 10 bits each allow, the earlier passes taking the
@@ -604,9 +647,9 @@ struct LevelTiles {
 };
 
 // tiles over local parents given by cstart [n_parents + 1] (or one parent [0, n) when cstart is null)
-void build_tiles(Workspace& ws, int key_bytes, const u64* cstart, u64 n_parents, u64 n, u64 n_cap, LevelTiles& tiles) {
+void build_tiles(Workspace& ws, ElemKind ek, const u64* cstart, u64 n_parents, u64 n, u64 n_cap, LevelTiles& tiles) {
     cudaStream_t s = ws.stream;
-    const u32 tile_keys = partition_tile_keys(key_bytes);
+    const u32 tile_keys = tile_elems(ek);
     tiles.tiles_ub = cstart ? (n_cap + tile_keys - 1) / tile_keys + n_parents : (n + tile_keys - 1) / tile_keys;
     if (tiles.tiles_ub > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
     if (!cstart) return;
@@ -620,17 +663,17 @@ void build_tiles(Workspace& ws, int key_bytes, const u64* cstart, u64 n_parents,
 }
 
 // hist[parent << bits | digit] += number of such keys (hist must be zeroed by the caller)
-void level_hist(Workspace& ws, int key_bytes, PartArgs pa, const LevelTiles& tiles, u64* hist) {
+void level_hist(Workspace& ws, ElemKind ek, PartArgs pa, const LevelTiles& tiles, u64* hist) {
     tiles.apply(pa);
     pa.hist = hist;
     const int grid = (int)std::min<u64>(tiles.tiles_ub, (u64)ws.sm_count * 8);
     if (grid == 0) return;
-    if (key_bytes == 8) launch_hist<u64>(pa, grid, ws.stream); else launch_hist<Key128>(pa, grid, ws.stream);
+    launch_hist(ek, pa, grid, ws.stream);
     ++ws.launches;
 }
 
 // child starts from the histogram, cursors, the scatter pass itself
-void level_scatter(Workspace& ws, int key_bytes, PartArgs pa, const LevelTiles& tiles, const u64* hist, u64 n_children, DevBuf<u64>& cstart_out,
+void level_scatter(Workspace& ws, ElemKind ek, PartArgs pa, const LevelTiles& tiles, const u64* hist, u64 n_children, DevBuf<u64>& cstart_out,
                    PartitionTiming* timing, std::vector<LevelTiming>& events) {
     cudaStream_t s = ws.stream;
     DevBuf<u64> cnext(&ws, n_children + 1), scan_tmp(&ws, scan_tmp_elems(n_children));
@@ -644,36 +687,39 @@ void level_scatter(Workspace& ws, int key_bytes, PartArgs pa, const LevelTiles& 
     pa.cursor = cursor.p; pa.cstride = cstride; pa.hist = nullptr;
     LevelTiming lt;
     if (timing) { GSB_CUDA_TRY(cudaEventCreate(&lt.e0)); GSB_CUDA_TRY(cudaEventCreate(&lt.e1)); GSB_CUDA_TRY(cudaEventRecord(lt.e0, s)); }
-    if (tiles.tiles_ub) launch_scatter(key_bytes, pa, tiles.tiles_ub, ws);
+    if (tiles.tiles_ub) launch_scatter(ek, pa, tiles.tiles_ub, ws);
     if (timing) { GSB_CUDA_TRY(cudaEventRecord(lt.e1, s)); events.push_back(lt); }
     cstart_out = std::move(cnext);
 }
 
-PartArgs local_args(const void* cur, void* other, u64 n, int consumed, int bits) {
+// top_bits: where the digits start -- 64 for the mixed low word of an instance key, the key width for pairs ordered by the real key
+PartArgs local_args(const void* cur, void* other, u64 n, int consumed, int bits, int top_bits = 64) {
     PartArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.src_base[0] = cur; pa.out = other; pa.n = n;
-    pa.shift = 64 - consumed - bits; pa.bits = bits;
+    pa.shift = top_bits - consumed - bits; pa.bits = bits;
     pa.peer[0] = other; pa.n_peers = 1; pa.abort = nullptr;
     return pa;
 }
 
 // One pass over `cur` (parents given by cstart, or one parent [0, n) when cstart is empty) by `bits` more bits into `other`.
 // Produces the child starts.  hist_ready: optional histogram [n_parents << bits] that is already known.
-void run_level(Workspace& ws, int key_bytes, void* cur, void* other, u64 n, u64 n_cap, DevBuf<u64>& cstart, u64 n_parents, int consumed, int bits,
-               const u64* hist_ready, PartitionTiming* timing, std::vector<LevelTiming>& events) {
+// n_dev (single-parent passes only): the key count lives on the device; n is then its upper bound.
+void run_level(Workspace& ws, ElemKind ek, void* cur, void* other, u64 n, u64 n_cap, DevBuf<u64>& cstart, u64 n_parents, int consumed, int bits,
+               const u64* hist_ready, PartitionTiming* timing, std::vector<LevelTiming>& events, int top_bits = 64, const u64* n_dev = nullptr) {
     const u64 n_children = n_parents << bits;
-    PartArgs pa = local_args(cur, other, n, consumed, bits);
+    PartArgs pa = local_args(cur, other, n, consumed, bits, top_bits);
+    pa.n_dev = cstart.p ? nullptr : n_dev;
     LevelTiles tiles;
-    build_tiles(ws, key_bytes, cstart.p, n_parents, n, n_cap, tiles);
+    build_tiles(ws, ek, cstart.p, n_parents, n, n_cap, tiles);
     DevBuf<u64> hist;
     if (!hist_ready) {
         hist.reset(&ws, n_children);
         GSB_CUDA_TRY(cudaMemsetAsync(hist.p, 0, n_children * 8, ws.stream));
-        level_hist(ws, key_bytes, pa, tiles, hist.p);
+        level_hist(ws, ek, pa, tiles, hist.p);
         hist_ready = hist.p;
     }
-    level_scatter(ws, key_bytes, pa, tiles, hist_ready, n_children, cstart, timing, events);
+    level_scatter(ws, ek, pa, tiles, hist_ready, n_children, cstart, timing, events);
 }
 
 // ---- pull exchange: tiles over the runs that every source rank holds of this rank's children ------------------------------
@@ -752,7 +798,7 @@ void partition_scatter_to_peers(Workspace& ws, int key_bytes, const void* in, u6
     const u64 tiles = (n + tile_keys - 1) / tile_keys;
     if (tiles > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
     pa.n_tiles = (u32)tiles;
-    launch_scatter(key_bytes, pa, tiles, ws);
+    launch_scatter(mixed_kind(key_bytes), pa, tiles, ws);
 }
 
 void partition_fold_hist(Workspace& ws, const u64* hist_top, int bits, u64* out) {
@@ -772,7 +818,7 @@ void partition_local_level0(Workspace& ws, int key_bytes, void* in, void* out, u
         hist_ready = folded.p;
     }
     DevBuf<u64> none;
-    run_level(ws, key_bytes, in, out, n, n, none, 1, 0, bits, hist_ready, nullptr, ev);
+    run_level(ws, mixed_kind(key_bytes), in, out, n, n, none, 1, 0, bits, hist_ready, nullptr, ev);
     cstart_out = std::move(none);
 }
 
@@ -782,8 +828,8 @@ void partition_next_hist(Workspace& ws, int key_bytes, const void* keys, const u
     GSB_CUDA_TRY(cudaMemsetAsync(hist, 0, (n_parents << bits) * 8, ws.stream));
     PartArgs pa = local_args(keys, nullptr, n, bits0, bits);
     LevelTiles tiles;
-    build_tiles(ws, key_bytes, cstart, n_parents, n, n, tiles);
-    level_hist(ws, key_bytes, pa, tiles, hist);
+    build_tiles(ws, mixed_kind(key_bytes), cstart, n_parents, n, n, tiles);
+    level_hist(ws, mixed_kind(key_bytes), pa, tiles, hist);
 }
 
 void partition_pull_check(Workspace& ws, u64* hist_all, const u64* gathered, int bits0, int bits1, int n_ranks, int rank, u64 cap_keys,
@@ -817,7 +863,7 @@ void partition_pull_level(Workspace& ws, int key_bytes, const void* const* src_b
     pa.abort = abort_flag;
     std::vector<LevelTiming> ev;
     if (e0) GSB_CUDA_TRY(cudaEventRecord(e0, s));
-    level_scatter(ws, key_bytes, pa, tiles, hist_slice, (u64)n_parents << bits, cstart_out, nullptr, ev);
+    level_scatter(ws, mixed_kind(key_bytes), pa, tiles, hist_slice, (u64)n_parents << bits, cstart_out, nullptr, ev);
     if (e1) GSB_CUDA_TRY(cudaEventRecord(e1, s));
 }
 
@@ -860,7 +906,7 @@ bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, PartitionInpu
             partition_fold_hist(ws, in.hist_top, bits, folded.p);
             hist_ready = folded.p;
         }
-        run_level(ws, key_bytes, cur, other, in.n, n_cap, cstart, n_parents, consumed, bits, hist_ready, timing, levels_ev);
+        run_level(ws, mixed_kind(key_bytes), cur, other, in.n, n_cap, cstart, n_parents, consumed, bits, hist_ready, timing, levels_ev);
         std::swap(cur, other);
         n_parents <<= bits;
         consumed += bits;
@@ -943,6 +989,296 @@ bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, PartitionInpu
     *m_distinct = h[2] + d2;
     *n_self_rc = h[3] + self2;
     ws.sync();
+    return true;
+}
+
+// ======================================================================================================================
+// Ordering (key, count) pairs with DISTINCT keys by the real key: the survivors of the count come back in arbitrary order
+// and the writers need them sorted (src/BackyardHash.cc:244-271 is the order the reference's emit loop sees).  An LSD
+// radix sort of (key, count) pairs reads and writes every pair once per key byte -- 8 sweeps at k = 31, 14 at k = 55.
+// Distinct keys need no stable sort, so the same most-significant-digit passes as above are used, on 16/32-byte
+// {key, count} elements and the top bits of the REAL key, until a bucket holds ~2000 pairs; one CTA then orders a bucket
+// in shared memory: counting sort on the next 12 bits, rank among the (few) pairs that share a bin by direct comparison.
+// A bucket that does not fit (real genomes are not uniform: low-complexity prefixes) is written out unordered and
+// radix-sorted on its own afterwards, so the result never depends on the data; if there are many such buckets the caller
+// falls back to the radix sort of everything.
+// ======================================================================================================================
+namespace {
+
+static const int kPkThreads = 256;
+static const int kPkItems = 4;
+static const int kBsThreads = 512;
+static const int kBsBinBits = 12;
+
+template <typename K> struct PairOf;
+template <> struct PairOf<u64> {
+    typedef Pair64 type;
+    static __device__ __forceinline__ Pair64 make(u64 k, u64 c) { Pair64 e; e.key = k; e.count = c; return e; }
+    static __device__ __forceinline__ u64 key(const Pair64& e) { return e.key; }
+};
+template <> struct PairOf<Key128> {
+    typedef Pair128 type;
+    static __device__ __forceinline__ Pair128 make(const Key128& k, u64 c) { Pair128 e; e.lo = k.lo; e.hi = k.hi; e.count = c; e.pad = 0; return e; }
+    static __device__ __forceinline__ Key128 key(const Pair128& e) { Key128 k; k.lo = e.lo; k.hi = e.hi; return k; }
+};
+
+// (keys[i], counts[i]) -> out[i]; fold_w > 0: additionally (rc keys[i], counts[i]) for every key that is not its own reverse
+// complement, appended behind the first m elements (cursor starts at m; arbitrary order).  Fuses the histogram of the top
+// `bits` bits of every element written.
+template <typename K>
+__global__ void __launch_bounds__(kPkThreads) pairs_pack_kernel(const K* __restrict__ keys, const u64* __restrict__ counts, u64 m, int fold_w,
+                                                                typename PairOf<K>::type* __restrict__ out, u64* __restrict__ cursor,
+                                                                u64* __restrict__ hist, int shift, int bits) {
+    typedef typename PairOf<K>::type E;
+    __shared__ u32 cnt_s[kPtMaxBins];
+    const int t = threadIdx.x, lane = t & 31;
+    const u32 lt = (1u << lane) - 1;
+    const u32 nbins = 1u << bits, mask = nbins - 1;
+    for (u32 i = t; i < nbins; i += kPkThreads) cnt_s[i] = 0;
+    __syncthreads();
+    const u64 tiles = (m + (u64)kPkThreads * kPkItems - 1) / ((u64)kPkThreads * kPkItems);
+    for (u64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const u64 base0 = tile * kPkThreads * kPkItems;
+        E r[kPkItems]; u32 bal[kPkItems]; u32 total = 0;
+#pragma unroll
+        for (int it = 0; it < kPkItems; ++it) {
+            const u64 i = base0 + (u64)it * kPkThreads + t;
+            bool take = false;
+            if (i < m) {
+                const K y = keys[i];
+                const u64 c = counts[i];
+                const E e = PairOf<K>::make(y, c);
+                out[i] = e;
+                if (bits) atomicAdd(&cnt_s[RealDigit::digit(e, shift, mask)], 1u);
+                if (fold_w) {
+                    const K ry = key_rc(y, fold_w);
+                    take = !KeyOps<K>::eq(ry, y);
+                    r[it] = PairOf<K>::make(ry, c);
+                }
+            }
+            bal[it] = __ballot_sync(0xffffffffu, take);
+            total += __popc(bal[it]);
+        }
+        if (fold_w) {
+            u64 base = 0;
+            if (lane == 0 && total) base = atomicAdd(cursor, (u64)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int it = 0; it < kPkItems; ++it) {
+                if ((bal[it] >> lane) & 1u) {
+                    out[base + __popc(bal[it] & lt)] = r[it];
+                    if (bits) atomicAdd(&cnt_s[RealDigit::digit(r[it], shift, mask)], 1u);
+                }
+                base += __popc(bal[it]);
+            }
+        }
+    }
+    __syncthreads();
+    for (u32 i = t; i < nbins; i += kPkThreads) { const u32 c = cnt_s[i]; if (c) atomicAdd(&hist[i], (u64)c); }
+}
+
+template <typename K> struct BucketSmem;
+template <> struct BucketSmem<u64> {
+    static const u32 kCap = 4096;
+    u64* k; u64* c;
+    __device__ __forceinline__ void bind(unsigned char* p) { k = (u64*)p; c = k + kCap; }
+    static size_t bytes() { return (size_t)kCap * 16; }
+    __device__ __forceinline__ void put(u32 i, const Pair64& e) { k[i] = e.key; c[i] = e.count; }
+    __device__ __forceinline__ u64 key(u32 i) const { return k[i]; }
+};
+template <> struct BucketSmem<Key128> {
+    static const u32 kCap = 2048;
+    u64* lo; u64* hi; u64* c;
+    __device__ __forceinline__ void bind(unsigned char* p) { lo = (u64*)p; hi = lo + kCap; c = hi + kCap; }
+    static size_t bytes() { return (size_t)kCap * 24; }
+    __device__ __forceinline__ void put(u32 i, const Pair128& e) { lo[i] = e.lo; hi[i] = e.hi; c[i] = e.count; }
+    __device__ __forceinline__ Key128 key(u32 i) const { Key128 k; k.lo = lo[i]; k.hi = hi[i]; return k; }
+};
+
+// One CTA per bucket [cstart[b], cstart[b+1]) of elems (all pairs of a bucket share the top `consumed` bits of the key):
+// the pairs come out ordered by key into out_keys / out_counts at the same positions.  Buckets above the capacity are
+// copied unordered and listed in ovf ({first, length}; ctr[0] counts them).
+template <typename K>
+__global__ void __launch_bounds__(kBsThreads) bucket_sort_kernel(const typename PairOf<K>::type* __restrict__ elems, const u64* __restrict__ cstart, u32 n_buckets,
+                                                                 int key_bits, int consumed, u32 cap, K* __restrict__ out_keys, u64* __restrict__ out_counts,
+                                                                 ulonglong2* __restrict__ ovf, u64 ovf_cap, u64* __restrict__ ctr) {
+    typedef typename PairOf<K>::type E;
+    typedef KeyOps<K> KO;
+    constexpr u32 CAP = BucketSmem<K>::kCap;
+    constexpr u32 NB = 1u << kBsBinBits;
+    constexpr int BPT = NB / kBsThreads;
+    extern __shared__ __align__(16) unsigned char bs_smem[];
+    __shared__ u32 bin_s[NB + 1];
+    __shared__ u16 pos_s[CAP];          // place inside the bin, later: perm[rank] = element
+    __shared__ u16 ord_s[CAP];          // elements in bin order
+    __shared__ u32 scan_s[kBsThreads / 32 + 1];
+    BucketSmem<K> sm;
+    sm.bind(bs_smem);
+    const int t = threadIdx.x;
+    const int rem = key_bits - consumed;
+    const int bb = rem < kBsBinBits ? (rem > 0 ? rem : 0) : kBsBinBits;
+    const int shift = rem - bb;
+    const u32 bmask = (1u << bb) - 1;
+    for (u32 b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+        const u64 st = cstart[b];
+        const u64 nb64 = cstart[b + 1] - st;
+        if (nb64 == 0) continue;
+        if (nb64 > cap) {                                              // cap <= CAP
+            for (u64 i = t; i < nb64; i += kBsThreads) {
+                const E e = elems[st + i];
+                out_keys[st + i] = PairOf<K>::key(e);
+                out_counts[st + i] = e.count;
+            }
+            if (t == 0) {
+                const u64 o = atomicAdd(&ctr[0], 1ull);
+                if (o < ovf_cap) ovf[o] = make_ulonglong2(st, nb64);
+            }
+            continue;
+        }
+        const u32 nb = (u32)nb64;
+#pragma unroll
+        for (int j = 0; j < BPT; ++j) bin_s[t * BPT + j] = 0;
+        __syncthreads();
+        for (u32 i = t; i < nb; i += kBsThreads) {
+            const E e = elems[st + i];
+            sm.put(i, e);
+            pos_s[i] = (u16)atomicAdd(&bin_s[(u32)KO::shr64(PairOf<K>::key(e), shift) & bmask], 1u);
+        }
+        __syncthreads();
+        {
+            u32 c[BPT]; u32 sum = 0;
+#pragma unroll
+            for (int j = 0; j < BPT; ++j) { c[j] = bin_s[t * BPT + j]; sum += c[j]; }
+            u32 run = block_exclusive_scan<u32, kBsThreads>(sum, (u32*)nullptr, scan_s);
+#pragma unroll
+            for (int j = 0; j < BPT; ++j) { bin_s[t * BPT + j] = run; run += c[j]; }
+            if (t == kBsThreads - 1) bin_s[NB] = run;
+        }
+        __syncthreads();
+        for (u32 i = t; i < nb; i += kBsThreads) ord_s[bin_s[(u32)KO::shr64(sm.key(i), shift) & bmask] + pos_s[i]] = (u16)i;
+        __syncthreads();
+        for (u32 i = t; i < nb; i += kBsThreads) {
+            const K mine = sm.key(i);
+            const u32 bin = (u32)KO::shr64(mine, shift) & bmask;
+            const u32 s0 = bin_s[bin], s1 = bin_s[bin + 1];
+            u32 r = s0;
+            if (s1 - s0 > 1) {
+                for (u32 j = s0; j < s1; ++j) {
+                    const u32 o = ord_s[j];
+                    const K other = sm.key(o);
+                    r += (KO::lt(other, mine) || (KO::eq(other, mine) && o < i)) ? 1u : 0u;
+                }
+            }
+            pos_s[r] = (u16)i;             // pos_s[i] was last read before the barrier above
+        }
+        __syncthreads();
+        for (u32 r = t; r < nb; r += kBsThreads) {
+            const u32 i = pos_s[r];
+            out_keys[st + r] = sm.key(i);
+            out_counts[st + r] = sm.c[i];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename K>
+static void launch_bucket_sort(const void* elems, const u64* cstart, u32 n_buckets, int key_bits, int consumed, u32 cap, void* out_keys, u64* out_counts,
+                               ulonglong2* ovf, u64 ovf_cap, u64* ctr, int sm_count, int device, cudaStream_t s) {
+    typedef typename PairOf<K>::type E;
+    const size_t smem = BucketSmem<K>::bytes();
+    static bool configured[64] = {false};
+    if (device < 0 || device >= 64 || !configured[device]) {
+        GSB_CUDA_TRY(cudaFuncSetAttribute(bucket_sort_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_CUDA_TRY(cudaFuncSetAttribute(bucket_sort_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        if (device >= 0 && device < 64) configured[device] = true;
+    }
+    const int grid = (int)std::min<u64>(n_buckets, (u64)sm_count * 2 * 8);
+    bucket_sort_kernel<K><<<grid, kBsThreads, smem, s>>>((const E*)elems, cstart, n_buckets, key_bits, consumed, cap, (K*)out_keys, out_counts, ovf, ovf_cap, ctr);
+}
+
+}  // namespace
+
+// m (key, count) pairs with distinct keys, arbitrary order -> ordered by key; fold_w > 0: the reverse complement of every
+// key that is not self-complementary joins the set first (fold.cu: the folded, filtered run becomes the reference's edge
+// set).  out is (re)allocated; out.m = pairs produced.  Returns false (nothing produced) when the data defeat the bucket
+// geometry -- the caller radix-sorts instead.
+bool sort_pairs_msd(Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w, ReducedRun& out) {
+    cudaStream_t s = ws.stream;
+    const u64 n_cap = fold_w ? 2 * m : m;
+    if (n_cap == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); out.m = 0; return true; }
+    const ElemKind ek = pair_kind(key_bytes);
+    const u32 eb = elem_bytes(ek);
+    u32 cap = key_bytes == 8 ? BucketSmem<u64>::kCap : BucketSmem<Key128>::kCap;
+    if (g_force_pair_cap >= 2 && g_force_pair_cap < cap) cap = g_force_pair_cap;
+    // bits so that the mean bucket is half the capacity; as few passes as 10 bits each allow
+    int bits = 0;
+    while (bits < 40 && (n_cap >> bits) > cap / 2) ++bits;
+    if (g_force_pair_bits >= 0) bits = g_force_pair_bits;
+    if (bits > key_bits) bits = key_bits;
+    const int levels = (bits + 9) / 10;
+    int lb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int l = 0; l < levels; ++l) lb[l] = bits / levels + (l < bits % levels ? 1 : 0);
+
+    DevBuf<u8> ea(&ws, n_cap * eb + 64), eb2(&ws, levels ? n_cap * eb + 64 : 1);
+    DevBuf<u64> n_dev(&ws, 1), hist0(&ws, (size_t)1 << lb[0]), ctr(&ws, 1);
+    GSB_CUDA_TRY(cudaMemcpyAsync(n_dev.p, &m, 8, cudaMemcpyHostToDevice, s));          // cursor of the appended reverse complements
+    GSB_CUDA_TRY(cudaMemsetAsync(hist0.p, 0, hist0.bytes(), s));
+    GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 8, s));
+    {
+        const u64 tiles = (m + (u64)kPkThreads * kPkItems - 1) / ((u64)kPkThreads * kPkItems);
+        const int grid = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)ws.sm_count * 8));
+        const int shift0 = key_bits - lb[0];
+        if (key_bytes == 8) pairs_pack_kernel<u64><<<grid, kPkThreads, 0, s>>>((const u64*)keys, counts, m, fold_w, (Pair64*)ea.p, n_dev.p, hist0.p, shift0, lb[0]);
+        else pairs_pack_kernel<Key128><<<grid, kPkThreads, 0, s>>>((const Key128*)keys, counts, m, fold_w, (Pair128*)ea.p, n_dev.p, hist0.p, shift0, lb[0]);
+        ++ws.launches;
+    }
+    void* cur = ea.p; void* other = eb2.p;
+    DevBuf<u64> cstart;
+    u64 n_parents = 1;
+    int consumed = 0;
+    std::vector<LevelTiming> ev;
+    for (int l = 0; l < levels; ++l) {
+        run_level(ws, ek, cur, other, n_cap, n_cap, cstart, n_parents, consumed, lb[l], l == 0 ? hist0.p : nullptr, nullptr, ev, key_bits, n_dev.p);
+        std::swap(cur, other);
+        n_parents <<= lb[l];
+        consumed += lb[l];
+    }
+    if (cstart.p == nullptr) {                                          // no pass at all: one bucket [0, n)
+        cstart.reset(&ws, 2);
+        GSB_CUDA_TRY(cudaMemsetAsync(cstart.p, 0, 8, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(cstart.p + 1, n_dev.p, 8, cudaMemcpyDeviceToDevice, s));
+    }
+    const u64 ovf_cap = 64;
+    DevBuf<ulonglong2> ovf(&ws, ovf_cap);
+    out.keys.reset(&ws, n_cap * key_bytes);
+    out.counts.reset(&ws, n_cap);
+    if (key_bytes == 8) launch_bucket_sort<u64>(cur, cstart.p, (u32)n_parents, key_bits, consumed, cap, out.keys.p, out.counts.p, ovf.p, ovf_cap, ctr.p, ws.sm_count, ws.device, s);
+    else launch_bucket_sort<Key128>(cur, cstart.p, (u32)n_parents, key_bits, consumed, cap, out.keys.p, out.counts.p, ovf.p, ovf_cap, ctr.p, ws.sm_count, ws.device, s);
+    ++ws.launches;
+    u64 h[2] = {0, 0};
+    GSB_CUDA_TRY(cudaMemcpyAsync(&h[0], n_dev.p, 8, cudaMemcpyDeviceToHost, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(&h[1], ctr.p, 8, cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    const u64 n = h[0];
+    if (h[1] > ovf_cap) return false;
+    if (h[1]) {
+        // buckets that did not fit: every one is a contiguous range of the final order, radix-sorted on its own
+        std::vector<ulonglong2> d(h[1]);
+        GSB_CUDA_TRY(cudaMemcpyAsync(d.data(), ovf.p, h[1] * sizeof(ulonglong2), cudaMemcpyDeviceToHost, s));
+        ws.sync();
+        for (const ulonglong2& r : d) {
+            DevBuf<u8> ka(&ws, r.y * key_bytes);
+            DevBuf<u64> ca(&ws, r.y);
+            u8* kp = out.keys.p + r.x * key_bytes;
+            u64* cp = out.counts.p + r.x;
+            const int where = sort_keys(ws, key_bytes, key_bits, kp, ka.p, cp, ca.p, r.y, nullptr, nullptr);
+            if (where) {
+                GSB_CUDA_TRY(cudaMemcpyAsync(kp, ka.p, r.y * key_bytes, cudaMemcpyDeviceToDevice, s));
+                GSB_CUDA_TRY(cudaMemcpyAsync(cp, ca.p, r.y * 8, cudaMemcpyDeviceToDevice, s));
+            }
+        }
+    }
+    out.m = n;
     return true;
 }
 

@@ -274,6 +274,44 @@ def test_partition_counting_any_bucket_geometry(k, min_count, max_slots, total_b
     assert (counts.n_instances, counts.n_distinct, counts.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
 
 
+@pytest.mark.parametrize("k,min_count,cap,bits", [(31, 2, 0, -1), (31, 1, 64, -1), (55, 1, 64, -1), (25, 1, 0, 3), (55, 2, 32, 6), (31, 1, 4, 1), (25, 2, 4, 8), (27, 1, 0, 0),
+                                                  (62, 1, 16, -1), (15, 1, 0, 22)])
+def test_pair_sort_geometry_does_not_matter(k, min_count, cap, bits):
+    # the survivors are ordered by most-significant-digit passes + a shared-memory sort per bucket; forced capacities and
+    # pass widths exercise one pass / two passes / three passes, buckets that overflow (radix-sorted on their own), the
+    # whole-array fallback (more than 64 overflowing buckets: cap 4 with 8 bits) and more bits than the key has
+    text = _random_reads(13 * k + min_count, 30_000, 12_000, 100, err=0.01)
+    want, ost = O.build_graph([(text, O.FASTQ)], k, min_count=min_count, threads=4)
+    try:
+        G.debug_set_pairsort(cap, bits)
+        sink, counts, stats = G.build_graph([(text, G.FASTQ)], k, min_count=min_count)
+    finally:
+        G.debug_set_pairsort(0, -1)
+    assert not _diff(sink.as_bytes(), want.files())
+    assert (counts.n_instances, counts.n_distinct, counts.n_kept) == (ost.n_instances, ost.n_distinct, ost.n_kept)
+
+
+def test_pair_sort_skewed_keys():
+    # low-complexity reads: most distinct edges share a long prefix (A..A / T..T), so the top bits of the real key are far
+    # from uniform -- oversize buckets take the radix sort, the rest the shared-memory sort; same files either way
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(6000):
+        tail = "".join("ACGT"[x] for x in rng.integers(0, 4, 24))
+        head = "A" * int(rng.integers(40, 76))
+        recs.append(f"@s{i}\n{head}{tail}\n+\n{'I' * (len(head) + 24)}\n")
+    text = "".join(recs).encode() + _random_reads(99, 20_000, 3_000, 100, err=0.01)
+    for k in (31, 55):
+        want, ost = O.build_graph([(text, O.FASTQ)], k, min_count=1, threads=4)
+        try:
+            G.debug_set_pairsort(256, -1)
+            sink, counts, stats = G.build_graph([(text, G.FASTQ)], k, min_count=1)
+        finally:
+            G.debug_set_pairsort(0, -1)
+        assert not _diff(sink.as_bytes(), want.files())
+        assert counts.n_kept == ost.n_kept
+
+
 @pytest.mark.parametrize("k,min_count", [(31, 2), (25, 1), (55, 2)])
 def test_legacy_lsd_counting_still_matches(k, min_count):
     # the round-1 counting path (full LSD sort of the raw keys + run-length reduce) stays as the overflow path of the

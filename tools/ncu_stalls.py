@@ -1,4 +1,5 @@
-"""Summarise an ncu report: headline metrics + stall samples per SASS instruction.  Usage: ncu_stalls.py report.ncu-rep [top]"""
+"""Summarise an ncu report: headline metrics of every captured launch + stall samples per SASS instruction of the first
+launch whose kernel name contains `match` (default: the first launch).  Usage: ncu_stalls.py report.ncu-rep [top] [match]"""
 import csv
 import io
 import subprocess
@@ -6,6 +7,7 @@ import sys
 
 rep = sys.argv[1]
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+match = sys.argv[3] if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[0]
@@ -27,15 +29,17 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 h = None
 data = []
+take = match is None
 for r in rows:
-    if r and r[0] == "Address":
-        h = r
-        continue
     if r and r[0] == "Kernel Name":
         if data:
             break
+        take = match is None or (len(r) > 1 and match in r[1])
         continue
-    if h and len(r) == len(h):
+    if r and r[0] == "Address":
+        h = r
+        continue
+    if take and h and len(r) == len(h):
         data.append(r)
 i_s, i_src = h.index("# Samples"), h.index("Source")
 cols = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
