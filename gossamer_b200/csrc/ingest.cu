@@ -395,16 +395,46 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
     typedef WindowOps<K> WO;
     const int passes = PASSES > 0 ? PASSES : (PASSES < 0 ? (1 << kTopHistBits) / 256 : passes_rt);
     extern __shared__ u32 hist_s[];                            // [passes][256] (PASSES < 0: [2^kTopHistBits])
-    __shared__ u32 warp_cnt[kExThreads / 32];
-    __shared__ u64 base_s;
+    // The stream words a tile needs (its own 32-33 words and the two in front) are staged in shared memory ONE TILE AHEAD:
+    // ncu showed every warp waiting on its own first-touch loads of codes / valid (long scoreboard 38 % of the stall
+    // samples).  Everything that is reused across iterations is double-buffered, which leaves two barriers per tile.
+    constexpr int kStage = kExThreads * kExItems / 32 + 4;     // words per tile incl. the two leading ones and misalignment
+    __shared__ u64 codes_s[2][kStage];
+    __shared__ u32 valid_s[2][kStage];
+    __shared__ u32 warp_cnt[2][kExThreads / 32];
+    __shared__ u64 base_s[2];
     for (int i = threadIdx.x; i < passes * 256; i += kExThreads) hist_s[i] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 wmask = w >= 64 ? ~0ull : ((1ull << w) - 1);
     const u32 lt = (1u << lane) - 1;
     constexpr u64 kSpan = (u64)kExThreads * kExItems;
-
-    for (u64 tile = p_begin + (u64)blockIdx.x * kSpan; tile < p_end; tile += (u64)gridDim.x * kSpan) {
+    const int t = threadIdx.x;
+    // thread t < kStage fetches code word t of a tile, thread 64 + t valid word t (two different warps)
+    const bool f_code = t < kStage, f_valid = t >= 64 && t < 64 + kStage;
+    const int f_idx = f_code ? t : t - 64;
+    auto fetch = [&](u64 tile, u64& c, u32& v) {
+        c = 0; v = 0;
+        if (tile >= p_end) return;
+        const u64 b = (tile >> 5) - 2 + (u64)f_idx;            // tile >= 64: the stream starts with 64 pad symbols
+        if ((b << 5) >= p_end) return;
+        if (f_code) c = codes[b];
+        if (f_valid) v = valid[b];
+    };
+    u64 tile = p_begin + (u64)blockIdx.x * kSpan;
+    {
+        u64 c; u32 v;
+        fetch(tile, c, v);
+        if (f_code) codes_s[0][f_idx] = c;
+        if (f_valid) valid_s[0][f_idx] = v;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (; tile < p_end; tile += (u64)gridDim.x * kSpan, cur ^= 1) {
+        u64 pre_c; u32 pre_v;
+        fetch(tile + (u64)gridDim.x * kSpan, pre_c, pre_v);    // in flight during this tile's arithmetic
+        const u64* cs = codes_s[cur];
+        const u32* vs_ = valid_s[cur];
+        const u64 b0 = (tile >> 5) - 2;
         K x[kExItems];
         u32 ballot[kExItems];
         u32 wtot = 0;
@@ -414,13 +444,13 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
             bool ok = false;
             x[it] = KO::make(0, 0);
             if (p < p_end) {
-                const u64 b = p >> 5; const int j = (int)(p & 31);
+                const int b = (int)((p >> 5) - b0); const int j = (int)(p & 31);
                 const int vs = 31 - j;
-                u64 v = ((u64)valid[b] >> vs) | ((u64)valid[b - 1] << (32 - vs));
-                if (vs) v |= (u64)valid[b - 2] << (64 - vs);
+                u64 v = ((u64)vs_[b] >> vs) | ((u64)vs_[b - 1] << (32 - vs));
+                if (vs) v |= (u64)vs_[b - 2] << (64 - vs);
                 ok = (v & wmask) == wmask;
                 if (ok) {
-                    x[it] = WO::load(codes, b, 2 * vs, w);
+                    x[it] = WO::load(cs, (u64)b, 2 * vs, w);
                     const K r = WO::rc(x[it], w);
                     if (MODE == GSB_KIND_GRAPH) {               // fold the two strands
                         if (KO::lt(r, x[it])) x[it] = r;
@@ -435,20 +465,23 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
             ballot[it] = __ballot_sync(0xffffffffu, ok);
             wtot += __popc(ballot[it]);
         }
-        if (lane == 0) warp_cnt[warp] = wtot;
+        if (lane == 0) warp_cnt[cur][warp] = wtot;
+        if (f_code) codes_s[cur ^ 1][f_idx] = pre_c;
+        if (f_valid) valid_s[cur ^ 1][f_idx] = pre_v;
         __syncthreads();
         if (threadIdx.x == 0) {
             u32 tot = 0;
 #pragma unroll
-            for (int i = 0; i < kExThreads / 32; ++i) { u32 c = warp_cnt[i]; warp_cnt[i] = tot; tot += c; }
-            base_s = tot ? atomicAdd(cursor, (u64)tot) : 0;
+            for (int i = 0; i < kExThreads / 32; ++i) { u32 c = warp_cnt[cur][i]; warp_cnt[cur][i] = tot; tot += c; }
+            base_s[cur] = tot ? atomicAdd(cursor, (u64)tot) : 0;
         }
         __syncthreads();
-        u32 slot = warp_cnt[warp];
+        u32 slot = warp_cnt[cur][warp];
+        const u64 base = base_s[cur];
 #pragma unroll
         for (int it = 0; it < kExItems; ++it) {
             if ((ballot[it] >> lane) & 1u) {
-                const u64 idx = base_s + (u64)(slot + __popc(ballot[it] & lt));
+                const u64 idx = base + (u64)(slot + __popc(ballot[it] & lt));
                 if (idx < capacity) out[idx] = x[it];
                 else st->error = GSB_PE_KEY_OVERFLOW;
                 if (PASSES < 0) {
@@ -462,7 +495,6 @@ __global__ void __launch_bounds__(kExThreads) extract_kernel(const u64* __restri
             }
             slot += __popc(ballot[it]);
         }
-        __syncthreads();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * 256; i += kExThreads) {

@@ -6,6 +6,7 @@ import ctypes as C
 import hashlib
 import os
 import struct
+import time
 
 import numpy as np
 import pytest
@@ -57,6 +58,7 @@ class HashSink:
 
 
 def _build(kind, k, genome, read_len, n_reads, err, chunk_reads, min_count=1, max_batch_keys=0):
+    t_start = time.perf_counter()
     b = G.Builder(kind, k, min_count=min_count, max_batch_keys=max_batch_keys)
     done = 0
     i = 0
@@ -67,10 +69,16 @@ def _build(kind, k, genome, read_len, n_reads, err, chunk_reads, min_count=1, ma
         done += n
         i += 1
     counts = b.finish()
-    st = b.stats()
     sink = HashSink()
     b.emit("out", sink)
+    st = b.stats()
     b.close()
+    d = st.as_dict()
+    print(f"[big] kind={kind} k={k} m={min_count} reads={n_reads} x {read_len} max_batch_keys={max_batch_keys}: "
+          f"{counts.n_instances} instances, {counts.n_distinct} distinct, {counts.n_kept} kept, {st.n_batches} batches, "
+          f"{time.perf_counter() - t_start:.1f} s wall (read simulation included); device ms: "
+          + ", ".join(f"{key[3:]} {d[key]:.1f}" for key in ("ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_merge", "ms_unfold", "ms_emit"))
+          + f"; hbm peak {st.hbm_peak_bytes / 1e9:.1f} GB; bytes out {st.bytes_out}", flush=True)
     return counts, st, sink
 
 
@@ -80,7 +88,7 @@ def test_config2_full_size_single_vs_multi_batch():
     c1, st1, s1 = _build(G.GRAPH, 31, g, 150, 1_666_667, 0.01, 600_000, min_count=2)
     assert c1.n_instances == 1_666_667 * 119 * 2 == 396_666_746
     assert c1.n_kept < c1.n_distinct < c1.n_instances and st1.n_batches == 1
-    c2, st2, s2 = _build(G.GRAPH, 31, g, 150, 1_666_667, 0.01, 600_000, min_count=2, max_batch_keys=150_000_000)
+    c2, st2, s2 = _build(G.GRAPH, 31, g, 150, 1_666_667, 0.01, 600_000, min_count=2, max_batch_keys=60_000_000)     # 198.3 M folded keys: four batches
     assert st2.n_batches >= 3
     assert (c2.n_instances, c2.n_distinct, c2.n_kept) == (c1.n_instances, c1.n_distinct, c1.n_kept)
     assert s1.digest() == s2.digest()                                     # merging batches changes no byte
@@ -116,7 +124,7 @@ def test_config4_scaled_128bit_keys():
     n_reads = 5_000_000
     c1, st1, s1 = _build(G.GRAPH, 55, g, 150, n_reads, 0.01, 1_000_000)
     assert c1.n_instances == n_reads * 95 * 2 and st1.sort_key_bytes == 16
-    c2, st2, s2 = _build(G.GRAPH, 55, g, 150, n_reads, 0.01, 1_000_000, max_batch_keys=300_000_000)
+    c2, st2, s2 = _build(G.GRAPH, 55, g, 150, n_reads, 0.01, 1_000_000, max_batch_keys=150_000_000)                 # 475 M folded keys: four batches
     assert st2.n_batches >= 3 and s1.digest() == s2.digest()
 
 
