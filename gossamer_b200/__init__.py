@@ -50,7 +50,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ms_h2d", "ms_scan", "ms_extract", "ms_sort", "ms_reduce", "ms_merge", "ms_emit",
                                           "ms_d2h", "ms_exchange", "ms_sort_sweeps", "ms_all_to_all", "ms_unfold")] + \
                [(n, C.c_uint64) for n in ("exchange_bytes_sent", "exchange_peer_memory", "bytes_in", "bytes_out", "n_symbols", "sort_key_bytes", "sort_passes",
-                                          "sort_passes_model", "n_batches", "kernel_launches", "hbm_peak_bytes", "n_sorted_keys", "device_allocs")]
+                                          "sort_passes_model", "n_batches", "kernel_launches", "hbm_peak_bytes", "n_sorted_keys", "device_allocs")] + \
+               [(n, C.c_double) for n in ("ms_exchange_agree", "ms_exchange_survivors", "ms_exchange_publish")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

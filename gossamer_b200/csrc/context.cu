@@ -155,6 +155,7 @@ struct gsb_ctx {
     // host<->device staging
     u8* pinned = nullptr;
     size_t pinned_bytes = 0;
+    EmitRing ring;                   // overlapped device -> sink delivery of gsb_emit (created on first use)
     DevBuf<u8> text_dev;
     size_t text_cap = 0;
     // GSB_BLOCK_ASYNC: two text buffers filled by a copy stream while the main stream works on the other one
@@ -628,6 +629,7 @@ void gsb_destroy(gsb_ctx* c) {
     c->timer.destroy();
     if (c->user_e0) cudaEventDestroy(c->user_e0);
     if (c->user_e1) cudaEventDestroy(c->user_e1);
+    c->ring.destroy(c->ws);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ws.stream) { cudaStreamSynchronize(c->ws.stream); c->ws.trim(); cudaStreamDestroy(c->ws.stream); c->ws.stream = nullptr; }
     delete c;
@@ -685,7 +687,9 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
             if (c->comm) {
                 const u64 mine[3] = {spilled, self_rc_all, c->n_keys};
                 std::vector<u64> all;
+                c->timer.start();
                 exchange_allgather_u64(c->comm, c->ws, mine, 3, all);
+                c->timer.stop(c->stats.ms_exchange_agree);
                 spilled = 0; self_rc_all = 0; n_total = 0;
                 for (int r = 0; r < exchange_size(c->comm); ++r) {
                     spilled += all[3 * r]; self_rc_all += all[3 * r + 1]; n_total += all[3 * r + 2];
@@ -829,7 +833,7 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                 u8* rk = nullptr; u64* rc = nullptr;
                 std::vector<u64> totals;
                 const bool ok = exchange_pairs_p2p(c->comm, c->ws, kb, uk.p, uc.p, m + n_rc, &rk, &rc, &totals);
-                c->timer.stop(c->stats.ms_exchange);
+                c->timer.stop(c->stats.ms_exchange_survivors);
                 if (ok) {
                     uk.free(); uc.free();
                     const u64 mine = totals[exchange_rank(c->comm)];
@@ -865,7 +869,7 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                     if (exchanged_instances) c->counts.n_distinct = dist;
                     stats_summed = true;
                     c->dist_ready = true;
-                    c->timer.stop(c->stats.ms_exchange);
+                    c->timer.stop(c->stats.ms_exchange_publish);
                     done = true;
                 }
             }
@@ -908,6 +912,7 @@ int gsb_emit(gsb_ctx* c, const char* prefix, const gsb_sink* sink) {
         if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_emit before gsb_finish_counting"};
         Emitter em;
         em.ws = &c->ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
+        if (sink) { c->ring.create(c->ws); c->ring.drop(); em.ring = &c->ring; }
         if (c->comm && !c->gathered && !c->dist_ready) {
             // peer memory is not available here: fall back to shipping every slice to rank 0
             c->timer.start();
@@ -925,6 +930,7 @@ int gsb_emit(gsb_ctx* c, const char* prefix, const gsb_sink* sink) {
             else write_kmer_set_files(c, em, prefix);
         }
         c->timer.stop(c->stats.ms_emit);
+        em.flush();                                              // the last chunks cross PCIe and reach the sink
         c->stats.bytes_out += em.bytes_out;
     });
 }

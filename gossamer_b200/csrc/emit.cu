@@ -47,11 +47,82 @@ void Emitter::put_host(const std::string& name, const void* data, u64 len) {
     if (sink->close(sink->user, h) != 0) sink_fail("close", name);
 }
 
+void EmitRing::create(Workspace& ws) {
+    if (created) return;
+    GSB_CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    for (int i = 0; i < kSlots; ++i) {
+        dev[i] = (u8*)ws.alloc(kChunk);
+        GSB_CUDA_TRY(cudaMallocHost((void**)&host[i], kChunk));
+        GSB_CUDA_TRY(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+        GSB_CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    created = true;
+}
+
+void EmitRing::drop() {
+    if (!created) return;
+    cudaStreamSynchronize(copy);
+    for (int i = 0; i < kSlots; ++i) pend[i] = Pending();
+    head = 0;
+}
+
+void EmitRing::destroy(Workspace& ws) {
+    if (!created) return;
+    drop();
+    for (int i = 0; i < kSlots; ++i) {
+        if (dev[i]) ws.release(dev[i], kChunk);
+        if (host[i]) cudaFreeHost(host[i]);
+        cudaEventDestroy(ready[i]); cudaEventDestroy(done[i]);
+        dev[i] = nullptr; host[i] = nullptr;
+    }
+    cudaStreamDestroy(copy);
+    created = false;
+}
+
+void Emitter::ring_deliver(int slot) {
+    EmitRing::Pending& p = ring->pend[slot];
+    if (!p.busy) return;
+    GSB_CUDA_TRY(cudaEventSynchronize(ring->done[slot]));
+    p.busy = false;
+    if (!p.prefix.empty()) memcpy(ring->host[slot], p.prefix.data(), p.prefix.size());
+    if (p.len && sink->pwrite(sink->user, p.handle, p.file_off, ring->host[slot], p.len) != 0) sink_fail("pwrite", p.name);
+    if (p.close && sink->close(sink->user, p.handle) != 0) sink_fail("close", p.name);
+}
+
+void Emitter::flush() {
+    if (!ring || !sink) return;
+    for (int i = 0; i < EmitRing::kSlots; ++i) ring_deliver((ring->head + i) % EmitRing::kSlots);   // oldest first
+}
+
+// [file_off, file_off + len) of an open file from device memory, through the ring; the handle is closed after the last chunk
+void Emitter::ring_put(void* handle, const std::string& name, u64 file_off, const void* dev, u64 len, const void* host_prefix, u64 prefix_len) {
+    for (u64 off = 0; off < len || off == 0; off += EmitRing::kChunk) {
+        const u64 chunk = std::min<u64>(EmitRing::kChunk, len - off);
+        const int slot = ring->head;
+        ring_deliver(slot);                                         // the slot's previous chunk goes to the sink first
+        ring->head = (ring->head + 1) % EmitRing::kSlots;
+        if (chunk) {
+            GSB_CUDA_TRY(cudaMemcpyAsync(ring->dev[slot], (const u8*)dev + off, chunk, cudaMemcpyDeviceToDevice, ws->stream));
+            GSB_CUDA_TRY(cudaEventRecord(ring->ready[slot], ws->stream));
+            GSB_CUDA_TRY(cudaStreamWaitEvent(ring->copy, ring->ready[slot], 0));
+            GSB_CUDA_TRY(cudaMemcpyAsync(ring->host[slot], ring->dev[slot], chunk, cudaMemcpyDeviceToHost, ring->copy));
+        }
+        GSB_CUDA_TRY(cudaEventRecord(ring->done[slot], ring->copy));
+        EmitRing::Pending& p = ring->pend[slot];
+        p.busy = true; p.handle = handle; p.name = name; p.file_off = file_off + off; p.len = chunk;
+        p.close = off + chunk >= len;
+        p.prefix.clear();
+        if (off < prefix_len) p.prefix.assign((const u8*)host_prefix + off, (const u8*)host_prefix + std::min<u64>(prefix_len, off + chunk));
+        if (len == 0) break;
+    }
+}
+
 void Emitter::put_device(const std::string& name, const void* dev, u64 len, const void* host_prefix, u64 prefix_len) {
     bytes_out += len;
     if (!sink) return;
     void* h = nullptr;
     if (sink->open(sink->user, name.c_str(), len, &h) != 0) sink_fail("open", name);
+    if (ring) { ring_put(h, name, 0, dev, len, host_prefix, prefix_len); return; }
     for (u64 off = 0; off < len; off += pinned_bytes) {
         u64 chunk = std::min<u64>(pinned_bytes, len - off);
         GSB_CUDA_TRY(cudaMemcpyAsync(pinned, (const u8*)dev + off, chunk, cudaMemcpyDeviceToHost, ws->stream));
@@ -69,6 +140,7 @@ void Emitter::put_device_at(const std::string& name, u64 total, u64 offset, cons
     if (!sink || !len) return;
     void* h = nullptr;
     if (sink->open(sink->user, name.c_str(), total, &h) != 0) sink_fail("open", name);
+    if (ring) { ring_put(h, name, offset, dev, len, nullptr, 0); return; }
     for (u64 off = 0; off < len; off += pinned_bytes) {
         u64 chunk = std::min<u64>(pinned_bytes, len - off);
         GSB_CUDA_TRY(cudaMemcpyAsync(pinned, (const u8*)dev + off, chunk, cudaMemcpyDeviceToHost, ws->stream));

@@ -185,12 +185,39 @@ void merge_disjoint_runs(Workspace& ws, int key_bytes, const void* ka, const u64
                          void* out_keys, u64* out_counts);
 
 // ---- emit.cu ---------------------------------------------------------------------------------
+// Device -> sink pipeline of the emitter: a ring of staging slots (device + pinned host) and a copy stream.  A file chunk
+// is copied device-to-device into a slot on the library's stream (the producer's buffer is free again at once), crosses
+// PCIe on the copy stream while the next emit kernels run, and is handed to the sink when its slot comes round again or at
+// Emitter::flush() -- the analogue of the reference's writer threads behind Graph::Builder (src/Graph.cc:148-150).
+struct EmitRing {
+    static const int kSlots = 8;
+    static const size_t kChunk = 16ull << 20;
+    struct Pending {
+        bool busy = false, close = false;
+        void* handle = nullptr;
+        std::string name;
+        u64 file_off = 0, len = 0;
+        std::vector<u8> prefix;        // host bytes that override the start of this chunk (file headers)
+    };
+    cudaStream_t copy = nullptr;
+    u8* dev[kSlots] = {};
+    u8* host[kSlots] = {};
+    cudaEvent_t ready[kSlots], done[kSlots];
+    Pending pend[kSlots];
+    int head = 0;
+    bool created = false;
+    void create(Workspace& ws);
+    void destroy(Workspace& ws);
+    void drop();                   // forget everything pending (after an error); waits for the copy stream
+};
+
 struct Emitter {
     Workspace* ws;
     const gsb_sink* sink;          // nullptr: build on the device, count the bytes, drop
     u64 bytes_out = 0;
-    u8* pinned = nullptr;          // staging for device -> sink copies
+    u8* pinned = nullptr;          // staging for device -> sink copies when there is no ring
     size_t pinned_bytes = 0;
+    EmitRing* ring = nullptr;      // optional: overlapped delivery (gsb_emit)
     // whole file from host memory
     void put_host(const std::string& name, const void* data, u64 len);
     // whole file = optional host prefix that overrides the first prefix_len bytes + device payload
@@ -198,6 +225,11 @@ struct Emitter {
     // one piece of a file of `total` bytes (multi-GPU emission: every rank hands over its own pieces)
     void put_device_at(const std::string& name, u64 total, u64 offset, const void* dev, u64 len);
     void put_host_at(const std::string& name, u64 total, u64 offset, const void* data, u64 len);
+    // hands every chunk still in the ring to the sink; must be called before the sink's owner looks at the files
+    void flush();
+private:
+    void ring_put(void* handle, const std::string& name, u64 file_off, const void* dev, u64 len, const void* host_prefix, u64 prefix_len);
+    void ring_deliver(int slot);
 };
 
 struct U128 { u64 lo, hi; };

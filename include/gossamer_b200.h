@@ -114,6 +114,10 @@ typedef struct gsb_stats {
                                    = n_instances / 2, because the two strands are folded) */
     uint64_t device_allocs;     /* cudaMalloc calls made by this context so far (NOT reset by gsb_reset): a steady-state
                                    step makes none -- every buffer comes from the context's caching allocator */
+    /* multi-GPU: parts of ms_exchange (the rest is the instance exchange itself: local first pass, histograms, pull pass) */
+    double ms_exchange_agree;     /* the collective that agrees on the finish path */
+    double ms_exchange_survivors; /* re-partition of the surviving (key,count) pairs into the final order's slices */
+    double ms_exchange_publish;   /* statistics all-gather / barrier that publishes the slices */
 } gsb_stats;
 
 /* Replaces: GossCmdFactoryBuildGraph::create parameter checks (src/GossCmdBuildGraph.cc:428-477)
