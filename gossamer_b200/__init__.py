@@ -498,6 +498,7 @@ def debug_sort_keys(lo, hi, key_bits, device=0):
 
 
 LEGACY_COUNTING = 1 << 16
+SAMPLED_SURVIVORS = 1 << 17      # multi-GPU: re-partition the survivors with sampled splitters (the fallback of the pair-sort exchange)
 
 
 def debug_set_tuning(tuning_id):

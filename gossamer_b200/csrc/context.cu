@@ -192,6 +192,7 @@ namespace {
 
 // test / profiling switch (gsb_debug_set_tuning bit 16): count by the full LSD sort of raw keys instead of by partitioning
 int g_legacy_counting = 0;
+int g_sampled_survivors = 0;        // test switch: re-partition the survivors with sampled splitters (the fallback path)
 
 thread_local std::string g_create_error;
 
@@ -813,7 +814,38 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
             }
             // acc: final counts, filtered, folded (graphs); sorted by key unless acc_unsorted
             bool done = false;
-            if (repartition && exchange_peer_memory_usable(c->comm)) {
+            // publishing the slices: the global view, the summed statistics, and the barrier that makes every slice sorted and
+            // in place before anyone reads a neighbour's -- one all-gather
+            auto publish = [&](const std::vector<u64>& totals) {
+                c->timer.start();
+                exchange_view(c->comm, c->key_bytes, totals, &c->dist);
+                const u64 mine_stats[2] = {c->counts.n_instances, exchanged_instances ? c->counts.n_distinct : 0};
+                std::vector<u64> all_stats;
+                exchange_allgather_u64(c->comm, c->ws, mine_stats, 2, all_stats);
+                u64 inst = 0, dist = 0;
+                for (int r = 0; r < exchange_size(c->comm); ++r) { inst += all_stats[2 * r]; dist += all_stats[2 * r + 1]; }
+                c->counts.n_instances = inst;
+                if (exchanged_instances) c->counts.n_distinct = dist;
+                stats_summed = true;
+                c->dist_ready = true;
+                c->timer.stop(c->stats.ms_exchange_publish);
+            };
+            if (repartition && exchange_peer_memory_usable(c->comm) && !g_sampled_survivors) {
+                // The survivors (folded for graphs: the reverse complements join here) go to the ranks that own their range
+                // of the FINAL order as the first pass of the pair sort, stored straight into the owners' windows; each
+                // owner finishes the sort of its slice locally (exchange.cu).
+                c->timer.start();
+                ReducedRun sorted;
+                std::vector<u64> totals;
+                const bool ok = exchange_pairs_msd(c->comm, c->ws, c->key_bytes, c->key_bits, c->acc.keys.p, c->acc.counts.p, c->acc.m, c->fold_w, sorted, &totals);
+                c->timer.stop(c->stats.ms_exchange_survivors);
+                if (ok) {
+                    c->acc = std::move(sorted);
+                    publish(totals);
+                    done = true;
+                }
+            }
+            if (!done && repartition && exchange_peer_memory_usable(c->comm)) {
                 // U = acc (++ rc(acc) for graphs) is built unsorted, every pair is stored straight into the window of the rank
                 // that owns its range of the FINAL order (splitters sampled from U itself, so the slices are balanced), and
                 // the owner sorts what it received -- the slice is then already published for the emitters.
@@ -856,20 +888,7 @@ int gsb_finish_counting(gsb_ctx* c, gsb_counts* out) {
                         c->acc.keys = std::move(bk); c->acc.counts = std::move(bc); c->acc.m = mine;
                     }
                     c->timer.stop(c->stats.ms_unfold);
-                    c->timer.start();
-                    exchange_view(c->comm, kb, totals, &c->dist);
-                    // one all-gather: the global statistics, and the barrier that makes every slice sorted and in place
-                    // before anyone reads a neighbour's
-                    const u64 mine_stats[2] = {c->counts.n_instances, exchanged_instances ? c->counts.n_distinct : 0};
-                    std::vector<u64> all_stats;
-                    exchange_allgather_u64(c->comm, c->ws, mine_stats, 2, all_stats);
-                    u64 inst = 0, dist = 0;
-                    for (int r = 0; r < exchange_size(c->comm); ++r) { inst += all_stats[2 * r]; dist += all_stats[2 * r + 1]; }
-                    c->counts.n_instances = inst;
-                    if (exchanged_instances) c->counts.n_distinct = dist;
-                    stats_summed = true;
-                    c->dist_ready = true;
-                    c->timer.stop(c->stats.ms_exchange_publish);
+                    publish(totals);
                     done = true;
                 }
             }
@@ -1332,7 +1351,7 @@ int gsb_debug_set_partition(int max_slots, int total_bits) { partition_set_debug
 
 int gsb_debug_set_pairsort(int cap, int bits) { pairsort_set_debug((u32)(cap < 0 ? 0 : cap), bits); return GSB_OK; }
 
-int gsb_debug_set_tuning(int id) { g_legacy_counting = (id >> 16) & 1; sort_set_tuning(id & 0xFFFF); return GSB_OK; }
+int gsb_debug_set_tuning(int id) { g_legacy_counting = (id >> 16) & 1; g_sampled_survivors = (id >> 17) & 1; sort_set_tuning(id & 0xFFFF); return GSB_OK; }
 
 int gsb_debug_emit_sparse_array(int device, const uint64_t* key_lo, const uint64_t* key_hi, uint64_t m,
                                 uint64_t universe_lo, uint64_t universe_hi, uint64_t m_est,

@@ -840,6 +840,75 @@ bool exchange_pairs_p2p(Exchange* x, Workspace& ws, int key_bytes, const void* k
     return true;
 }
 
+// The same job as exchange_pairs_p2p -- every rank ends up with the r-th contiguous slice of the global order, sorted, in
+// its window -- as the FIRST PASS OF THE PAIR SORT (partition.cu): the pairs are split by the top 10 bits of the real key,
+// the 1024 children are dealt to the ranks as contiguous ranges of nearly equal size (one all-gather of the per-rank
+// histograms; every rank derives the same plan on the device), each child's run is stored straight into its owner's
+// window, and the owner finishes the sort locally (remaining passes + shared-memory sort per bucket).  No samples, no
+// splitters, one host synchronisation (the totals) instead of three.
+//   keys / counts [m]: this rank's survivors (folded when fold_w > 0: the reverse complements are added here).
+//   On success: sorted holds this rank's slice (also copied into the window, layout of exchange_view), totals_out[r] the
+//   slice sizes.  Collective; false (on every rank alike, nothing changed) if peer memory cannot be used or a slice would not
+//   fit -- the caller then takes exchange_pairs_p2p.
+bool exchange_pairs_msd(Exchange* x, Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w,
+                        ReducedRun& sorted, std::vector<u64>* totals_out) {
+    if (!x->p2p_usable || x->n > kMaxRanks) return false;
+    const int n = x->n;
+    cudaStream_t s = ws.stream;
+    NcclApi& api = nccl();
+    const int bits0 = key_bits < 10 ? key_bits : 10;
+    const u32 C = 1u << bits0;
+    const u32 eb = pairsort_elem_bytes(key_bytes);
+    const u64 n_cap_local = fold_w ? 2 * m : m;
+    const u32 cstride = 32;
+    DevBuf<u8> elems(&ws, n_cap_local * eb + 64);
+    DevBuf<u64> n_dev(&ws, 1), hist_mine(&ws, C), hist_all(&ws, (size_t)C * n), cursor(&ws, (size_t)C * cstride), totals(&ws, kMaxRanks + 2), cstart_local(&ws, (size_t)C + 1);
+    DevBuf<u8> owner(&ws, C);
+    GSB_CUDA_TRY(cudaMemsetAsync(hist_mine.p, 0, hist_mine.bytes(), s));
+    pairsort_pack(ws, key_bytes, key_bits, keys, counts, m, fold_w, elems.p, n_dev.p, hist_mine.p, bits0);
+    // (the all-gather also orders every peer's stores into this rank's window behind this rank's last use of it)
+    check(api.AllGather(hist_mine.p, hist_all.p, C, ncclUint64, x->comm, s), "ncclAllGather(pair histograms)");
+    u32* range = (u32*)(totals.p + kMaxRanks);
+    pairsort_plan_owners(ws, hist_all.p, n, x->rank, bits0, cursor.p, cstride, owner.p, totals.p, range, cstart_local.p);
+    u64 h[kMaxRanks + 2];
+    GSB_CUDA_TRY(cudaMemcpyAsync(h, totals.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    ws.sync();
+    std::vector<u64> total(h, h + n), need_all(n);
+    const u32 clo = (u32)(h[kMaxRanks] & 0xffffffffu), chi = (u32)(h[kMaxRanks] >> 32);
+    for (int r = 0; r < n; ++r) need_all[r] = std::max<u64>(total[r] * eb, align256(total[r] * key_bytes) + total[r] * 8) + 256;
+    if (!ensure_windows(x, ws, need_all[x->rank], &need_all)) { x->p2p_usable = false; return false; }
+    void* bases[kMaxRanks];
+    for (int r = 0; r < n; ++r) bases[r] = x->peer_ptr[r];
+    pairsort_scatter_to_peers(ws, key_bytes, key_bits, elems.p, n_cap_local, n_dev.p, bits0, cursor.p, cstride, owner.p, bases, n);
+    // barrier on the stream: what follows runs after every rank's stores have landed
+    DevBuf<u64> flag(&ws, 2);
+    GSB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, 16, s));
+    check(api.AllReduce(flag.p, flag.p + 1, 1, ncclUint64, ncclSum, x->comm, s), "ncclAllReduce(barrier)");
+    elems.free();
+    const u64 mine = total[x->rank];
+    if (mine == 0) {
+        sorted.keys.reset(&ws, 0); sorted.counts.reset(&ws, 0); sorted.m = 0;
+    } else {
+        const u64 n_parents = chi - clo;
+        // the remaining passes: as if all 2^bits0 children were as full as this rank's (no collective below this point)
+        PairSortPlan plan = pairsort_plan(key_bytes, key_bits, mine * C / std::max<u64>(1, n_parents), bits0);
+        DevBuf<u8> other(&ws, plan.levels > 1 ? mine * eb + 64 : 1);
+        if (!pairsort_finish(ws, key_bytes, key_bits, x->recv_buf, other.p, mine, nullptr, cstart_local, n_parents, bits0, plan, 1, nullptr, sorted)) {
+            // the data defeat the bucket geometry: radix sort of what arrived (converted in place by the bucket kernel)
+            DevBuf<u8> kb2(&ws, mine * key_bytes);
+            DevBuf<u64> cb2(&ws, mine);
+            const int where = sort_keys(ws, key_bytes, key_bits, sorted.keys.p, kb2.p, sorted.counts.p, cb2.p, mine, nullptr, nullptr);
+            if (where) { sorted.keys = std::move(kb2); sorted.counts = std::move(cb2); }
+            sorted.m = mine;
+        }
+        // the slice, published in the window for the emitters of the other ranks
+        GSB_CUDA_TRY(cudaMemcpyAsync(x->recv_buf, sorted.keys.p, mine * key_bytes, cudaMemcpyDeviceToDevice, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(x->recv_buf + align256(mine * key_bytes), sorted.counts.p, mine * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    *totals_out = total;
+    return true;
+}
+
 // The global view of slices that already sit in the windows (layout of exchange_pairs_p2p / exchange_publish).
 void exchange_view(const Exchange* x, int key_bytes, const std::vector<u64>& totals, DistRun* out) {
     const int n = x->n;

@@ -60,6 +60,11 @@ bool exchange_peer_memory_usable(const Exchange* x);
 // window, arbitrary order), totals[r] = pairs received by rank r.  false: peer memory unavailable.
 bool exchange_pairs_p2p(Exchange* x, Workspace& ws, int key_bytes, const void* keys, const u64* counts, u64 n_pairs,
                         u8** recv_keys, u64** recv_counts, std::vector<u64>* totals);
+// Collective.  The same result with the first pass of the pair sort (partition.cu) crossing NVLink: children of the top key
+// bits are dealt to the ranks as balanced contiguous ranges (one all-gather of histograms, no samples); `sorted` = this
+// rank's slice, ordered, also copied into its window.  false: peer memory unavailable (take exchange_pairs_p2p).
+bool exchange_pairs_msd(Exchange* x, Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w,
+                        ReducedRun& sorted, std::vector<u64>* totals);
 // global view of slices already sitting in the windows (layout of exchange_pairs_p2p / exchange_publish)
 void exchange_view(const Exchange* x, int key_bytes, const std::vector<u64>& totals, DistRun* out);
 // Collective: n_words u64 from every rank, concatenated in rank order on the host of every rank.

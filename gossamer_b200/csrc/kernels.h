@@ -167,6 +167,17 @@ void partition_pull_level(Workspace& ws, int key_bytes, const void* const* src_b
 // (key, count) pairs with distinct keys, arbitrary order -> ordered by key (most-significant-digit passes + a shared-memory
 // sort per bucket, partition.cu); fold_w > 0: the reverse complements join the set first.  false = declined, radix-sort instead.
 bool sort_pairs_msd(Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w, ReducedRun& out);
+// its pieces (the multi-GPU re-partition of the survivors runs the first pass across NVLink, exchange.cu)
+struct PairSortPlan { int bits = 0, levels = 0; int lb[8] = {0, 0, 0, 0, 0, 0, 0, 0}; u32 cap = 0; };
+u32 pairsort_elem_bytes(int key_bytes);
+PairSortPlan pairsort_plan(int key_bytes, int key_bits, u64 n_cap, int first_bits);
+void pairsort_pack(Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w, void* elems, u64* n_dev, u64* hist0, int bits0);
+bool pairsort_finish(Workspace& ws, int key_bytes, int key_bits, void* cur, void* other, u64 n_cap, const u64* n_dev, DevBuf<u64>& cstart, u64 n_parents,
+                     int consumed, const PairSortPlan& plan, int first_level, const u64* hist_first, ReducedRun& out);
+void pairsort_plan_owners(Workspace& ws, const u64* hist_all, int n_ranks, int rank, int bits0, u64* cursor, u32 cstride, u8* owner, u64* totals, u32* range,
+                          u64* cstart_local);
+void pairsort_scatter_to_peers(Workspace& ws, int key_bytes, int key_bits, const void* elems, u64 n_cap, const u64* n_dev, int bits0, u64* cursor, u32 cstride,
+                               const u8* owner, void* const* peer_base, int n_peers);
 
 // ---- fold.cu ---------------------------------------------------------------------------------
 // Strand folding (graph mode): instances are counted as min(x, rc x); these restore both strands.

@@ -102,6 +102,7 @@ struct PartArgs {
     void* peer[kMaxRanks];
     int n_peers;
     const u32* abort;          // optional: non-zero = do nothing (the exchange found a window too small)
+    const u8* owner_tab;       // optional [2^bits]: the peer that owns each child (balanced ranges of the real key space)
 };
 
 // What a pass moves and which bits it splits by.
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
 #pragma unroll
             for (int j = 0; j < BPT; ++j) {
                 const u32 bin = (u32)(t * BPT + j);
-                const u32 owner = a.n_peers > 1 ? (u32)(((u64)(bin & mask) * (u32)a.n_peers) >> a.bits) : 0u;
+                const u32 owner = a.n_peers > 1 ? (a.owner_tab ? (u32)a.owner_tab[bin & mask] : (u32)(((u64)(bin & mask) * (u32)a.n_peers) >> a.bits)) : 0u;
                 gaddr_s[bin] = (u64)a.peer[owner] + (g[j] - (u64)run) * sizeof(K);
                 run += c[j];
             }
@@ -1198,68 +1199,82 @@ static void launch_bucket_sort(const void* elems, const u64* cstart, u32 n_bucke
 
 }  // namespace
 
-// m (key, count) pairs with distinct keys, arbitrary order -> ordered by key; fold_w > 0: the reverse complement of every
-// key that is not self-complementary joins the set first (fold.cu: the folded, filtered run becomes the reference's edge
-// set).  out is (re)allocated; out.m = pairs produced.  Returns false (nothing produced) when the data defeat the bucket
-// geometry -- the caller radix-sorts instead.
-bool sort_pairs_msd(Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w, ReducedRun& out) {
-    cudaStream_t s = ws.stream;
-    const u64 n_cap = fold_w ? 2 * m : m;
-    if (n_cap == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); out.m = 0; return true; }
-    const ElemKind ek = pair_kind(key_bytes);
-    const u32 eb = elem_bytes(ek);
-    u32 cap = key_bytes == 8 ? BucketSmem<u64>::kCap : BucketSmem<Key128>::kCap;
-    if (g_force_pair_cap >= 2 && g_force_pair_cap < cap) cap = g_force_pair_cap;
-    // bits so that the mean bucket is half the capacity; as few passes as 10 bits each allow
+// ---- pieces of the pair sort (also used by the multi-GPU re-partition of the survivors, exchange.cu) -------------------------
+u32 pairsort_elem_bytes(int key_bytes) { return elem_bytes(pair_kind(key_bytes)); }
+
+// Pass widths for n_cap pairs: buckets of half the capacity on average, as few passes as 10 bits each allow.
+// first_bits > 0 fixes the width of the first pass (the multi-GPU exchange splits by a fixed 2^first_bits children).
+PairSortPlan pairsort_plan(int key_bytes, int key_bits, u64 n_cap, int first_bits) {
+    PairSortPlan p;
+    p.cap = key_bytes == 8 ? BucketSmem<u64>::kCap : BucketSmem<Key128>::kCap;
+    if (g_force_pair_cap >= 2 && g_force_pair_cap < p.cap) p.cap = g_force_pair_cap;
     int bits = 0;
-    while (bits < 40 && (n_cap >> bits) > cap / 2) ++bits;
+    while (bits < 40 && (n_cap >> bits) > p.cap / 2) ++bits;
     if (g_force_pair_bits >= 0) bits = g_force_pair_bits;
     if (bits > key_bits) bits = key_bits;
-    const int levels = (bits + 9) / 10;
-    int lb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int l = 0; l < levels; ++l) lb[l] = bits / levels + (l < bits % levels ? 1 : 0);
-
-    DevBuf<u8> ea(&ws, n_cap * eb + 64), eb2(&ws, levels ? n_cap * eb + 64 : 1);
-    DevBuf<u64> n_dev(&ws, 1), hist0(&ws, (size_t)1 << lb[0]), ctr(&ws, 1);
-    GSB_CUDA_TRY(cudaMemcpyAsync(n_dev.p, &m, 8, cudaMemcpyHostToDevice, s));          // cursor of the appended reverse complements
-    GSB_CUDA_TRY(cudaMemsetAsync(hist0.p, 0, hist0.bytes(), s));
-    GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 8, s));
-    {
-        const u64 tiles = (m + (u64)kPkThreads * kPkItems - 1) / ((u64)kPkThreads * kPkItems);
-        const int grid = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)ws.sm_count * 8));
-        const int shift0 = key_bits - lb[0];
-        if (key_bytes == 8) pairs_pack_kernel<u64><<<grid, kPkThreads, 0, s>>>((const u64*)keys, counts, m, fold_w, (Pair64*)ea.p, n_dev.p, hist0.p, shift0, lb[0]);
-        else pairs_pack_kernel<Key128><<<grid, kPkThreads, 0, s>>>((const Key128*)keys, counts, m, fold_w, (Pair128*)ea.p, n_dev.p, hist0.p, shift0, lb[0]);
-        ++ws.launches;
+    if (first_bits > 0) {
+        if (first_bits > key_bits) first_bits = key_bits;
+        const int rest = bits > first_bits ? bits - first_bits : 0;
+        const int rl = (rest + 9) / 10;
+        p.levels = 1 + rl;
+        p.lb[0] = first_bits;
+        for (int l = 0; l < rl; ++l) p.lb[1 + l] = rest / rl + (l < rest % rl ? 1 : 0);
+        p.bits = first_bits + rest;
+        return p;
     }
-    void* cur = ea.p; void* other = eb2.p;
-    DevBuf<u64> cstart;
-    u64 n_parents = 1;
-    int consumed = 0;
+    p.bits = bits;
+    p.levels = (bits + 9) / 10;
+    for (int l = 0; l < p.levels; ++l) p.lb[l] = bits / p.levels + (l < bits % p.levels ? 1 : 0);
+    return p;
+}
+
+// (keys, counts)[0, m) -> {key, count} elements in `elems` (room for 2 m when fold_w > 0: the reverse complements are
+// appended); *n_dev = elements written; hist0 [2^bits0] += histogram of their top bits0 bits (zeroed by the caller)
+void pairsort_pack(Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w, void* elems, u64* n_dev, u64* hist0, int bits0) {
+    cudaStream_t s = ws.stream;
+    GSB_CUDA_TRY(cudaMemcpyAsync(n_dev, &m, 8, cudaMemcpyHostToDevice, s));              // cursor of the appended reverse complements (pageable source: staged before the call returns)
+    const u64 tiles = (m + (u64)kPkThreads * kPkItems - 1) / ((u64)kPkThreads * kPkItems);
+    const int grid = (int)std::max<u64>(1, std::min<u64>(tiles, (u64)ws.sm_count * 8));
+    const int shift0 = key_bits - bits0;
+    if (key_bytes == 8) pairs_pack_kernel<u64><<<grid, kPkThreads, 0, s>>>((const u64*)keys, counts, m, fold_w, (Pair64*)elems, n_dev, hist0, shift0, bits0);
+    else pairs_pack_kernel<Key128><<<grid, kPkThreads, 0, s>>>((const Key128*)keys, counts, m, fold_w, (Pair128*)elems, n_dev, hist0, shift0, bits0);
+    ++ws.launches;
+}
+
+// The remaining passes plan.lb[first_level ..] and the shared-memory sort of every bucket.  The elements are in `cur`
+// (`other`: scratch of the same capacity, unused when no pass remains); either one parent whose size is *n_dev (cstart
+// empty), or parents made by earlier passes (cstart [n_parents + 1], `consumed` bits).  n_cap bounds the element count.
+// hist_first: the histogram of the first remaining pass if it is known already.  false = the data defeat the geometry.
+bool pairsort_finish(Workspace& ws, int key_bytes, int key_bits, void* cur, void* other, u64 n_cap, const u64* n_dev, DevBuf<u64>& cstart, u64 n_parents,
+                     int consumed, const PairSortPlan& plan, int first_level, const u64* hist_first, ReducedRun& out) {
+    cudaStream_t s = ws.stream;
+    const ElemKind ek = pair_kind(key_bytes);
     std::vector<LevelTiming> ev;
-    for (int l = 0; l < levels; ++l) {
-        run_level(ws, ek, cur, other, n_cap, n_cap, cstart, n_parents, consumed, lb[l], l == 0 ? hist0.p : nullptr, nullptr, ev, key_bits, n_dev.p);
+    for (int l = first_level; l < plan.levels; ++l) {
+        if (plan.lb[l] == 0) continue;
+        run_level(ws, ek, cur, other, n_cap, n_cap, cstart, n_parents, consumed, plan.lb[l], l == first_level ? hist_first : nullptr, nullptr, ev, key_bits, n_dev);
         std::swap(cur, other);
-        n_parents <<= lb[l];
-        consumed += lb[l];
+        n_parents <<= plan.lb[l];
+        consumed += plan.lb[l];
     }
     if (cstart.p == nullptr) {                                          // no pass at all: one bucket [0, n)
         cstart.reset(&ws, 2);
         GSB_CUDA_TRY(cudaMemsetAsync(cstart.p, 0, 8, s));
-        GSB_CUDA_TRY(cudaMemcpyAsync(cstart.p + 1, n_dev.p, 8, cudaMemcpyDeviceToDevice, s));
+        GSB_CUDA_TRY(cudaMemcpyAsync(cstart.p + 1, n_dev, 8, cudaMemcpyDeviceToDevice, s));
     }
     const u64 ovf_cap = 64;
     DevBuf<ulonglong2> ovf(&ws, ovf_cap);
+    DevBuf<u64> ctr(&ws, 1);
+    GSB_CUDA_TRY(cudaMemsetAsync(ctr.p, 0, 8, s));
     out.keys.reset(&ws, n_cap * key_bytes);
     out.counts.reset(&ws, n_cap);
-    if (key_bytes == 8) launch_bucket_sort<u64>(cur, cstart.p, (u32)n_parents, key_bits, consumed, cap, out.keys.p, out.counts.p, ovf.p, ovf_cap, ctr.p, ws.sm_count, ws.device, s);
-    else launch_bucket_sort<Key128>(cur, cstart.p, (u32)n_parents, key_bits, consumed, cap, out.keys.p, out.counts.p, ovf.p, ovf_cap, ctr.p, ws.sm_count, ws.device, s);
+    if (key_bytes == 8) launch_bucket_sort<u64>(cur, cstart.p, (u32)n_parents, key_bits, consumed, plan.cap, out.keys.p, out.counts.p, ovf.p, ovf_cap, ctr.p, ws.sm_count, ws.device, s);
+    else launch_bucket_sort<Key128>(cur, cstart.p, (u32)n_parents, key_bits, consumed, plan.cap, out.keys.p, out.counts.p, ovf.p, ovf_cap, ctr.p, ws.sm_count, ws.device, s);
     ++ws.launches;
     u64 h[2] = {0, 0};
-    GSB_CUDA_TRY(cudaMemcpyAsync(&h[0], n_dev.p, 8, cudaMemcpyDeviceToHost, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(&h[0], cstart.p + n_parents, 8, cudaMemcpyDeviceToHost, s));   // the element count
     GSB_CUDA_TRY(cudaMemcpyAsync(&h[1], ctr.p, 8, cudaMemcpyDeviceToHost, s));
     ws.sync();
-    const u64 n = h[0];
     if (h[1] > ovf_cap) return false;
     if (h[1]) {
         // buckets that did not fit: every one is a contiguous range of the final order, radix-sorted on its own
@@ -1278,8 +1293,103 @@ bool sort_pairs_msd(Workspace& ws, int key_bytes, int key_bits, const void* keys
             }
         }
     }
-    out.m = n;
+    out.m = h[0];
     return true;
+}
+
+// m (key, count) pairs with distinct keys, arbitrary order -> ordered by key; fold_w > 0: the reverse complement of every
+// key that is not self-complementary joins the set first (fold.cu: the folded, filtered run becomes the reference's edge
+// set).  out is (re)allocated; out.m = pairs produced.  Returns false (nothing produced) when the data defeat the bucket
+// geometry -- the caller radix-sorts instead.
+bool sort_pairs_msd(Workspace& ws, int key_bytes, int key_bits, const void* keys, const u64* counts, u64 m, int fold_w, ReducedRun& out) {
+    cudaStream_t s = ws.stream;
+    const u64 n_cap = fold_w ? 2 * m : m;
+    if (n_cap == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); out.m = 0; return true; }
+    const u32 eb = pairsort_elem_bytes(key_bytes);
+    const PairSortPlan plan = pairsort_plan(key_bytes, key_bits, n_cap, 0);
+    const int bits0 = plan.levels ? plan.lb[0] : 0;
+    DevBuf<u8> ea(&ws, n_cap * eb + 64), eb2(&ws, plan.levels ? n_cap * eb + 64 : 1);
+    DevBuf<u64> n_dev(&ws, 1), hist0(&ws, (size_t)1 << bits0);
+    GSB_CUDA_TRY(cudaMemsetAsync(hist0.p, 0, hist0.bytes(), s));
+    pairsort_pack(ws, key_bytes, key_bits, keys, counts, m, fold_w, ea.p, n_dev.p, hist0.p, bits0);
+    DevBuf<u64> cstart;
+    return pairsort_finish(ws, key_bytes, key_bits, ea.p, eb2.p, n_cap, n_dev.p, cstart, 1, 0, plan, 0, hist0.p, out);
+}
+
+// ---- multi-GPU: level 0 of the pair sort crosses NVLink (orchestrated by exchange.cu) ---------------------------------------
+namespace {
+
+// One CTA.  hist_all [n][C]: every rank's histogram of the top bits of its elements.  Children are dealt to the ranks as
+// contiguous ranges of (nearly) equal element counts -- rank o owns [clo_o, chi_o), so the concatenation of the ranks'
+// slices is the global order -- and inside its owner's window a child lies at (elements of the owner's earlier children)
+// + (the same child's elements from lower ranks).
+//   cursor [C * cstride]: where THIS rank's elements of each child go (element index in the owner's window)
+//   owner [C]; totals [n]: elements every rank receives; range [2]: this rank's children [clo, chi)
+//   cstart_local [C + 1]: starts of this rank's children in its own window (entries 0 .. chi - clo)
+__global__ void __launch_bounds__(1024) pair_owner_plan_kernel(const u64* __restrict__ hist_all, int n, int rank, u32 C, u64* __restrict__ cursor, u32 cstride,
+                                                               u8* __restrict__ owner, u64* __restrict__ totals, u32* __restrict__ range, u64* __restrict__ cstart_local) {
+    __shared__ u64 scan_s[1024 / 32 + 1];
+    __shared__ u64 first_s[kMaxRanks], tot_s[kMaxRanks];
+    __shared__ u32 lo_s, hi_s;
+    const u32 c = threadIdx.x;
+    if (c < (u32)kMaxRanks) { first_s[c] = ~0ull; tot_s[c] = 0; }
+    if (c == 0) { lo_s = 0xffffffffu; hi_s = 0; }
+    u64 tot = 0, before_me = 0;
+    if (c < C) {
+        for (int r = 0; r < n; ++r) {
+            const u64 v = hist_all[(size_t)r * C + c];
+            tot += v;
+            if (r < rank) before_me += v;
+        }
+    }
+    u64 grand = 0;
+    const u64 P = block_exclusive_scan<u64, 1024>(tot, &grand, scan_s);     // barriers inside: the initialisations above are visible
+    u32 own = 0;
+    if (c < C) {
+        own = grand ? (u32)((P * (u64)n) / grand) : 0u;
+        if (own >= (u32)n) own = (u32)n - 1;
+        atomicMin(&first_s[own], P);
+        atomicAdd(&tot_s[own], tot);
+        if (own == (u32)rank) { atomicMin(&lo_s, c); atomicMax(&hi_s, c + 1); }
+    }
+    __syncthreads();
+    if (c < C) {
+        owner[c] = (u8)own;
+        cursor[(size_t)c * cstride] = P - first_s[own] + before_me;
+        if (own == (u32)rank) cstart_local[c - lo_s] = P - first_s[own];
+    }
+    if (c < (u32)n) totals[c] = tot_s[c];
+    if (c == 0) {
+        const u32 lo = lo_s == 0xffffffffu ? 0u : lo_s, hi = lo_s == 0xffffffffu ? 0u : hi_s;
+        range[0] = lo; range[1] = hi;
+        cstart_local[hi - lo] = tot_s[rank];
+    }
+}
+
+}  // namespace
+
+void pairsort_plan_owners(Workspace& ws, const u64* hist_all, int n_ranks, int rank, int bits0, u64* cursor, u32 cstride, u8* owner, u64* totals, u32* range,
+                          u64* cstart_local) {
+    pair_owner_plan_kernel<<<1, 1024, 0, ws.stream>>>(hist_all, n_ranks, rank, 1u << bits0, cursor, cstride, owner, totals, range, cstart_local);
+    ++ws.launches;
+}
+
+// first pass of the pair sort, every child stored straight into its owner's window
+void pairsort_scatter_to_peers(Workspace& ws, int key_bytes, int key_bits, const void* elems, u64 n_cap, const u64* n_dev, int bits0, u64* cursor, u32 cstride,
+                               const u8* owner, void* const* peer_base, int n_peers) {
+    if (!n_cap) return;
+    const ElemKind ek = pair_kind(key_bytes);
+    PartArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.src_base[0] = elems; pa.out = nullptr; pa.n = n_cap; pa.n_dev = n_dev;
+    pa.shift = key_bits - bits0; pa.bits = bits0;
+    for (int r = 0; r < n_peers; ++r) pa.peer[r] = peer_base[r];
+    pa.n_peers = n_peers; pa.owner_tab = owner;
+    pa.cursor = cursor; pa.cstride = cstride;
+    const u64 tiles = (n_cap + tile_elems(ek) - 1) / tile_elems(ek);
+    if (tiles > 0xffffffffull) throw StatusError{GSB_EINVAL, "internal: too many partition tiles"};
+    pa.n_tiles = (u32)tiles;
+    launch_scatter(ek, pa, tiles, ws);
 }
 
 }  // namespace gsb

@@ -32,6 +32,12 @@ def _worker(rank, world, nccl_id, k, min_count, mode, out):
     sys.path.insert(0, os.path.dirname(HERE))
     import gossamer_b200 as G
     kind = G.KMERSET if mode == "kmerset" else G.GRAPH
+    if mode == "sampled":                                                # the fallback of the pair-sort exchange: sampled splitters
+        G.debug_set_tuning(G.SAMPLED_SURVIVORS)
+    if mode == "pairgeo":                                                # tiny buckets: more passes after the exchange, overflowing buckets
+        G.debug_set_pairsort(64, -1)
+    if mode == "pairovf":                                                # nothing fits: the whole-slice radix-sort fallback
+        G.debug_set_pairsort(2, 10)
     limited = mode == "batches" or (mode == "onespill" and rank == 0)       # onespill: only ONE rank ever flushes a batch early
     b = G.Builder(kind, k, min_count=min_count, device=rank, max_batch_keys=400_000 if limited else 0)
     b.attach(nccl_id, world, rank)
@@ -78,7 +84,8 @@ def _assemble(per_rank):
 
 @pytest.mark.parametrize("k,min_count,mode", [(25, 1, "dist"), (31, 2, "dist"), (55, 1, "dist"), (31, 3, "gather"), (27, 2, "batches"),
                                               (5, 2, "dist"), (25, 1, "kmerset"), (40, 1, "kmerset"), (31, 2, "skew"), (25, 1, "onespill"),
-                                              (55, 2, "onespill")])
+                                              (55, 2, "onespill"), (31, 2, "sampled"), (55, 1, "sampled"), (31, 1, "pairgeo"), (55, 2, "pairgeo"),
+                                              (25, 1, "pairovf"), (7, 1, "dist")])
 def test_multi_gpu_build_bit_exact(k, min_count, mode):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
