@@ -2,6 +2,7 @@
 #include "file_io.hh"
 
 #include <dirent.h>
+#include <dlfcn.h>
 #include <sys/stat.h>
 
 #include <fcntl.h>
@@ -12,6 +13,7 @@
 #include <cerrno>
 #include <cstring>
 #include <fstream>
+#include <vector>
 
 namespace goss {
 
@@ -20,9 +22,57 @@ static bool ends_with(const std::string& s, const char* suf) {
     return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
 }
 
+// ---- bzip2 input (src/PhysicalFileFactory.cc:272-275: the reference pushes Boost.Iostreams' bzip2_decompressor, i.e.
+// libbz2, in front of the file).  The image ships libbz2.so.1 without its header, so the library's (stable, documented)
+// low-level C interface is declared here and bound at run time.
+namespace {
+struct BzStream {                                   // bz_stream of bzlib.h
+    char* next_in; unsigned avail_in; unsigned total_in_lo32, total_in_hi32;
+    char* next_out; unsigned avail_out; unsigned total_out_lo32, total_out_hi32;
+    void* state;
+    void* (*bzalloc)(void*, int, int); void (*bzfree)(void*, void*); void* opaque;
+};
+enum { kBzOk = 0, kBzStreamEnd = 4 };
+struct BzApi {
+    int (*init)(BzStream*, int, int) = nullptr;
+    int (*decompress)(BzStream*) = nullptr;
+    int (*end)(BzStream*) = nullptr;
+    bool ok = false;
+};
+BzApi& bz_api() {
+    static BzApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libbz2.so.1.0", RTLD_NOW);
+        if (!h) h = dlopen("libbz2.so.1", RTLD_NOW);
+        if (h) {
+            api.init = (int (*)(BzStream*, int, int))dlsym(h, "BZ2_bzDecompressInit");
+            api.decompress = (int (*)(BzStream*))dlsym(h, "BZ2_bzDecompress");
+            api.end = (int (*)(BzStream*))dlsym(h, "BZ2_bzDecompressEnd");
+            api.ok = api.init && api.decompress && api.end;
+        }
+    }
+    return api;
+}
+struct BzState {
+    BzStream strm;
+    std::vector<char> in;
+    bool stream_open = false, eof = false;
+};
+}  // namespace
+
 InputFile::InputFile(const std::string& name) : name_(name) {
-    if (ends_with(name, ".bz2"))
-        throw Error{"\t'" + name + "': bzip2 input is not supported by this build (no libbz2 in the image); decompress first\n"};
+    if (ends_with(name, ".bz2")) {
+        if (!bz_api().ok) throw Error{"\t'" + name + "': bzip2 input needs libbz2.so.1, which could not be loaded\n"};
+        fd_ = open(name.c_str(), O_RDONLY);
+        if (fd_ < 0) throw Error{"\t'" + name + "': " + strerror(errno) + "\n"};
+        BzState* st = new BzState();
+        memset(&st->strm, 0, sizeof(st->strm));
+        st->in.resize(1 << 20);
+        bz_ = st;
+        return;
+    }
     if (name == "-") { fd_ = 0; return; }
     if (ends_with(name, ".gz")) {
         gz_ = gzopen(name.c_str(), "rb");
@@ -38,11 +88,53 @@ InputFile::InputFile(const std::string& name) : name_(name) {
 }
 
 InputFile::~InputFile() {
+    if (bz_) {
+        BzState* st = (BzState*)bz_;
+        if (st->stream_open) bz_api().end(&st->strm);
+        delete st;
+    }
     if (gz_) gzclose((gzFile)gz_);
     if (fd_ > 0) close(fd_);
 }
 
+// concatenated bzip2 streams are decoded one after the other, as bzip2(1) and Boost's multi-stream filter do
+size_t InputFile::read_bz2(void* dst, size_t n) {
+    BzState* st = (BzState*)bz_;
+    BzApi& api = bz_api();
+    size_t got = 0;
+    while (got < n && !st->eof) {
+        if (st->strm.avail_in == 0) {
+            long r;
+            do { r = ::read(fd_, st->in.data(), st->in.size()); } while (r < 0 && errno == EINTR);
+            if (r < 0) throw Error{"\t'" + name_ + "': read error\n"};
+            if (r == 0) {
+                if (st->stream_open) throw Error{"\t'" + name_ + "': unexpected end of bzip2 data\n"};
+                st->eof = true;
+                break;
+            }
+            st->strm.next_in = st->in.data();
+            st->strm.avail_in = (unsigned)r;
+        }
+        if (!st->stream_open) {
+            char* keep_in = st->strm.next_in; const unsigned keep_avail = st->strm.avail_in;
+            memset(&st->strm, 0, sizeof(st->strm));
+            st->strm.next_in = keep_in; st->strm.avail_in = keep_avail;
+            if (api.init(&st->strm, 0, 0) != kBzOk) throw Error{"\t'" + name_ + "': cannot start the bzip2 decoder\n"};
+            st->stream_open = true;
+        }
+        st->strm.next_out = (char*)dst + got;
+        st->strm.avail_out = (unsigned)std::min<size_t>(n - got, 1u << 30);
+        const unsigned before = st->strm.avail_out;
+        const int rc = api.decompress(&st->strm);
+        got += before - st->strm.avail_out;
+        if (rc == kBzStreamEnd) { api.end(&st->strm); st->stream_open = false; continue; }
+        if (rc != kBzOk) throw Error{"\t'" + name_ + "': corrupt bzip2 data\n"};
+    }
+    return got;
+}
+
 size_t InputFile::read(void* dst, size_t n) {
+    if (bz_) return read_bz2(dst, n);
     size_t got = 0;
     while (got < n) {
         long r;

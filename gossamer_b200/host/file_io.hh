@@ -18,7 +18,8 @@ struct Error {
     std::string text;     // already formatted the way src/App.cc:328-407 prints it
 };
 
-// Plain, ".gz" (zlib) or "-" (stdin) input, chosen by suffix like PhysicalFileFactory::in.
+// Plain, ".gz" (zlib), ".bz2" (libbz2, bound at run time) or "-" (stdin) input, chosen by suffix like PhysicalFileFactory::in
+// (src/PhysicalFileFactory.cc:261-280).
 class InputFile {
 public:
     explicit InputFile(const std::string& name);
@@ -29,8 +30,10 @@ public:
     size_t read(void* dst, size_t n);
     const std::string& name() const { return name_; }
 private:
+    size_t read_bz2(void* dst, size_t n);
     std::string name_;
     void* gz_ = nullptr;
+    void* bz_ = nullptr;           // .bz2: decoder state (libbz2's bz_stream + the compressed-side buffer)
     int fd_ = -1;
 };
 

@@ -121,3 +121,42 @@ def test_key_mix_is_a_bijection_and_separates_substitution_variants(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_compressed_input_readers(tmp_path):
+    """host/file_io.cc InputFile: plain, .gz and .bz2 input decode to the same bytes (src/PhysicalFileFactory.cc:261-280);
+    concatenated bzip2 / gzip streams are read through; truncated bzip2 data is an error, not a short file."""
+    import bz2
+    import gzip
+    import shutil
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    lib_dir = os.path.join(ROOT, "gossamer_b200")
+    if not cxx or not os.path.exists(os.path.join(lib_dir, "libgossamer_b200.so")):
+        pytest.skip("needs g++ and the built library")
+    exe = str(tmp_path / "inputfile_check")
+    r = subprocess.run([cxx, "-O1", "-std=c++17", "-w", "-I", "/usr/local/cuda/include", "-o", exe, os.path.join(ROOT, "tests", "cpp", "inputfile_check.cc"),
+                        os.path.join(lib_dir, "host", "file_io.cc"), "-L", lib_dir, "-lgossamer_b200", "-Wl,-rpath," + lib_dir, "-lz", "-ldl"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import simreads_py as S
+    text = bytes(S.reads_fastq(S.genome(30_000, 3), 100, 9_000, err=0.01, seed=4))          # ~2 MB
+    half = text.index(b"\n@r", len(text) // 2) + 1
+    cases = {
+        "plain.fq": text,
+        "one.fq.gz": gzip.compress(text, 6),
+        "two.fq.gz": gzip.compress(text[:half], 1) + gzip.compress(text[half:], 9),
+        "one.fq.bz2": bz2.compress(text, 9),
+        "two.fq.bz2": bz2.compress(text[:half], 1) + bz2.compress(text[half:], 9),
+        "empty.fq.bz2": bz2.compress(b""),
+    }
+    for name, data in cases.items():
+        (tmp_path / name).write_bytes(data)
+        r = subprocess.run([exe, str(tmp_path / name)], capture_output=True)
+        assert r.returncode == 0, (name, r.stderr)
+        assert r.stdout == (b"" if name.startswith("empty") else text), name
+    (tmp_path / "cut.fq.bz2").write_bytes(cases["one.fq.bz2"][:len(cases["one.fq.bz2"]) // 2])
+    r = subprocess.run([exe, str(tmp_path / "cut.fq.bz2")], capture_output=True)
+    assert r.returncode == 1 and b"bzip2" in r.stderr
+    (tmp_path / "junk.fq.bz2").write_bytes(b"this is not bzip2 data at all, not even close" * 10)
+    r = subprocess.run([exe, str(tmp_path / "junk.fq.bz2")], capture_output=True)
+    assert r.returncode == 1 and b"bzip2" in r.stderr

@@ -453,7 +453,7 @@ def test_goss_cli_writes_the_reference_file_set(tmp_path):
     def files(prefix):
         out = {}
         for p in tmp_path.iterdir():
-            if p.name.startswith(prefix) and p.name not in ("reads.fq", "ref.fa"):
+            if p.name.startswith(prefix) and p.name not in ("reads.fq", "ref.fa", "reads.fq.gz", "ref.fa.bz2"):
                 out[p.name] = p.read_bytes()
         return out
 
@@ -466,6 +466,16 @@ def test_goss_cli_writes_the_reference_file_set(tmp_path):
     r = subprocess.run([goss, "build-kmer-set", "-k", "25", "-I", str(fa), "-O", str(tmp_path / "ks")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert not _diff(files("ks"), want.files())
+    # compressed inputs (src/PhysicalFileFactory.cc:261-280): .gz through zlib, .bz2 through libbz2 -- same files
+    import bz2
+    import gzip
+    (tmp_path / "reads.fq.gz").write_bytes(gzip.compress(text, 1))
+    (tmp_path / "ref.fa.bz2").write_bytes(bz2.compress(fasta[:20_000], 5) + bz2.compress(fasta[20_000:], 9))
+    want, _ = O.build_graph([(fasta, O.FASTA), (text, O.FASTQ)], 27, min_count=2, threads=4, base="z")
+    r = subprocess.run([goss, "build-graph", "-k", "27", "-m", "2", "-i", str(tmp_path / "reads.fq.gz"), "-I", str(tmp_path / "ref.fa.bz2"), "-O", str(tmp_path / "z"),
+                        "--block-mb", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert not _diff(files("z"), want.files())
     # a parse error deep inside the file: the reference's message, exit code 1
     bad = tmp_path / "bad.fq"
     cut = text.index(b"\n", len(text) // 2) + 1
