@@ -194,4 +194,19 @@ void orc_kmer_to_string(uint64_t lo, uint64_t hi, int k, char* out) {
     std::string s = kmer_to_string((unsigned)k, mk128(hi, lo)); memcpy(out, s.data(), s.size()); out[s.size()] = 0;
 }
 
+// xenome index steps 3 and 4 on file sets already in `fs`; stats = {n_lhs, n_rhs, n_common, n_out}
+int orc_merge_and_annotate(void* fs, const char* lhs, const char* rhs, const char* out, uint64_t* stats, char* err, int errcap) {
+    ORC_TRY
+        AnnotateStats a = merge_and_annotate(((FsHandle*)fs)->fs, lhs, rhs, out);
+        if (stats) { stats[0] = a.n_lhs; stats[1] = a.n_rhs; stats[2] = a.n_common; stats[3] = a.n_out; }
+        return 0;
+    ORC_CATCH(-1)
+}
+
+int64_t orc_compute_near_kmers(void* fs, const char* base, char* err, int errcap) {
+    ORC_TRY
+        return (int64_t)compute_near_kmers(((FsHandle*)fs)->fs, base);
+    ORC_CATCH(-1)
+}
+
 }  // extern "C"

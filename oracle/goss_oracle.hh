@@ -1025,4 +1025,83 @@ static inline BuildStats build_kmer_set(const std::vector<Input>& inputs, unsign
     return st;
 }
 
+// ---------------------------------------------------------------------------------------
+// xenome index, steps 3 and 4 (src/XenoApp.cc:62-76)
+// ---------------------------------------------------------------------------------------
+
+// A plain bit vector written one bit at a time.  Reference: WordyBitVector::Builder::push_backX / end,
+// src/WordyBitVector.hh:90-116: ceil(n / 64) little-endian words, one (zero) word when nothing was pushed.
+static inline std::string write_bit_vector(const std::vector<bool>& bits) {
+    std::vector<uint64_t> words(std::max<size_t>(1, (bits.size() + 63) / 64), 0);
+    for (uint64_t i = 0; i < bits.size(); ++i)
+        if (bits[i]) words[i >> 6] |= 1ULL << (i & 63);
+    return std::string(reinterpret_cast<const char*>(words.data()), words.size() * 8);
+}
+static inline bool bit_vector_get(const std::string& f, uint64_t i) {
+    uint64_t w; memcpy(&w, f.data() + 8 * (i >> 6), 8);
+    return (w >> (i & 63)) & 1;
+}
+
+struct AnnotateStats { uint64_t n_lhs, n_rhs, n_common, n_out; };
+
+// merge-and-annotate-kmer-sets.  Reference: src/GossCmdMergeAndAnnotateKmerSets.cc:27-207 -- the union of two kmer sets
+// (size estimate = exact size of the union, :121) plus one membership bit per element and side.
+static inline AnnotateStats merge_and_annotate(MemFS& fs, const std::string& lhs_base, const std::string& rhs_base, const std::string& out_base) {
+    KmerSetContents a = read_kmer_set(fs, lhs_base, false), b = read_kmer_set(fs, rhs_base, false);
+    if (a.count == 0 || b.count == 0 || a.k != b.k) throw std::runtime_error("nonsense");   // :41-49 (a bare `throw "nonsense"` there)
+    std::vector<u128> u; std::vector<bool> lb, rb;
+    uint64_t l = 0, r = 0, c = 0;
+    while (l < a.kmers.size() || r < b.kmers.size()) {
+        const bool take_l = r >= b.kmers.size() || (l < a.kmers.size() && a.kmers[l] <= b.kmers[r]);
+        const bool take_r = l >= a.kmers.size() || (r < b.kmers.size() && b.kmers[r] <= a.kmers[l]);
+        u.push_back(take_l ? a.kmers[l] : b.kmers[r]);
+        lb.push_back(take_l); rb.push_back(take_r);
+        if (take_l && take_r) ++c;
+        if (take_l) ++l;
+        if (take_r) ++r;
+    }
+    KmerSetWriter w(fs, out_base, a.k, u.size());
+    for (u128 x : u) w.push_back(x);
+    w.finish();
+    fs[out_base + ".lhs-bits"] = write_bit_vector(lb);
+    fs[out_base + ".rhs-bits"] = write_bit_vector(rb);
+    return AnnotateStats{(uint64_t)a.kmers.size(), (uint64_t)b.kmers.size(), c, (uint64_t)u.size()};
+}
+
+// compute-near-kmers.  Reference: src/GossCmdComputeNearKmers.cc:57-118,158-225.  A k-mer that belongs to exactly one
+// side turns "gray" (both bits cleared) when one of its variants y = x ^ (b << j), 0 <= j < K, 0 <= b < 4, is a member that
+// belongs to exactly one side and to the OTHER side than x.  Decisions use the ORIGINAL bits throughout (:71,:99).
+// Two things in the reference are restated as they ARE, not as they may have been meant (the files must match):
+//   * the variant mask is shifted by j BITS, not by j bases (:82-83);
+//   * `mKmerSet.normalize(y);` (:96) calls GraphEssentials::normalize(const Edge&) const (src/GraphEssentials.hh:152-157),
+//     which RETURNS the normalised edge; the result is discarded, so y is looked up as it is.
+static inline uint64_t compute_near_kmers(MemFS& fs, const std::string& base) {
+    KmerSetContents s = read_kmer_set(fs, base, false);
+    const std::string lf = fs_get(fs, base + ".lhs-bits"), rf = fs_get(fs, base + ".rhs-bits");
+    const uint64_t n = s.kmers.size();
+    std::vector<bool> nl(n), nr(n);
+    uint64_t gray = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const bool li = bit_vector_get(lf, i), ri = bit_vector_get(rf, i);
+        nl[i] = li; nr[i] = ri;
+        if (li == ri) continue;
+        const u128 x = s.kmers[i];
+        bool found = false;
+        for (uint64_t j = 0; !found && j < s.k; ++j) {
+            for (uint64_t b = 0; !found && b < 4; ++b) {
+                u128 y = x ^ ((u128)b << j);
+                if (y == x) continue;
+                auto it = std::lower_bound(s.kmers.begin(), s.kmers.end(), y);
+                if (it == s.kmers.end() || *it != y) continue;
+                const uint64_t r = (uint64_t)(it - s.kmers.begin());
+                if (bit_vector_get(lf, r) != bit_vector_get(rf, r) && li != bit_vector_get(lf, r)) found = true;
+            }
+        }
+        if (found) { ++gray; nl[i] = false; nr[i] = false; }
+    }
+    fs[base + ".lhs-bits"] = write_bit_vector(nl);
+    fs[base + ".rhs-bits"] = write_bit_vector(nr);
+    return gray;
+}
+
 }  // namespace goss_oracle

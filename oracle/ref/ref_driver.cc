@@ -17,6 +17,8 @@
 #include "GossCmdMergeKmerSets.hh"
 #include "GossCmdDumpGraph.hh"
 #include "GossCmdRestoreGraph.hh"
+#include "GossCmdMergeAndAnnotateKmerSets.hh"
+#include "GossCmdComputeNearKmers.hh"
 #include "Graph.hh"
 #include "KmerSet.hh"
 #include "Logger.hh"
@@ -224,6 +226,32 @@ int ref_restore_graph(void* sv, const char* in_file, const char* out, char* err,
         GossCmdRestoreGraph cmd(in_file, out);
         boost::program_options::variables_map opts;
         GossCmdContext cxt(s->fac, log, "restore-graph", opts);
+        cmd(cxt);
+        return 0;
+    REF_CATCH
+}
+
+// xenome index, steps 3 and 4 (src/XenoApp.cc:62-76): merge-and-annotate-kmer-sets (src/GossCmdMergeAndAnnotateKmerSets.cc:27-207)
+// and compute-near-kmers (src/GossCmdComputeNearKmers.cc:158-225)
+int ref_merge_and_annotate(void* sv, const char* lhs, const char* rhs, const char* out, char* err, int errcap) {
+    REF_TRY
+        Store* s = (Store*)sv;
+        Logger log("log.txt", s->fac);
+        GossCmdMergeAndAnnotateKmerSets cmd(lhs, rhs, out);
+        boost::program_options::variables_map opts;
+        GossCmdContext cxt(s->fac, log, "merge-and-annotate-kmer-sets", opts);
+        cmd(cxt);
+        return 0;
+    REF_CATCH
+}
+
+int ref_compute_near_kmers(void* sv, const char* in, uint64_t threads, char* err, int errcap) {
+    REF_TRY
+        Store* s = (Store*)sv;
+        Logger log("log.txt", s->fac);
+        GossCmdComputeNearKmers cmd(in, threads);
+        boost::program_options::variables_map opts;
+        GossCmdContext cxt(s->fac, log, "compute-near-kmers", opts);
         cmd(cxt);
         return 0;
     REF_CATCH

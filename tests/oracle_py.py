@@ -275,3 +275,22 @@ def kmer_to_string(x, k):
     buf = C.create_string_buffer(k + 1)
     lib().orc_kmer_to_string(C.c_uint64(x & (2**64 - 1)), C.c_uint64(x >> 64), k, buf)
     return buf.value.decode()
+
+
+def merge_and_annotate(files, lhs, rhs, out):
+    """Restated merge-and-annotate-kmer-sets: -> (files of `out` incl. .lhs-bits/.rhs-bits, (n_lhs, n_rhs, n_common, n_out))."""
+    fs = _as_fs(files)
+    err = C.create_string_buffer(512)
+    st = (C.c_uint64 * 4)()
+    _check(lib().orc_merge_and_annotate(fs.h, lhs.encode(), rhs.encode(), out.encode(), st, err, 512), err)
+    return {n: v for n, v in fs.files().items() if n.startswith(out + ".")}, tuple(int(x) for x in st)
+
+
+def compute_near_kmers(files, base):
+    """Restated compute-near-kmers: -> ({base.lhs-bits, base.rhs-bits}, number of gray k-mers)."""
+    fs = _as_fs(files)
+    err = C.create_string_buffer(512)
+    lib().orc_compute_near_kmers.restype = C.c_int64
+    gray = _check(lib().orc_compute_near_kmers(fs.h, base.encode(), err, 512), err)
+    out = fs.files()
+    return {n: out[n] for n in (base + ".lhs-bits", base + ".rhs-bits")}, int(gray)

@@ -198,3 +198,21 @@ def restore_graph(store, text, out, in_file="restore.txt"):
     store.put_all({in_file: bytes(text)})
     _check(lib().ref_restore_graph(store.h, in_file.encode(), out.encode(), err, 512), err)
     return store.files(graph_names(out))
+
+
+def annotated_names(base):
+    return kmer_set_names(base) + [base + ".lhs-bits", base + ".rhs-bits"]
+
+
+def merge_and_annotate(store, lhs, rhs, out):
+    """The reference's own merge-and-annotate-kmer-sets (xenome index, step 3) on kmer sets already in `store`."""
+    err = C.create_string_buffer(512)
+    _check(lib().ref_merge_and_annotate(store.h, lhs.encode(), rhs.encode(), out.encode(), err, 512), err)
+    return store.files(annotated_names(out))
+
+
+def compute_near_kmers(store, base, threads=2):
+    """The reference's own compute-near-kmers (xenome index, step 4): rewrites base.lhs-bits / base.rhs-bits in `store`."""
+    err = C.create_string_buffer(512)
+    _check(lib().ref_compute_near_kmers(store.h, base.encode(), C.c_uint64(threads), err, 512), err)
+    return store.files([base + ".lhs-bits", base + ".rhs-bits"])

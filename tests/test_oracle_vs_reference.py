@@ -171,3 +171,29 @@ def test_parse_errors_match_reference_command(text, fmt):
     with pytest.raises(O.OracleParseError) as oe:
         O.build_graph([(text, fmt)], 3)
     assert str(oe.value) in str(re_.value)
+
+
+@pytest.mark.parametrize("k,n_bases,n_subst", [(15, 3000, 40), (25, 20000, 300), (31, 8000, 100), (32, 8000, 100), (40, 5000, 60), (9, 2000, 30)])
+def test_xenome_index_steps_equal_reference_commands(k, n_bases, n_subst):
+    """merge-and-annotate-kmer-sets and compute-near-kmers (src/XenoApp.cc:62-76): the restated oracle writes the bytes the
+    reference's own commands write -- the union kmer set, the two membership bit vectors, and the bit vectors after the
+    near-k-mer pass (including its variant-mask and discarded-normalize quirks)."""
+    from xeno_cases import related_references
+    graft, host = related_references(n_bases, n_subst, k)
+    st1, f1 = R.build_kmer_set([(graft, 0)], k, base="ga")
+    st2, f2 = R.build_kmer_set([(host, 0)], k, base="ho")
+    st = R.Store()
+    st.put_all(f1)
+    st.put_all(f2)
+    theirs = R.merge_and_annotate(st, "ga", "ho", "both")
+    both_in = dict(f1)
+    both_in.update(f2)
+    ours, stats = O.merge_and_annotate(both_in, "ga", "ho", "both")
+    assert not _diff(ours, theirs)
+    assert stats[3] == stats[0] + stats[1] - stats[2] and 0 < stats[2] < min(stats[0], stats[1])
+    theirs2 = R.compute_near_kmers(st, "both", threads=3)
+    ours2, gray = O.compute_near_kmers(ours, "both")
+    assert not _diff(ours2, theirs2)
+    before = sum(bin(b).count("1") for b in ours["both.lhs-bits"])
+    after = sum(bin(b).count("1") for b in ours2["both.lhs-bits"])
+    assert gray > 0 and before - after <= gray
