@@ -78,7 +78,7 @@ class GraphInfo(C.Structure):
     _fields_ = [("version", C.c_uint64), ("k", C.c_uint64), ("flags", C.c_uint64), ("n_items", C.c_uint64)]
 
 
-EXPORTS = ["gsb_graph_peek", "gsb_graph_load", "gsb_graph_load_pairs", "gsb_graph_finish", "gsb_graph_dump", "gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
+EXPORTS = ["gsb_kmerset_merge_annotate", "gsb_kmerset_near_kmers", "gsb_graph_peek", "gsb_graph_load", "gsb_graph_load_pairs", "gsb_graph_finish", "gsb_graph_dump", "gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
            "gsb_emit", "gsb_timer_begin", "gsb_timer_end", "gsb_host_alloc", "gsb_host_free", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root", "gsb_plan_splitters", "gsb_samples_per_rank",
            "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_sort_bench", "gsb_debug_set_tuning", "gsb_debug_set_partition", "gsb_debug_set_pairsort", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
            "gsb_debug_extract"]
@@ -114,6 +114,8 @@ def lib():
         L.gsb_graph_load_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.gsb_graph_finish.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Counts)]
         L.gsb_graph_dump.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Sink)]
+        L.gsb_kmerset_merge_annotate.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(Source), C.c_char_p, C.POINTER(Sink), C.POINTER(C.c_uint64)]
+        L.gsb_kmerset_near_kmers.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(Source), C.POINTER(Sink), C.POINTER(C.c_uint64)]
         L.gsb_debug_copy_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.gsb_debug_copy_counts.restype = C.c_int64
         L.gsb_debug_sort_keys.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
@@ -455,6 +457,36 @@ def merge_file_sets(files, prefixes, dst_prefix, kind=GRAPH, max_merge=8, device
         files.update(merge([p for p, _ in group], out))
         todo.append((out, True))
     return merge([p for p, _ in todo], dst_prefix)
+
+
+def merge_and_annotate_kmer_sets(files, lhs_prefix, rhs_prefix, dst_prefix, device=0):
+    """`goss merge-and-annotate-kmer-sets` (xenome index, step 3; src/GossCmdMergeAndAnnotateKmerSets.cc:27-207) on file sets
+    held in memory.  Returns ({name: bytes} of dst_prefix incl. .lhs-bits / .rhs-bits, (n_lhs, n_rhs, n_common, n_out))."""
+    source = MemorySource(files)
+    info = graph_peek(lhs_prefix, source, KMERSET)
+    b = Builder(KMERSET, int(info.k), device=device)
+    try:
+        sink = MemorySink()
+        st = (C.c_uint64 * 4)()
+        b._check(lib().gsb_kmerset_merge_annotate(b.h, lhs_prefix.encode(), rhs_prefix.encode(), C.byref(source.c), dst_prefix.encode(), C.byref(sink.c), st))
+        return sink.as_bytes(), tuple(int(x) for x in st)
+    finally:
+        b.close()
+
+
+def compute_near_kmers(files, prefix, device=0):
+    """`goss compute-near-kmers` (xenome index, step 4; src/GossCmdComputeNearKmers.cc:57-225).  Returns ({prefix.lhs-bits,
+    prefix.rhs-bits: bytes}, number of gray k-mers)."""
+    source = MemorySource(files)
+    info = graph_peek(prefix, source, KMERSET)
+    b = Builder(KMERSET, int(info.k), device=device)
+    try:
+        sink = MemorySink()
+        gray = C.c_uint64()
+        b._check(lib().gsb_kmerset_near_kmers(b.h, prefix.encode(), C.byref(source.c), C.byref(sink.c), C.byref(gray)))
+        return sink.as_bytes(), int(gray.value)
+    finally:
+        b.close()
 
 
 def build_graph(inputs, k, min_count=1, prefix="graph", sink=None, device=0):

@@ -85,11 +85,14 @@ struct PhaseTimer {
     std::vector<Interval> open_, free_;
     cudaStream_t s = nullptr;
     Interval cur_{nullptr, nullptr, nullptr};
+    bool running_ = false;
     void init(cudaStream_t st) { s = st; }
     void destroy() {
         for (auto& v : {&open_, &free_}) { for (auto& i : *v) { cudaEventDestroy(i.e0); cudaEventDestroy(i.e1); } v->clear(); }
     }
     void start() {
+        if (running_) throw StatusError{GSB_EINVAL, "internal: phase timer started twice"};
+        running_ = true;
         if (free_.empty()) {
             Interval i{nullptr, nullptr, nullptr};
             GSB_CUDA_TRY(cudaEventCreate(&i.e0)); GSB_CUDA_TRY(cudaEventCreate(&i.e1));
@@ -99,6 +102,7 @@ struct PhaseTimer {
         GSB_CUDA_TRY(cudaEventRecord(cur_.e0, s));
     }
     void stop(double& acc_ms) {
+        running_ = false;
         GSB_CUDA_TRY(cudaEventRecord(cur_.e1, s));
         cur_.acc = &acc_ms;
         open_.push_back(cur_);
@@ -199,7 +203,7 @@ thread_local std::string g_create_error;
 template <typename F>
 int guarded(gsb_ctx* ctx, F&& body) {
     try {
-        if (ctx) GSB_CUDA_TRY(cudaSetDevice(ctx->ws.device));
+        if (ctx) { GSB_CUDA_TRY(cudaSetDevice(ctx->ws.device)); ctx->timer.running_ = false; }   // an earlier call may have thrown inside a phase
         body();
         return GSB_OK;
     } catch (const StatusError& e) {
@@ -1075,6 +1079,99 @@ int gsb_graph_finish(gsb_ctx* c, uint64_t cutoff, uint64_t m_est, gsb_counts* ou
         c->acc_unsorted = false;
         c->counted = true;
         if (out) *out = c->counts;
+    });
+}
+
+// ---- xenome index, steps 3 and 4 (xeno.cu) --------------------------------------------------------------------------------
+static void load_kmer_set_weighted(gsb_ctx* c, const std::string& prefix, const gsb_source* src, u64 weight, u64* m_out) {
+    gsb_graph_info info;
+    peek_graph(prefix, src, GSB_KIND_KMERSET, &info);
+    if ((int)info.k != c->cfg.k) throw StatusError{GSB_EINVAL, prefix + " has k=" + std::to_string(info.k) + ", this context was created for k=" + std::to_string(c->cfg.k)};
+    ReducedRun run;
+    read_sparse_array(c->ws, src, prefix + ".kmers", c->key_bytes, c->pinned, c->pinned_bytes, run.keys, &run.m);
+    run.counts.reset(&c->ws, run.m);
+    fill_value(c->ws, run.counts.p, run.m, weight);           // the summed weight of an element of the union is its membership
+    *m_out = run.m;
+    absorb_run(c, run);
+}
+
+int gsb_kmerset_merge_annotate(gsb_ctx* c, const char* lhs_prefix, const char* rhs_prefix, const gsb_source* src, const char* out_prefix,
+                               const gsb_sink* sink, uint64_t* stats) {
+    if (!c || !lhs_prefix || !rhs_prefix || !out_prefix || !src || !src->size || !src->pread) return GSB_EINVAL;
+    if (sink && (!sink->open || !sink->pwrite || !sink->close)) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (c->cfg.kind != GSB_KIND_KMERSET) throw StatusError{GSB_EINVAL, "merge-and-annotate-kmer-sets wants a kmer-set context"};
+        if (c->comm) throw StatusError{GSB_EINVAL, "merge-and-annotate-kmer-sets is a single-GPU operation"};
+        if (c->counted || c->have_acc || c->n_keys) throw StatusError{GSB_EINVAL, "the context is in use (call gsb_reset first)"};
+        u64 n_lhs = 0, n_rhs = 0;
+        load_kmer_set_weighted(c, lhs_prefix, src, 1, &n_lhs);      // (absorb_run times the merge itself: the phase timer does not nest)
+        load_kmer_set_weighted(c, rhs_prefix, src, 2, &n_rhs);
+        // src/GossCmdMergeAndAnnotateKmerSets.cc:41-49: a bare `throw "nonsense"` for an empty side (k is checked above)
+        if (n_lhs == 0 || n_rhs == 0) throw StatusError{GSB_EINVAL, "nonsense"};
+        const u64 n = c->acc.m;
+        c->counts.n_instances = n_lhs + n_rhs; c->counts.n_distinct = n; c->counts.n_kept = n;
+        c->m_est = n;                                            // KmerSet::Builder bld(K, out, fac, n), :121
+        c->counted = true;
+        Emitter em;
+        em.ws = &c->ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
+        if (sink) { c->ring.create(c->ws); c->ring.drop(); em.ring = &c->ring; }
+        c->timer.start();
+        const std::string out(out_prefix);
+        write_kmer_set_files(c, em, out);
+        DevBuf<u64> lhs, rhs;
+        xeno_annotate_bits(c->ws, c->acc.counts.p, n, lhs, rhs);
+        em.put_device(out + ".lhs-bits", lhs.p, bit_vector_words(n) * 8);
+        em.put_device(out + ".rhs-bits", rhs.p, bit_vector_words(n) * 8);
+        c->timer.stop(c->stats.ms_emit);
+        em.flush();
+        c->stats.bytes_out += em.bytes_out;
+        if (stats) { stats[0] = n_lhs; stats[1] = n_rhs; stats[2] = n_lhs + n_rhs - n; stats[3] = n; }
+    });
+}
+
+int gsb_kmerset_near_kmers(gsb_ctx* c, const char* prefix, const gsb_source* src, const gsb_sink* sink, uint64_t* n_gray) {
+    if (!c || !prefix || !src || !src->size || !src->pread) return GSB_EINVAL;
+    if (sink && (!sink->open || !sink->pwrite || !sink->close)) return GSB_EINVAL;
+    return guarded(c, [&] {
+        if (c->cfg.kind != GSB_KIND_KMERSET) throw StatusError{GSB_EINVAL, "compute-near-kmers wants a kmer-set context"};
+        if (c->comm) throw StatusError{GSB_EINVAL, "compute-near-kmers is a single-GPU operation"};
+        const std::string p(prefix);
+        gsb_graph_info info;
+        peek_graph(p, src, GSB_KIND_KMERSET, &info);
+        if ((int)info.k != c->cfg.k) throw StatusError{GSB_EINVAL, p + " has k=" + std::to_string(info.k) + ", this context was created for k=" + std::to_string(c->cfg.k)};
+        Workspace& ws = c->ws;
+        DevBuf<u8> keys; u64 m = 0;
+        c->timer.start();
+        read_sparse_array(ws, src, p + ".kmers", c->key_bytes, c->pinned, c->pinned_bytes, keys, &m);
+        const u64 words = bit_vector_words(m);
+        DevBuf<u64> bits[2];
+        const char* suffix[2] = {".lhs-bits", ".rhs-bits"};
+        for (int side = 0; side < 2; ++side) {
+            const std::string name = p + suffix[side];
+            uint64_t size = 0;
+            if (src->size(src->user, name.c_str(), &size) != 0) throw StatusError{GSB_EIO, "missing file " + name};
+            if (size < words * 8) throw StatusError{GSB_EINVAL, name + " is shorter than the kmer set it annotates"};
+            bits[side].reset(&ws, words);
+            for (u64 off = 0; off < words * 8; off += c->pinned_bytes) {
+                const u64 chunk = std::min<u64>(c->pinned_bytes, words * 8 - off);
+                if (src->pread(src->user, name.c_str(), off, c->pinned, chunk) != 0) throw StatusError{GSB_EIO, "read failed for " + name};
+                GSB_CUDA_TRY(cudaMemcpyAsync((u8*)bits[side].p + off, c->pinned, chunk, cudaMemcpyHostToDevice, ws.stream));
+                ws.sync();
+            }
+        }
+        c->timer.stop(c->stats.ms_scan);
+        c->timer.start();
+        DevBuf<u64> nl, nr;
+        const u64 gray = xeno_near_kmers(ws, c->key_bytes, c->cfg.k, keys.p, m, bits[0].p, bits[1].p, nl, nr);
+        c->timer.stop(c->stats.ms_reduce);
+        Emitter em;
+        em.ws = &ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
+        if (sink) { c->ring.create(ws); c->ring.drop(); em.ring = &c->ring; }
+        em.put_device(p + ".lhs-bits", nl.p, words * 8);
+        em.put_device(p + ".rhs-bits", nr.p, words * 8);
+        em.flush();
+        c->stats.bytes_out += em.bytes_out;
+        if (n_gray) *n_gray = gray;
     });
 }
 

@@ -262,7 +262,13 @@ void read_sparse_array(Workspace& ws, const gsb_source* src, const std::string& 
                        DevBuf<u8>& keys_out, u64* m_out);
 void read_counts(Workspace& ws, const gsb_source* src, const std::string& base, u64 m, u8* pinned, size_t pinned_bytes, DevBuf<u64>& counts_out);
 void fill_ones(Workspace& ws, u64* counts, u64 m);
+void fill_value(Workspace& ws, u64* counts, u64 m, u64 v);
 void dump_text(Workspace& ws, int key_bytes, const void* keys, const u64* counts, u64 m, int w, DevBuf<u8>& text_out, u64* bytes_out);
+
+// ---- xeno.cu ---------------------------------------------------------------------------------
+u64 bit_vector_words(u64 m);
+void xeno_annotate_bits(Workspace& ws, const u64* weight, u64 m, DevBuf<u64>& lhs, DevBuf<u64>& rhs);
+u64 xeno_near_kmers(Workspace& ws, int key_bytes, int k, const void* keys, u64 m, const u64* lhs, const u64* rhs, DevBuf<u64>& new_lhs, DevBuf<u64>& new_rhs);
 
 struct ParseFailure { int code; u64 line; };
 struct StatusError { int status; std::string message; };

@@ -89,8 +89,8 @@ __global__ void vba_ord2_kernel(const u64* __restrict__ pos1, const u64* __restr
         if (r < n1) { const u64 i = pos1[r]; if (i < m) counts[i] |= (u64)ord2[q] << 16; }
     }
 }
-__global__ void fill_ones_kernel(u64* __restrict__ counts, u64 m) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) counts[i] = 1;
+__global__ void fill_value_kernel(u64* __restrict__ counts, u64 m, u64 v) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) counts[i] = v;
 }
 
 // ---- dump-graph text: "<k+1 bases>\t<count>\n" per edge -----------------------------------------------------------
@@ -261,11 +261,12 @@ void read_counts(Workspace& ws, const gsb_source* src, const std::string& base, 
     ws.sync();
 }
 
-void fill_ones(Workspace& ws, u64* counts, u64 m) {
+void fill_value(Workspace& ws, u64* counts, u64 m, u64 v) {
     if (!m) return;
-    fill_ones_kernel<<<(unsigned)std::min<u64>((m + 255) / 256, (u64)ws.sm_count * 16), 256, 0, ws.stream>>>(counts, m);
+    fill_value_kernel<<<(unsigned)std::min<u64>((m + 255) / 256, (u64)ws.sm_count * 16), 256, 0, ws.stream>>>(counts, m, v);
     ++ws.launches;
 }
+void fill_ones(Workspace& ws, u64* counts, u64 m) { fill_value(ws, counts, m, 1); }
 
 // dump-graph's body lines for the run, as one device buffer of text
 void dump_text(Workspace& ws, int key_bytes, const void* keys, const u64* counts, u64 m, int w, DevBuf<u8>& text_out, u64* bytes_out) {

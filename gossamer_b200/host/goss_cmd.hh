@@ -78,6 +78,8 @@ void run_trim_graph(const RewriteOptions& o, const GossCmdContext& cxt);
 void run_merge(const RewriteOptions& o, const GossCmdContext& cxt, bool kmer_sets);
 void run_dump_graph(const RewriteOptions& o, const GossCmdContext& cxt);
 void run_restore_graph(const RewriteOptions& o, const GossCmdContext& cxt);
+void run_merge_and_annotate(const RewriteOptions& o, const GossCmdContext& cxt);   // xenome index step 3
+void run_compute_near_kmers(const RewriteOptions& o, const GossCmdContext& cxt);   // xenome index step 4
 
 struct ParsedArgs {
     BuildOptions opt;

@@ -21,6 +21,8 @@ static int help(std::ostream& os) {
        << "  merge-kmer-sets   create a new k-mer set by merging existing k-mer sets\n"
        << "  dump-graph        write out the graph in a robust text representation\n"
        << "  restore-graph     read in a graph from the text representation\n"
+       << "  merge-and-annotate-kmer-sets   union of two k-mer sets + membership bit vectors (xenome index)\n"
+       << "  compute-near-kmers             mark k-mers of one set that are one variant away from the other (xenome index)\n"
        << "  help              show this message\n"
        << "use `goss <command> -h` for the options of a command.\n";
     return 0;
@@ -30,7 +32,8 @@ int main(int argc, char** argv) {
     if (argc < 2) { help(std::cerr); return 1; }
     const std::string cmd = argv[1];
     if (cmd == "help" || cmd == "-h" || cmd == "--help") return help(std::cout);
-    const bool rewrite = cmd == "trim-graph" || cmd == "merge-graphs" || cmd == "merge-kmer-sets" || cmd == "dump-graph" || cmd == "restore-graph";
+    const bool rewrite = cmd == "trim-graph" || cmd == "merge-graphs" || cmd == "merge-kmer-sets" || cmd == "dump-graph" || cmd == "restore-graph" ||
+                         cmd == "merge-and-annotate-kmer-sets" || cmd == "compute-near-kmers";
     if (cmd != "build-graph" && cmd != "build-kmer-set" && !rewrite) {
         std::cerr << "unrecognised command '" << cmd << "'\n";
         help(std::cerr);
@@ -54,6 +57,8 @@ int main(int argc, char** argv) {
                 else if (cmd == "merge-graphs") run_merge(o, cxt, false);
                 else if (cmd == "merge-kmer-sets") run_merge(o, cxt, true);
                 else if (cmd == "dump-graph") run_dump_graph(o, cxt);
+                else if (cmd == "merge-and-annotate-kmer-sets") run_merge_and_annotate(o, cxt);
+                else if (cmd == "compute-near-kmers") run_compute_near_kmers(o, cxt);
                 else run_restore_graph(o, cxt);
             } catch (Error& e) {
                 e.text = "error performing " + cmd + ":\n" + e.text;

@@ -4,6 +4,8 @@
 //                                    when there are more than --max-merge inputs: the last merge's size estimate depends on it)
 //   dump-graph      src/GossCmdDumpGraph.cc:31-60
 //   restore-graph   src/GossCmdRestoreGraph.cc:70-128
+//   merge-and-annotate-kmer-sets   src/GossCmdMergeAndAnnotateKmerSets.cc:27-229   (xenome index, step 3)
+//   compute-near-kmers             src/GossCmdComputeNearKmers.cc:158-247          (xenome index, step 4)
 // All decoding, merging, filtering and writing happens on the GPU through the C ABI (gsb_graph_*); this file is option
 // handling, the reference's messages, and the text parser of restore-graph.
 #include <chrono>
@@ -216,11 +218,51 @@ void run_restore_graph(const RewriteOptions& o, const GossCmdContext& cxt) {
     h.check(rc);
 }
 
+void run_merge_and_annotate(const RewriteOptions& o, const GossCmdContext& cxt) {
+    Logger& log = cxt.log;
+    auto t0 = std::chrono::steady_clock::now();
+    InputFiles in;
+    const gsb_graph_info lhs = peek(o.ins[0], in, GSB_KIND_KMERSET), rhs = peek(o.ins[1], in, GSB_KIND_KMERSET);
+    if (lhs.n_items == 0 || rhs.n_items == 0 || lhs.k != rhs.k) throw Error{"nonsense\n"};     // the reference's own words (:41-49)
+    log(info, "counting kmers.");
+    Ctx h;
+    h.create(GSB_KIND_KMERSET, lhs.k, o.device, log);
+    OutputFiles files;
+    uint64_t st[4] = {0, 0, 0, 0};
+    int rc = gsb_kmerset_merge_annotate(h.c, o.ins[0].c_str(), o.ins[1].c_str(), in.source(), o.out.c_str(), files.sink(), st);
+    if (rc == GSB_EIO) throw Error{"\tcannot write to '" + o.out + "'\n"};
+    h.check(rc);
+    log(info, "writing out " + std::to_string(st[3]) + " kmers.");
+    log(info, "of which " + std::to_string(st[2]) + " are common.");
+    std::cout << st[0] << '\t' << st[1] << '\t' << st[2] << '\n';                            // :204
+    log(info, "total elapsed time: " + std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
+}
+
+void run_compute_near_kmers(const RewriteOptions& o, const GossCmdContext& cxt) {
+    Logger& log = cxt.log;
+    auto t0 = std::chrono::steady_clock::now();
+    InputFiles in;
+    const gsb_graph_info gi = peek(o.ins[0], in, GSB_KIND_KMERSET);
+    Ctx h;
+    h.create(GSB_KIND_KMERSET, gi.k, o.device, log);
+    log(info, "calculating grey set");
+    // the bit vectors are rewritten in place, as the reference does (:218-226): collected first, written after the pass
+    OutputFiles files;
+    uint64_t gray = 0;
+    int rc = gsb_kmerset_near_kmers(h.c, o.ins[0].c_str(), in.source(), files.sink(), &gray);
+    if (rc == GSB_EIO) throw Error{"\tcannot write to '" + o.ins[0] + "'\n"};
+    h.check(rc);
+    log(info, "found " + std::to_string(gray) + " gray bits (out of " + std::to_string(gi.n_items) + ").");
+    log(info, "total elapsed time: " + std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
+}
+
 std::string rewrite_usage_text(const std::string& cmd) {
     std::ostringstream os;
     if (cmd == "trim-graph") os << "usage: goss trim-graph -G <graph> -O <graph> -C <cutoff>\n";
     else if (cmd == "dump-graph") os << "usage: goss dump-graph -G <graph> [-o <file>]\n";
     else if (cmd == "restore-graph") os << "usage: goss restore-graph [-f <file>] -O <graph>\n";
+    else if (cmd == "merge-and-annotate-kmer-sets") os << "usage: goss merge-and-annotate-kmer-sets -G <kmer set> -G <kmer set> -O <kmer set>\n";
+    else if (cmd == "compute-near-kmers") os << "usage: goss compute-near-kmers -G <annotated kmer set>\n";
     else os << "usage: goss " << cmd << " {-G <in>}+ [--graphs-in <list>] [--max-merge n] -O <out>\n";
     os << "  -G, --graph-in arg         name of the input graph object (repeatable for merges)\n"
        << "  -O, --graph-out arg        name of the output graph object\n"
@@ -257,8 +299,8 @@ RewriteOptions parse_rewrite_args(const std::string& cmd, int argc, char** argv)
         else if (a == "-G" || a == "--graph-in") o.ins.push_back(need());
         else if (a == "-O" || a == "--graph-out") o.out = need();
         else if ((a == "-C" || a == "--cutoff") && cmd == "trim-graph") { o.cutoff = parse_u64(a, need()); o.have_cutoff = true; }
-        else if (a == "--graphs-in" && cmd.rfind("merge", 0) == 0) list = need();
-        else if (a == "--max-merge" && cmd.rfind("merge", 0) == 0) o.max_merge = parse_u64(a, need());
+        else if (a == "--graphs-in" && (cmd == "merge-graphs" || cmd == "merge-kmer-sets")) list = need();
+        else if (a == "--max-merge" && (cmd == "merge-graphs" || cmd == "merge-kmer-sets")) o.max_merge = parse_u64(a, need());
         else if ((a == "-o" || a == "--output-file") && cmd == "dump-graph") o.text_file = need();
         else if ((a == "-f" || a == "--input-file") && cmd == "restore-graph") o.text_file = need();
         else if (a == "--device") o.device = (int)parse_u64(a, need());
@@ -268,7 +310,17 @@ RewriteOptions parse_rewrite_args(const std::string& cmd, int argc, char** argv)
     }
     if (o.help) return o;
     if (!list.empty()) for (const std::string& n : expand_file_list(list)) o.ins.push_back(n);
-    const bool merge = cmd.rfind("merge", 0) == 0;
+    const bool merge = cmd == "merge-graphs" || cmd == "merge-kmer-sets";
+    if (cmd == "merge-and-annotate-kmer-sets") {
+        if (o.ins.size() != 2) throw usage("the option '--graph-in' must be given exactly twice\n");      // GossOptionChecker::getRepeatingTwice
+        if (o.out.empty()) throw usage("the option '--graph-out' is required but missing\n");
+        check_output_prefix(o.out);
+        return o;
+    }
+    if (cmd == "compute-near-kmers") {
+        if (o.ins.size() != 1) throw usage(o.ins.empty() ? "the option '--graph-in' is required but missing\n" : "the option '--graph-in' may only be given once\n");
+        return o;
+    }
     if (cmd != "restore-graph") {
         if (o.ins.empty()) {
             if (merge) throw usage("At least one input graph must be supplied either using --graph-in or --graphs-in.\n\n");

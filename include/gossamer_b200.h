@@ -174,6 +174,17 @@ int gsb_graph_load_pairs(gsb_ctx* ctx, const uint64_t* key_lo, const uint64_t* k
  * exact n), merge passes the sum of the inputs' sizes (src/GossCmdMerge.tcc:224-263,296), restore the header's n.
  * gsb_emit then writes the file set. */
 int gsb_graph_finish(gsb_ctx* ctx, uint64_t cutoff, uint64_t m_est, gsb_counts* out);
+/* xenome index, steps 3 and 4 (src/XenoApp.cc:62-76), on a GSB_KIND_KMERSET context of the sets' k.
+ * Replaces: GossCmdMergeAndAnnotateKmerSets::operator() (src/GossCmdMergeAndAnnotateKmerSets.cc:27-207): the union of
+ * the kmer sets <lhs_prefix> and <rhs_prefix> (read through `src`) is written as kmer set <out_prefix> plus the membership
+ * bit vectors <out_prefix>.lhs-bits / .rhs-bits.  stats (optional) = {n_lhs, n_rhs, n_common, n_out}. */
+int gsb_kmerset_merge_annotate(gsb_ctx* ctx, const char* lhs_prefix, const char* rhs_prefix, const gsb_source* src, const char* out_prefix,
+                               const gsb_sink* sink, uint64_t* stats);
+/* Replaces: GossCmdComputeNearKmers::operator() (src/GossCmdComputeNearKmers.cc:57-225): k-mers of exactly one side that
+ * have a one-sided member of the OTHER side among their variants turn gray (both bits cleared); <prefix>.lhs-bits /
+ * .rhs-bits are rewritten through the sink.  *n_gray (optional) = how many turned gray. */
+int gsb_kmerset_near_kmers(gsb_ctx* ctx, const char* prefix, const gsb_source* src, const gsb_sink* sink, uint64_t* n_gray);
+
 /* dump-graph's text (src/GossCmdDumpGraph.cc:31-60) of the finished run, formatted on the device, as one file `name`. */
 int gsb_graph_dump(gsb_ctx* ctx, const char* name, const gsb_sink* sink);
 
