@@ -79,7 +79,7 @@ class GraphInfo(C.Structure):
 
 
 EXPORTS = ["gsb_kmerset_merge_annotate", "gsb_kmerset_near_kmers", "gsb_graph_peek", "gsb_graph_load", "gsb_graph_load_pairs", "gsb_graph_finish", "gsb_graph_dump", "gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
-           "gsb_emit", "gsb_timer_begin", "gsb_timer_end", "gsb_host_alloc", "gsb_host_free", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root", "gsb_plan_splitters", "gsb_samples_per_rank",
+           "gsb_emit", "gsb_timer_begin", "gsb_timer_end", "gsb_host_alloc", "gsb_host_free", "gsb_host_bind_near_device", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root", "gsb_plan_splitters", "gsb_samples_per_rank",
            "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_sort_bench", "gsb_debug_set_tuning", "gsb_debug_set_partition", "gsb_debug_set_pairsort", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
            "gsb_debug_extract"]
 
@@ -541,6 +541,11 @@ def debug_set_tuning(tuning_id):
 def debug_set_partition(max_slots=0, total_bits=0):
     """Test-only: force the bucket geometry of the partition counting (0 = default)."""
     lib().gsb_debug_set_partition(int(max_slots), int(total_bits))
+
+
+def host_bind_near_device(device):
+    """Bind this process to the CPUs of the NUMA node the GPU hangs off (call before allocating pinned buffers)."""
+    lib().gsb_host_bind_near_device(int(device))
 
 
 def debug_set_pairsort(cap=0, bits=-1):

@@ -260,10 +260,22 @@ __device__ __forceinline__ void pack32_fast(const u8* __restrict__ text, u64 off
     }
 }
 
+// word_line[w] = the line that holds the first symbol of stream word w, for every word that starts inside this block's
+// symbols: one thread per line marks the (typically five) words that begin in it.  The packing kernel used to find its
+// line with a binary search over sym_off -- 23 dependent loads per word, 60 % of its stall samples (ncu).
+__global__ void __launch_bounds__(256) word_lines_kernel(const u32* __restrict__ sym_off, u32 n_lines, u64 first_block_sym, u64 n_words,
+                                                         u32* __restrict__ word_line) {
+    const u32 L = blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= n_lines) return;
+    const u64 a = first_block_sym + sym_off[L], b = first_block_sym + sym_off[L + 1];
+    for (u64 w = (a + 31) >> 5; (w << 5) < b && w < n_words; ++w) word_line[w] = L;
+}
+
 __global__ void __launch_bounds__(256) pack_symbols_kernel(const u8* __restrict__ text, u64 text_bytes, const u32* __restrict__ line_start,
                                                            const u8* __restrict__ kind, const u32* __restrict__ sym_off /* n_lines+1 */,
                                                            u32 n_lines, const u8* __restrict__ carry, u32 n_carry, u64 n_sym_total,
-                                                           u64* __restrict__ codes, u32* __restrict__ valid, u64 n_words) {
+                                                           u64* __restrict__ codes, u32* __restrict__ valid, u64 n_words,
+                                                           const u32* __restrict__ word_line) {
     const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     const u64 s0 = w * 32;
@@ -282,7 +294,8 @@ __global__ void __launch_bounds__(256) pack_symbols_kernel(const u8* __restrict_
     // into place.  (A per-symbol loop here cost 105 warp instructions per symbol, ncu.)
     if (s0 >= first_block_sym && s0 + 32 <= n_sym_total) {
         u32 x = (u32)(s0 - first_block_sym);
-        seek(x);
+        L = (long long)word_line[w];
+        line_lo = sym_off[L]; line_hi = sym_off[L + 1]; src = line_start[L]; lk = kind[L];
         int j = 0;
         while (j < 32) {
             while (x >= line_hi) { ++L; line_lo = line_hi; line_hi = sym_off[L + 1]; src = line_start[L]; lk = kind[L]; }
@@ -566,10 +579,15 @@ void ingest_symbol_offsets(const u32* nsym, u32* sym_off, u32 n_lines, u32* tota
 }
 
 void ingest_pack(const u8* text, u64 text_bytes, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
-                 const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, cudaStream_t s, u64* launches) {
+                 const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, u32* word_line /* scratch [n_words] */,
+                 cudaStream_t s, u64* launches) {
     if (!n_words) return;
+    if (n_lines) {
+        word_lines_kernel<<<(n_lines + 255) / 256, 256, 0, s>>>(sym_off, n_lines, 64 + (u64)n_carry, n_words, word_line);
+        ++*launches;
+    }
     pack_symbols_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, s>>>(text, text_bytes, line_start, kind, sym_off, n_lines, carry, n_carry,
-                                                                        n_sym_total, codes, valid, n_words);
+                                                                        n_sym_total, codes, valid, n_words, word_line);
     ++*launches;
 }
 

@@ -82,7 +82,8 @@ void ingest_classify(const u8* text, const u32* line_start, u32 n_lines, int for
                      u8* kind, u32* nsym, IngestStatus* st_dev, cudaStream_t s, u64* launches);
 void ingest_symbol_offsets(const u32* nsym, u32* sym_off, u32 n_lines, u32* total_dev, u32* tmp, cudaStream_t s, u64* launches);
 void ingest_pack(const u8* text, u64 text_bytes, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
-                 const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, cudaStream_t s, u64* launches);
+                 const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, u32* word_line /* scratch [n_words] */,
+                 cudaStream_t s, u64* launches);
 void ingest_save_carry(const u64* codes, const u32* valid, u64 n_sym_total, u32 want, u8* carry_out, cudaStream_t s, u64* launches);
 // mix != 0 (graph mode only): the folded key is stored bit-mixed (key_mix, common.cuh)
 void ingest_extract(int kind, int key_bytes, const u64* codes, const u32* valid, u64 p_begin, u64 p_end, int w, int passes, int mix,

@@ -74,6 +74,7 @@ int build_worker(const BuildOptions& opt, const GossCmdContext& cxt, int kind, i
         } else if (!read_all(id_in_fd, id, sizeof(id))) {
             throw Error{"no communicator id from the launcher\n"};
         }
+        gsb_host_bind_near_device(opt.devices[rank]);             // pinned block buffers on the GPU's own NUMA node
         gsb_config cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.abi_version = GSB_ABI_VERSION;

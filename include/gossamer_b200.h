@@ -193,6 +193,9 @@ int gsb_graph_dump(gsb_ctx* ctx, const char* name, const gsb_sink* sink);
 int gsb_timer_begin(gsb_ctx* ctx);
 int gsb_timer_end(gsb_ctx* ctx, double* ms_out);
 
+/* Best effort: binds the calling thread to the CPUs of the NUMA node `device` hangs off, so that pinned buffers allocated
+ * afterwards are local to the GPU (matters when several ranks stream blocks at once).  Call before gsb_host_alloc. */
+int gsb_host_bind_near_device(int device);
 /* Page-locked host buffers for gsb_push_block (so that the host program need not link CUDA itself). */
 int gsb_host_alloc(size_t nbytes, void** out);
 void gsb_host_free(void* p);
