@@ -109,6 +109,8 @@ struct PhaseTimer {
         cur_.acc = &acc_ms;
         open_.push_back(cur_);
     }
+    // an interval whose events were recorded elsewhere (partition.cu); the events are recycled like the timer's own
+    void adopt(cudaEvent_t e0, cudaEvent_t e1, double& acc_ms) { if (e0 && e1) open_.push_back(Interval{e0, e1, &acc_ms}); }
     // adds every finished interval to its accumulator (waits for the last recorded event)
     void resolve() {
         for (auto& i : open_) {
@@ -149,6 +151,12 @@ struct gsb_ctx {
     DevBuf<u64> hist;              // histograms fused into the extraction: [256] top byte of the low key word (partition counting) or
                                    // [passes][256] every digit (legacy LSD counting)
     bool hist_valid = false;       // ... describe exactly the current batch
+    // streamed first pass (single GPU, partition counting): every block is split by its top bits as soon as it has been
+    // extracted -- while the next block is still crossing PCIe -- into `alt` at the offsets it has in `keys`
+    DevBuf<u64> runs;              // [blocks][2^bits0 + 1] absolute starts of every block's children
+    u64 runs_cap = 0, n_runs = 0;  // blocks: capacity / split so far in this batch
+    DevBuf<u64> hist_next;         // [2^(bits0 + kTopHistBits)] next-bits histogram of every child, summed over the blocks
+    u64 n_streamed = 0;            // keys covered by the blocks split so far (== n_keys when the batch is fully streamed)
     DevBuf<IngestStatus> status;
     u64 max_batch_keys = 0;
 
@@ -244,6 +252,8 @@ void reset_batch(gsb_ctx* c) {
     GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), s));
     c->hist_valid = c->mix || c->comm == nullptr;              // legacy counting with a communicator: the histograms are taken after the exchange
     c->n_keys = 0;
+    c->n_runs = 0; c->n_streamed = 0;
+    if (c->hist_next.p) GSB_CUDA_TRY(cudaMemsetAsync(c->hist_next.p, 0, c->hist_next.bytes(), s));
 }
 
 // merge two sorted reduced runs (merge path, fold.cu), then sum the counts of equal keys -- what AsyncMerge / PairMerge
@@ -269,6 +279,42 @@ void ensure_alt(gsb_ctx* c, u64 n) {
     c->alt.free();
     c->alt_cap = std::max<u64>(n, c->keys_cap);
     c->alt.reset(&c->ws, c->alt_cap * c->key_bytes + 64);         // slack: bulk tile loads are rounded up to 16 bytes
+}
+
+static bool streaming(const gsb_ctx* c) { return c->mix && !c->comm; }
+
+// First partition pass over the block that has just been extracted: keys[off, off + n_blk) -> alt (same offsets).
+void stream_block(gsb_ctx* c, u64 off, u64 n_blk) {
+    Workspace& ws = c->ws;
+    const int kb = c->key_bytes;
+    const int bits0 = partition_stream_bits0();
+    const u64 C = 1ull << bits0;
+    if (c->alt_cap < c->keys_cap) {                              // alt mirrors keys; what earlier blocks put there is kept
+        DevBuf<u8> bigger(&ws, c->keys_cap * kb + 64);
+        if (off && c->alt.p) GSB_CUDA_TRY(cudaMemcpyAsync(bigger.p, c->alt.p, off * kb, cudaMemcpyDeviceToDevice, ws.stream));
+        c->alt = std::move(bigger);
+        c->alt_cap = c->keys_cap;
+    }
+    if (c->n_runs + 1 > c->runs_cap) {
+        const u64 want = std::max<u64>(16, 2 * c->runs_cap);
+        DevBuf<u64> bigger(&ws, want * (C + 1));
+        if (c->n_runs) GSB_CUDA_TRY(cudaMemcpyAsync(bigger.p, c->runs.p, c->n_runs * (C + 1) * 8, cudaMemcpyDeviceToDevice, ws.stream));
+        c->runs = std::move(bigger);
+        c->runs_cap = want;
+    }
+    if (!c->hist_next.p || c->hist_next.n != ((size_t)C << kTopHistBits)) {
+        if (c->n_runs) throw StatusError{GSB_EINVAL, "internal: the first-pass width changed inside a batch"};
+        c->hist_next.reset(&ws, (size_t)C << kTopHistBits);
+        GSB_CUDA_TRY(cudaMemsetAsync(c->hist_next.p, 0, c->hist_next.bytes(), ws.stream));
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    c->timer.start();
+    partition_block_level0(ws, kb, c->keys.p, c->alt.p, off, n_blk, bits0, c->hist.p, c->runs.p + c->n_runs * (C + 1), c->hist_next.p, &e0, &e1);
+    c->timer.stop(c->stats.ms_sort);
+    c->timer.adopt(e0, e1, c->stats.ms_sort_sweeps);             // the scatter launch alone
+    if (e0) c->stats.sort_passes += 1;
+    ++c->n_runs;
+    c->n_streamed = off + n_blk;
 }
 
 // order a run of distinct (key, count) pairs by key
@@ -308,6 +354,7 @@ void flush_batch(gsb_ctx* c, bool final_and_only, PartitionInput* pre = nullptr,
     // un-mixed in arbitrary order; whoever needs them ordered sorts the (few) distinct keys afterwards.
     int where = 0;
     bool reduced = false;
+    bool streamed_in = false;
     if (c->mix) {
         PartitionTiming pt;
         PartitionInput in;
@@ -315,6 +362,12 @@ void flush_batch(gsb_ctx* c, bool final_and_only, PartitionInput* pre = nullptr,
         if (pre) {
             in = std::move(*pre);
             plan = *pre_plan;
+        } else if (c->n_runs && c->n_streamed == c->n_keys && src == c->keys.p) {
+            // every block of the batch has been through the first pass already (stream_block): the blocks' runs lie in alt
+            in.keys = alt; in.scratch = src; in.n = c->n_keys;
+            in.runs = c->runs.p; in.runs_n_src = (int)c->n_runs; in.runs_bits0 = partition_stream_bits0(); in.runs_hist_next = c->hist_next.p;
+            plan = partition_plan_streamed(kb, c->n_keys, in.runs_bits0);
+            streamed_in = true;
         } else {
             in.keys = src; in.scratch = alt; in.n = c->n_keys;
             // the fused top-bit histogram describes exactly this batch only if it came straight out of the extraction
@@ -322,6 +375,7 @@ void flush_batch(gsb_ctx* c, bool final_and_only, PartitionInput* pre = nullptr,
             plan = partition_plan(kb, c->n_keys);
         }
         reduced = count_partitioned(ws, kb, c->key_bits, in, plan, min_count, fold_w, run, &distinct, &n_self_rc, &where, &pt);
+        if (streamed_in) where ^= 1;                               // where is relative to in.keys, which was alt here
         if (pre && !reduced) c->n_keys = exchange_partition_received(c->comm);   // rare: the full sort below needs the exact number of keys that arrived
         c->stats.ms_sort += pt.ms_partition;
         c->stats.ms_reduce += pt.ms_count;
@@ -448,6 +502,11 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     // K3: windows -> keys (+ fused digit histograms)
     // (with a communicator attached the instances are exchanged before the sort and the digit histograms are taken from
     // what arrives, so the fused histograms -- the dominant cost of the kernel -- are switched off)
+    const u64 keys_before = c->n_keys;
+    if (streaming(c)) {                                          // the fused histogram describes THIS block: its first pass runs right behind the extraction
+        GSB_CUDA_TRY(cudaMemsetAsync(c->hist.p, 0, c->hist.bytes(), s));
+        c->hist_valid = false;
+    }
     ingest_extract(c->cfg.kind, c->key_bytes, codes.p, valid.p, 64 + n_carry, n_sym_total, c->window, c->mix ? -1 : (c->comm ? 0 : c->passes), c->mix ? 1 : 0,
                    c->keys.p, c->cursor.p, c->keys_cap, c->hist.p, c->status.p, ws.sm_count, s, &ws.launches);
     u64 cur = 0;
@@ -465,6 +524,7 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     if (st.error) throw StatusError{GSB_EINVAL, "key buffer overflow (internal sizing error)"};
     c->self_rc_windows += st.n_self_rc;
     c->n_keys = cur;
+    if (streaming(c) && cur > keys_before) stream_block(c, keys_before, cur - keys_before);
     c->file_open[format] = !last;
     c->line_base[format] = last ? 0 : c->line_base[format] + n_lines;
 }

@@ -149,7 +149,15 @@ struct PartitionInput {
     DevBuf<u64> cstart;              // ... or parents made by earlier passes: [n_parents + 1] starts (device), taken over
     u64 n_parents = 1, n_cap = 0;    //     n_cap: upper bound of the key count (allocation sizes)
     int consumed_bits = 0;
+    // ... or a first pass run block by block (partition_block_level0): keys = the buffer the blocks were split INTO, n keys in all
+    const u64* runs = nullptr;       //     [runs_n_src][2^runs_bits0 + 1] absolute starts of every block's children
+    int runs_n_src = 0, runs_bits0 = 0;
+    const u64* runs_hist_next = nullptr;   // [2^(runs_bits0 + kTopHistBits)] histogram of the next bits of every child, summed over the blocks
 };
+int partition_stream_bits0();
+PartitionPlan partition_plan_streamed(int key_bytes, u64 n, int bits0);
+void partition_block_level0(Workspace& ws, int key_bytes, void* keys_block, void* alt_block, u64 block_off, u64 n_block, int bits0, const u64* hist_block_top,
+                            u64* runs_out, u64* hist_next, cudaEvent_t* e0_out = nullptr, cudaEvent_t* e1_out = nullptr);
 // Counting by partitioning (partition.cu); see there for the contract.
 bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, PartitionInput& in, const PartitionPlan& plan, u64 min_count, int fold_w,
                        ReducedRun& out, u64* m_distinct, u64* n_self_rc, int* where_keys = nullptr, PartitionTiming* timing = nullptr);
@@ -158,12 +166,14 @@ void partition_scatter_to_peers(Workspace& ws, int key_bytes, const void* in, u6
                                 void* const* peer_base, int n_peers, const u32* abort_flag);
 void partition_fold_hist(Workspace& ws, const u64* hist_top, int bits, u64* out);
 // pieces of the multi-GPU PULL exchange (partition.cu; orchestrated by exchange.cu)
-void partition_local_level0(Workspace& ws, int key_bytes, void* in, void* out, u64 n, int bits, const u64* hist_top, DevBuf<u64>& cstart_out);
-void partition_next_hist(Workspace& ws, int key_bytes, const void* keys, const u64* cstart, int bits0, u64 n, int bits, u64* hist);
+void partition_local_level0(Workspace& ws, int key_bytes, void* in, void* out, u64 n, int bits, const u64* hist_top, DevBuf<u64>& cstart_out,
+                            cudaEvent_t* e0_out = nullptr, cudaEvent_t* e1_out = nullptr, u64 in_off = 0, u64 out_off = 0);
+void partition_next_hist(Workspace& ws, int key_bytes, const void* keys, const u64* cstart, int bits0, u64 n, int bits, u64* hist, bool accumulate = false);
 void partition_pull_check(Workspace& ws, u64* hist_all, const u64* gathered, int bits0, int bits1, int n_ranks, int rank, u64 cap_keys,
                           u32* abort_flag, u64* n_recv, u64* n_remote);
 void partition_pull_level(Workspace& ws, int key_bytes, const void* const* src_base, int n_src, const u64* gathered, int bits0, u32 c_lo, u32 n_parents,
-                          u64 n_cap, int bits, const u64* hist_slice, void* out, const u32* abort_flag, DevBuf<u64>& cstart_out, cudaEvent_t e0, cudaEvent_t e1);
+                          u64 n_cap, int bits, const u64* hist_slice, void* out, const u32* abort_flag, DevBuf<u64>& cstart_out, cudaEvent_t e0, cudaEvent_t e1,
+                          bool same_base = false);
 
 // (key, count) pairs with distinct keys, arbitrary order -> ordered by key (most-significant-digit passes + a shared-memory
 // sort per bucket, partition.cu); fold_w > 0: the reverse complements join the set first.  false = declined, radix-sort instead.

@@ -61,14 +61,15 @@ struct TileRef { u64 begin; u32 count; u32 parent; u32 src; };
 
 // descs == nullptr: one parent covering [0, n).  A descriptor is {begin bits 0..31, begin bits 32..55 | source rank << 24,
 // count, parent}: the tile's keys are src_base[source rank][begin, begin + count).
-__device__ __forceinline__ TileRef tile_ref(const uint4* __restrict__ descs, u32 tile, u64 n, u32 tile_keys) {
+__device__ __forceinline__ TileRef tile_ref(const uint4* __restrict__ descs, u32 tile, u64 n, u32 tile_keys, u64 begin0) {
     TileRef r;
     if (descs) {
         const uint4 d = descs[tile];
         r.begin = (u64)d.x | ((u64)(d.y & 0xFFFFFFu) << 32); r.src = d.y >> 24; r.count = d.z; r.parent = d.w;
     } else {
-        r.begin = (u64)tile * tile_keys;
-        const u64 rem = n - r.begin;
+        const u64 done = (u64)tile * tile_keys;
+        r.begin = begin0 + done;                                      // begin0: where the single parent starts in its buffer
+        const u64 rem = n - done;
         r.count = rem < (u64)tile_keys ? (u32)rem : tile_keys;
         r.parent = 0; r.src = 0;
     }
@@ -92,6 +93,7 @@ struct PartArgs {
     const u32* n_tiles_dev;    // nullptr = n_tiles
     u32 n_tiles;
     u64 n;
+    u64 begin0;                // single-parent passes: element offset of the parent in src_base[0]
     const u64* n_dev;          // optional: the key count of a single-parent pass, known only on the device (n_tiles is then an upper bound)
     u64* cursor;               // [(parent << bits | digit) * cstride]: next free slot of the child (element index from its owner's base)
     u64* hist;                 // [parent << bits | digit]
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(kPtThreads) part_hist_kernel(PartArgs a) {
         __syncthreads();
     };
     for (u32 it = blockIdx.x; it < n_tiles; it += gridDim.x) {
-        const TileRef tr = tile_ref(a.descs, perm_tile(it, mul, n_tiles), n_keys, TILE);
+        const TileRef tr = tile_ref(a.descs, perm_tile(it, mul, n_tiles), n_keys, TILE, a.begin0);
         if (tr.parent != cur_parent) {                               // uniform over the CTA
             if (cur_parent != 0xffffffffu) flush();
             cur_parent = tr.parent;
@@ -208,14 +210,14 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
     u32 it = blockIdx.x;
     TileRef cur{0, 0, 0, 0};
     if (it < n_tiles) {
-        cur = tile_ref(a.descs, perm_tile(it, mul, n_tiles), n_keys, TILE);
+        cur = tile_ref(a.descs, perm_tile(it, mul, n_tiles), n_keys, TILE, a.begin0);
         if (t == 0) issue(cur);
     }
     u32 parity = 0;
     for (; it < n_tiles; it += gridDim.x) {
         const u32 nit = it + gridDim.x;
         TileRef nxt{0, 0, 0, 0};
-        if (nit < n_tiles) nxt = tile_ref(a.descs, perm_tile(nit, mul, n_tiles), n_keys, TILE);
+        if (nit < n_tiles) nxt = tile_ref(a.descs, perm_tile(nit, mul, n_tiles), n_keys, TILE, a.begin0);
         mbar_wait(&full_bar, parity);
         parity ^= 1;
         const u32 skip = sizeof(K) == 8 ? (u32)(cur.begin & 1) : 0u;
@@ -304,9 +306,9 @@ __global__ void fill_descs_kernel(const u64* __restrict__ cstart, const u32* __r
     descs[tile] = make_uint4((u32)begin, (u32)(begin >> 32), rem < (u64)tile_keys ? (u32)rem : tile_keys, p);
 }
 
-__global__ void init_cursor_kernel(const u64* __restrict__ cstart, u64* __restrict__ cursor, u64 n_children, u32 cstride) {
+__global__ void init_cursor_kernel(const u64* __restrict__ cstart, u64* __restrict__ cursor, u64 n_children, u32 cstride, u64 out_off) {
     const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n_children) cursor[c * cstride] = cstart[c];
+    if (c < n_children) cursor[c * cstride] = cstart[c] + out_off;
 }
 
 // ---- exact count of every bucket in shared memory -------------------------------------------------------------------------
@@ -675,14 +677,14 @@ void level_hist(Workspace& ws, ElemKind ek, PartArgs pa, const LevelTiles& tiles
 
 // child starts from the histogram, cursors, the scatter pass itself
 void level_scatter(Workspace& ws, ElemKind ek, PartArgs pa, const LevelTiles& tiles, const u64* hist, u64 n_children, DevBuf<u64>& cstart_out,
-                   PartitionTiming* timing, std::vector<LevelTiming>& events) {
+                   PartitionTiming* timing, std::vector<LevelTiming>& events, u64 out_off = 0) {
     cudaStream_t s = ws.stream;
     DevBuf<u64> cnext(&ws, n_children + 1), scan_tmp(&ws, scan_tmp_elems(n_children));
     exclusive_scan<u64, u64>(hist, cnext.p, n_children, 0ull, cnext.p + n_children, scan_tmp.p, s, &ws.launches);
     // cursors: spread over distinct cache lines when there are few of them (every tile in flight hits all of them)
     const u32 cstride = n_children <= 4096 ? 32u : 1u;
     DevBuf<u64> cursor(&ws, n_children * cstride);
-    init_cursor_kernel<<<(unsigned)((n_children + 255) / 256), 256, 0, s>>>(cnext.p, cursor.p, n_children, cstride);
+    init_cursor_kernel<<<(unsigned)((n_children + 255) / 256), 256, 0, s>>>(cnext.p, cursor.p, n_children, cstride, out_off);
     ++ws.launches;
     tiles.apply(pa);
     pa.cursor = cursor.p; pa.cstride = cstride; pa.hist = nullptr;
@@ -707,10 +709,13 @@ PartArgs local_args(const void* cur, void* other, u64 n, int consumed, int bits,
 // Produces the child starts.  hist_ready: optional histogram [n_parents << bits] that is already known.
 // n_dev (single-parent passes only): the key count lives on the device; n is then its upper bound.
 void run_level(Workspace& ws, ElemKind ek, void* cur, void* other, u64 n, u64 n_cap, DevBuf<u64>& cstart, u64 n_parents, int consumed, int bits,
-               const u64* hist_ready, PartitionTiming* timing, std::vector<LevelTiming>& events, int top_bits = 64, const u64* n_dev = nullptr) {
+               const u64* hist_ready, PartitionTiming* timing, std::vector<LevelTiming>& events, int top_bits = 64, const u64* n_dev = nullptr,
+               u64 in_off = 0, u64 out_off = 0) {
+    // in_off / out_off (single-parent passes): the parent is cur[in_off, in_off + n), its children go to other[out_off + ...)
     const u64 n_children = n_parents << bits;
     PartArgs pa = local_args(cur, other, n, consumed, bits, top_bits);
     pa.n_dev = cstart.p ? nullptr : n_dev;
+    pa.begin0 = cstart.p ? 0 : in_off;
     LevelTiles tiles;
     build_tiles(ws, ek, cstart.p, n_parents, n, n_cap, tiles);
     DevBuf<u64> hist;
@@ -720,7 +725,7 @@ void run_level(Workspace& ws, ElemKind ek, void* cur, void* other, u64 n, u64 n_
         level_hist(ws, ek, pa, tiles, hist.p);
         hist_ready = hist.p;
     }
-    level_scatter(ws, ek, pa, tiles, hist_ready, n_children, cstart, timing, events);
+    level_scatter(ws, ek, pa, tiles, hist_ready, n_children, cstart, timing, events, out_off);
 }
 
 // ---- pull exchange: tiles over the runs that every source rank holds of this rank's children ------------------------------
@@ -733,8 +738,9 @@ __global__ void pull_tiles_per_pair_kernel(const u64* __restrict__ gathered, u32
     tp[q] = (u32)((g[1] - g[0] + tile_keys - 1) / tile_keys);
 }
 
+// same_base: all sources lie in ONE buffer and their starts are absolute (the blocks of a streamed single-GPU build)
 __global__ void pull_fill_descs_kernel(const u64* __restrict__ gathered, u32 C, u32 n_src, u32 c_lo, u32 n_pairs, const u32* __restrict__ tile_first,
-                                       const u32* __restrict__ n_tiles_dev, u32 tile_keys, uint4* __restrict__ descs) {
+                                       const u32* __restrict__ n_tiles_dev, u32 tile_keys, uint4* __restrict__ descs, int same_base) {
     const u32 tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= *n_tiles_dev) return;
     u32 lo = 0, hi = n_pairs;
@@ -743,7 +749,7 @@ __global__ void pull_fill_descs_kernel(const u64* __restrict__ gathered, u32 C, 
     const u64* g = gathered + (size_t)sr * (C + 1) + c_lo + p;
     const u64 begin = g[0] + (u64)(tile - tile_first[q]) * tile_keys;
     const u64 rem = g[1] - begin;
-    descs[tile] = make_uint4((u32)begin, (u32)((begin >> 32) & 0xFFFFFFu) | (sr << 24), rem < (u64)tile_keys ? (u32)rem : tile_keys, p);
+    descs[tile] = make_uint4((u32)begin, (u32)((begin >> 32) & 0xFFFFFFu) | ((same_base ? 0u : sr) << 24), rem < (u64)tile_keys ? (u32)rem : tile_keys, p);
 }
 
 // after the all-reduce of the next level's histograms: does this rank's share fit its buffer?  If not (on any rank: every
@@ -809,8 +815,10 @@ void partition_fold_hist(Workspace& ws, const u64* hist_top, int bits, u64* out)
 
 // ---- pieces of the multi-GPU pull exchange (orchestrated by exchange.cu) -------------------------------------------------
 // level 0, local: this rank's n keys by their top `bits` bits into `out` (its peer-mapped window); cstart_out [2^bits + 1]
-void partition_local_level0(Workspace& ws, int key_bytes, void* in, void* out, u64 n, int bits, const u64* hist_top, DevBuf<u64>& cstart_out) {
+void partition_local_level0(Workspace& ws, int key_bytes, void* in, void* out, u64 n, int bits, const u64* hist_top, DevBuf<u64>& cstart_out,
+                            cudaEvent_t* e0_out, cudaEvent_t* e1_out, u64 in_off, u64 out_off) {
     std::vector<LevelTiming> ev;
+    PartitionTiming want_events;
     DevBuf<u64> folded;
     const u64* hist_ready = nullptr;
     if (hist_top && bits <= kTopHistBits) {
@@ -819,14 +827,18 @@ void partition_local_level0(Workspace& ws, int key_bytes, void* in, void* out, u
         hist_ready = folded.p;
     }
     DevBuf<u64> none;
-    run_level(ws, mixed_kind(key_bytes), in, out, n, n, none, 1, 0, bits, hist_ready, nullptr, ev);
+    run_level(ws, mixed_kind(key_bytes), in, out, n, n, none, 1, 0, bits, hist_ready, e0_out ? &want_events : nullptr, ev, 64, nullptr, in_off, out_off);
     cstart_out = std::move(none);
+    if (e0_out) {                                                       // events around the scatter launch: the caller owns them now
+        *e0_out = ev.empty() ? nullptr : ev[0].e0;
+        *e1_out = ev.empty() ? nullptr : ev[0].e1;
+    }
 }
 
 // histogram of the NEXT `bits` bits of every level-0 child of this rank's own output: hist [2^(bits0 + bits)] (zeroed here)
-void partition_next_hist(Workspace& ws, int key_bytes, const void* keys, const u64* cstart, int bits0, u64 n, int bits, u64* hist) {
+void partition_next_hist(Workspace& ws, int key_bytes, const void* keys, const u64* cstart, int bits0, u64 n, int bits, u64* hist, bool accumulate) {
     const u64 n_parents = 1ull << bits0;
-    GSB_CUDA_TRY(cudaMemsetAsync(hist, 0, (n_parents << bits) * 8, ws.stream));
+    if (!accumulate) GSB_CUDA_TRY(cudaMemsetAsync(hist, 0, (n_parents << bits) * 8, ws.stream));
     PartArgs pa = local_args(keys, nullptr, n, bits0, bits);
     LevelTiles tiles;
     build_tiles(ws, mixed_kind(key_bytes), cstart, n_parents, n, n, tiles);
@@ -844,7 +856,8 @@ void partition_pull_check(Workspace& ws, u64* hist_all, const u64* gathered, int
 // fetch them over NVLink -- and split by the next `bits` bits into `out` (local).  hist_slice [n_parents << bits]: the
 // all-reduced histogram of exactly these children.  cstart_out [(n_parents << bits) + 1].
 void partition_pull_level(Workspace& ws, int key_bytes, const void* const* src_base, int n_src, const u64* gathered, int bits0, u32 c_lo, u32 n_parents,
-                          u64 n_cap, int bits, const u64* hist_slice, void* out, const u32* abort_flag, DevBuf<u64>& cstart_out, cudaEvent_t e0, cudaEvent_t e1) {
+                          u64 n_cap, int bits, const u64* hist_slice, void* out, const u32* abort_flag, DevBuf<u64>& cstart_out, cudaEvent_t e0, cudaEvent_t e1,
+                          bool same_base) {
     cudaStream_t s = ws.stream;
     const u32 tile_keys = partition_tile_keys(key_bytes);
     const u32 C = 1u << bits0;
@@ -857,15 +870,60 @@ void partition_pull_level(Workspace& ws, int key_bytes, const void* const* src_b
     DevBuf<u32> tile_first(&ws, (size_t)n_pairs + 1), scan_tmp32(&ws, scan_tmp_elems(n_pairs));
     pull_tiles_per_pair_kernel<<<(n_pairs + 255) / 256, 256, 0, s>>>(gathered, C, (u32)n_src, c_lo, n_pairs, tile_keys, tile_first.p);
     exclusive_scan<u32, u32>(tile_first.p, tile_first.p, n_pairs, 0u, tiles.n_tiles_dev.p, scan_tmp32.p, s, &ws.launches);
-    pull_fill_descs_kernel<<<(unsigned)((tiles.tiles_ub + 255) / 256), 256, 0, s>>>(gathered, C, (u32)n_src, c_lo, n_pairs, tile_first.p, tiles.n_tiles_dev.p, tile_keys, tiles.descs.p);
+    pull_fill_descs_kernel<<<(unsigned)((tiles.tiles_ub + 255) / 256), 256, 0, s>>>(gathered, C, (u32)n_src, c_lo, n_pairs, tile_first.p, tiles.n_tiles_dev.p, tile_keys, tiles.descs.p,
+                                                                                    same_base ? 1 : 0);
     ws.launches += 2;
     PartArgs pa = local_args(nullptr, out, 0, bits0, bits);
-    for (int r = 0; r < n_src; ++r) pa.src_base[r] = src_base[r];
+    if (same_base) pa.src_base[0] = src_base[0];
+    else for (int r = 0; r < n_src; ++r) pa.src_base[r] = src_base[r];
     pa.abort = abort_flag;
     std::vector<LevelTiming> ev;
     if (e0) GSB_CUDA_TRY(cudaEventRecord(e0, s));
     level_scatter(ws, mixed_kind(key_bytes), pa, tiles, hist_slice, (u64)n_parents << bits, cstart_out, nullptr, ev);
     if (e1) GSB_CUDA_TRY(cudaEventRecord(e1, s));
+}
+
+// ---- streamed single-GPU builds: the first pass runs per input block, while the next block is still crossing PCIe ----------
+// (context.cu).  Every block is split by the same top bits0 bits into its own region of `alt` (same offsets as in `keys`);
+// child c of the batch is then the union of every block's run c -- exactly the situation of the multi-GPU pull exchange
+// with the blocks as sources, all in one buffer -- and the second pass gathers the runs while it splits them further.
+namespace {
+__global__ void add_offset_kernel(const u64* __restrict__ in, u64 n, u64 off, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + off;
+}
+}  // namespace
+
+int partition_stream_bits0() { return g_force_total_bits > 0 ? std::min(g_force_total_bits, 8) : 8; }
+
+// First pass over ONE block: keys[block_off, block_off + n_block) by their top bits0 bits into alt at the same offsets (the
+// buffers are addressed from their aligned bases: a block may start at an odd key); runs_out [2^bits0 + 1] = ABSOLUTE
+// starts (block_off added) of the block's children; hist_next
+// [2^(bits0 + kTopHistBits)] += histogram of the next kTopHistBits bits of every child.
+// hist_block_top: the block's own histogram of the top kTopHistBits bits (fused into the extraction).
+void partition_block_level0(Workspace& ws, int key_bytes, void* keys, void* alt, u64 block_off, u64 n_block, int bits0, const u64* hist_block_top,
+                            u64* runs_out, u64* hist_next, cudaEvent_t* e0_out, cudaEvent_t* e1_out) {
+    const u64 C = 1ull << bits0;
+    DevBuf<u64> cstart_local;
+    partition_local_level0(ws, key_bytes, keys, alt, n_block, bits0, hist_block_top, cstart_local, e0_out, e1_out, block_off, block_off);
+    add_offset_kernel<<<(unsigned)((C + 1 + 255) / 256), 256, 0, ws.stream>>>(cstart_local.p, C + 1, block_off, runs_out);
+    ++ws.launches;
+    partition_next_hist(ws, key_bytes, alt, runs_out, bits0, n_block, kTopHistBits, hist_next, true);
+}
+
+// pass widths when the first pass (bits0) has been run already: the rest as partition_plan would split it; at least one
+// more pass (possibly of 0 bits: it gathers the blocks' runs into contiguous buckets)
+PartitionPlan partition_plan_streamed(int key_bytes, u64 n, int bits0) {
+    PartitionPlan full = partition_plan(key_bytes, n);
+    PartitionPlan p;
+    p.max_slots = full.max_slots;
+    const int rest = full.total_bits > bits0 ? full.total_bits - bits0 : 0;
+    const int rl = std::max(1, (rest + 9) / 10);
+    p.levels = 1 + rl;
+    p.bits[0] = bits0;
+    for (int l = 0; l < rl; ++l) p.bits[1 + l] = rest / rl + (l >= rl - rest % rl ? 1 : 0);
+    p.total_bits = bits0 + rest;
+    return p;
 }
 
 // Count bit-mixed keys (see the file header).  in.keys holds them; in.scratch is a buffer of the same capacity; both are
@@ -882,8 +940,9 @@ bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, PartitionInpu
     out.m = 0;
     *m_distinct = 0; *n_self_rc = 0;
     if (where_keys) *where_keys = 0;
-    const bool plain = in.cstart.p == nullptr;
-    const u64 n_cap = plain ? in.n : in.n_cap;
+    const bool streamed = in.runs != nullptr;                            // per-block first pass done (partition_block_level0)
+    const bool plain = in.cstart.p == nullptr && !streamed;
+    const u64 n_cap = (plain || streamed) ? in.n : in.n_cap;
     if (n_cap == 0) { out.keys.reset(&ws, 0); out.counts.reset(&ws, 0); return true; }
     if (min_count < 1) min_count = 1;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -899,6 +958,23 @@ bool count_partitioned(Workspace& ws, int key_bytes, int key_bits, PartitionInpu
     while (level < plan.levels && done_bits < consumed) done_bits += plan.bits[level++];   // passes the caller has run already
     mark(0);
     DevBuf<u64> folded;
+    if (streamed) {
+        // second pass: gathers every block's run of each child while splitting it by the next bits
+        const int bits0 = in.runs_bits0, bits1 = plan.bits[1];
+        const u32 C = 1u << bits0;
+        folded.reset(&ws, (size_t)C << bits1);
+        fold_hist_kernel<<<(unsigned)((((size_t)C << bits1) + 255) / 256), 256, 0, s>>>(in.runs_hist_next, bits0 + kTopHistBits, bits0 + bits1, folded.p);
+        ++ws.launches;
+        const void* base[1] = {cur};
+        LevelTiming lt;
+        if (timing) { GSB_CUDA_TRY(cudaEventCreate(&lt.e0)); GSB_CUDA_TRY(cudaEventCreate(&lt.e1)); }
+        partition_pull_level(ws, key_bytes, base, in.runs_n_src, in.runs, bits0, 0, C, in.n, bits1, folded.p, other, nullptr, cstart, lt.e0, lt.e1, true);
+        if (timing) levels_ev.push_back(lt);
+        std::swap(cur, other);
+        n_parents = (u64)C << bits1;
+        consumed = bits0 + bits1;
+        level = 2;
+    }
     for (; level < plan.levels; ++level) {
         const int bits = plan.bits[level];
         const u64* hist_ready = nullptr;
