@@ -356,6 +356,20 @@ static bool ensure_windows(Exchange* x, Workspace& ws, u64 need_bytes, const std
         for (int r = 0; r < n; ++r) enough = enough && (*need_all)[r] <= x->peer_cap[r];
         if (enough) return true;
     }
+    if ((int)x->peer_ptr.size() == n) {
+        // A window that is about to be replaced must not be freed while a peer still maps it (CUDA IPC: undefined
+        // behaviour).  Whether ANY window may grow is something every rank sees alike: the needs (need_all) and the capacities
+        // of the last handshake are common knowledge; a caller without need_all may grow its own window, which only it
+        // knows, so then every mapping is dropped.  Peers close first, a barrier, and only then the owners free.
+        bool any = false;
+        for (int r = 0; r < n; ++r) {
+            const bool replace = !need_all || (int)x->peer_cap.size() != n || (*need_all)[r] > x->peer_cap[r];
+            if (!replace) continue;
+            any = true;
+            if (r != x->rank && x->peer_open[r]) { cudaIpcCloseMemHandle(x->peer_ptr[r]); x->peer_open[r] = 0; x->peer_ptr[r] = nullptr; }
+        }
+        if (any) (void)exchange_sum(x, ws, 0);                     // every peer has closed what will be freed
+    }
     if (need_bytes > x->recv_cap_bytes || !x->recv_buf) {
         ws.sync();
         if (x->recv_buf) GSB_CUDA_TRY(cudaFree(x->recv_buf));

@@ -184,7 +184,36 @@ size_t BlockReader::cut_point(size_t filled, bool eof) const {
         }
         line_end = ls;
     }
-    return 0;
+    // Not the four-line layout (wrapped sequence / quality lines, or very short lines): find the record boundaries the way
+    // the reference's parser does (src/FastqParser.hh:78-176), forwards from the start of the buffer -- which IS a record
+    // boundary.  Sequence lines run up to the first line that starts with '@' or '+'; quality lines run up to the first
+    // such line seen once the quality is at least as long as the sequence; that line is the next record's header.  The last
+    // record in the buffer may continue in the next block, so the cut is the start of the last header found.
+    size_t pos = 0, last_header = 0;
+    auto line_end_of = [&](size_t from) { size_t e = from; while (e < nl && b[e] != '\n') ++e; return e; };   // nl is just after a '\n'
+    while (pos < nl) {
+        if (b[pos] != '@') return nl;                        // malformed: hand everything over, the device parser reports it precisely
+        last_header = pos;
+        pos = line_end_of(pos) + 1;
+        size_t seq = 0, qual = 0;
+        bool plus = false;
+        while (pos < nl) {                                   // sequence lines
+            const size_t e = line_end_of(pos);
+            if (e > pos && (b[pos] == '@' || b[pos] == '+')) { plus = b[pos] == '+'; if (plus) pos = e + 1; break; }
+            seq += e - pos;
+            pos = e + 1;
+        }
+        if (!plus) { if (pos < nl) return nl; break; }       // '@' where '+' was due: malformed; or the buffer ended inside the sequence
+        bool next_record = false;
+        while (pos < nl) {                                   // quality lines
+            const size_t e = line_end_of(pos);
+            if (e > pos && (b[pos] == '@' || b[pos] == '+') && qual >= seq) { next_record = true; break; }
+            qual += e - pos;
+            pos = e + 1;
+        }
+        if (!next_record) break;                             // the buffer ended inside (or right behind) this record
+    }
+    return last_header;
 }
 
 bool BlockReader::next(const uint8_t*& data, size_t& size, bool& last) {

@@ -484,6 +484,35 @@ def test_goss_cli_writes_the_reference_file_set(tmp_path):
     assert r.returncode == 1 and "bad.fq" in r.stderr and "error performing build-graph" in r.stderr
 
 
+def test_goss_cli_wrapped_fastq_across_blocks(tmp_path):
+    """Multi-line (wrapped) FASTQ records, quality lines that start with '@' or '+', streamed as 1 MiB blocks by the C++ host:
+    the block reader finds record boundaries with the reference's own state machine (src/FastqParser.hh:78-176) when the
+    four-line heuristic finds none, and the device frames the irregular blocks; files identical to the oracle's."""
+    import subprocess
+    goss = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gossamer_b200", "goss")
+    rng = np.random.default_rng(12)
+    g = bytes(S.genome(40_000, 9))
+    recs = []
+    for i in range(16_000):
+        a = int(rng.integers(0, len(g) - 150))
+        seq = g[a:a + 150]
+        qual = bytearray(b"I" * 150)
+        if i % 7 == 0:
+            qual[60] = ord("@")                               # a wrapped quality line that starts with '@'
+        if i % 11 == 0:
+            qual[120] = ord("+")
+        recs.append(b"@w%d\n" % i + b"\n".join(seq[j:j + 60] for j in range(0, 150, 60)) + b"\n+\n"
+                    + b"\n".join(bytes(qual[j:j + 60]) for j in range(0, 150, 60)) + b"\n")
+    text = b"".join(recs)                                     # ~5.3 MB -> six blocks
+    (tmp_path / "wrapped.fq").write_bytes(text)
+    want, _ = O.build_graph([(text, O.FASTQ)], 25, min_count=1, threads=4, base="w")
+    r = subprocess.run([goss, "build-graph", "-k", "25", "-i", str(tmp_path / "wrapped.fq"), "-O", str(tmp_path / "w"), "--block-mb", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = {p.name: p.read_bytes() for p in tmp_path.iterdir() if p.name.startswith("w.") or p.name.startswith("w-")}
+    assert not _diff(got, want.files())
+
+
 def test_k_range_and_call_order_errors():
     with pytest.raises(G.GossamerError) as e:
         G.Builder(G.GRAPH, 63)
