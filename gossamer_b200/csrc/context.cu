@@ -473,7 +473,11 @@ void process_block(gsb_ctx* c, const u8* text, u64 n, int format, u32 flags) {
     ingest_fill_line_starts(text, n, tile_counts.p, line_start.p, n_lines, s, &ws.launches);
 
     // K1b: framing
-    ingest_classify(text, line_start.p, n_lines, format, file_start ? 1 : 0, c->line_base[format], kind.p, nsym.p, c->status.p, s, &ws.launches);
+    {
+        DevBuf<u32> fq_scratch;                                // irregular FASTQ layouts are framed in parallel (speculate + verify, ingest.cu)
+        if (format == GSB_FMT_FASTQ && n_lines) fq_scratch.reset(&ws, ingest_fastq_scratch_words(n_lines));
+        ingest_classify(text, line_start.p, n_lines, format, file_start ? 1 : 0, c->line_base[format], kind.p, nsym.p, c->status.p, s, &ws.launches, fq_scratch.p);
+    }
     ingest_symbol_offsets(nsym.p, sym_off.p, n_lines, scalars.p + 1, scan_tmp.p, s, &ws.launches);
     GSB_CUDA_TRY(cudaMemcpyAsync(sym_off.p + n_lines, scalars.p + 1, 4, cudaMemcpyDeviceToDevice, s));
     IngestStatus st; u32 block_syms = 0;

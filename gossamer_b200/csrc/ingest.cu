@@ -218,6 +218,94 @@ __global__ void fastq_sequential_kernel(const u8* __restrict__ text, const u32* 
     st->n_reads += reads;
 }
 
+// FASTQ pass 2'' (parallel, irregular layouts): SPECULATE, THEN VERIFY.  The state machine above is sequential because a
+// line's role depends on everything before it (a quality line may start with '@' or '+').  The line table is cut into
+// segments of kFqSegLines lines;
+//   fastq_anchor_kernel : one thread per segment looks for the first '@' line at or behind the segment's start from which
+//                         the machine frames kFqLookahead well-formed records in a row -- a quality line posing as a header
+//                         fails that within a record or two;
+//   fastq_segment_kernel: one thread per segment runs the machine from its anchor to the first header at or behind the
+//                         segment's end and checks that this is exactly the next segment's anchor.
+// Segment 0 starts at line 0, a record boundary by contract, so if every hand-over matches, the framing IS the sequential
+// one, by induction.  Any mismatch or parse error raises a flag and the block is framed again by the one-thread kernel,
+// which also produces the reference's exact error text.  Results go to separate arrays: the inputs stay intact for it.
+static const u32 kFqSegLines = 2048;
+static const int kFqLookahead = 3;
+static const u32 kFqNone = 0xffffffffu;
+
+// One record starting at header line L.  Returns the line behind the record (the next header, or n_lines), or kFqNone when
+// the record is malformed or runs into the end of the table before it is complete (need_complete) .  Optionally writes the
+// framing.  seq/qual lengths as in fastq_sequential_kernel.
+__device__ __forceinline__ u32 fastq_one_record(const u8* __restrict__ text, const u32* __restrict__ line_start, u32 n_lines, const u8* __restrict__ c0,
+                                                const u32* __restrict__ slen, u32 L, u8* __restrict__ kind_out, u32* __restrict__ nsym_out) {
+    if (!(slen[L] > 0 && c0[L] == 1)) return kFqNone;
+    const u32 hdr = L, hdr_len = slen[L];
+    u64 seq_len = 0;
+    for (;;) {
+        ++L;
+        if (L >= n_lines) return kFqNone;
+        if (slen[L] > 0 && c0[L] != 0) break;
+        if (kind_out) { kind_out[L] = LK_SEQ; nsym_out[L] = slen[L]; }
+        seq_len += slen[L];
+    }
+    if (c0[L] != 2) return kFqNone;
+    if (slen[L] > 1) {
+        if (hdr_len != slen[L]) return kFqNone;
+        const u8* a = text + line_start[hdr] + 1; const u8* b = text + line_start[L] + 1;
+        for (u32 i = 0; i + 1 < hdr_len; ++i) if (a[i] != b[i]) return kFqNone;
+    }
+    if (kind_out) { kind_out[L] = LK_SKIP; nsym_out[L] = 0; kind_out[hdr] = LK_SEP; nsym_out[hdr] = 1; }
+    u64 qual_len = 0;
+    for (;;) {
+        ++L;
+        if (L >= n_lines) break;
+        if (slen[L] > 0 && c0[L] != 0 && qual_len >= seq_len) break;
+        qual_len += slen[L];
+        if (kind_out) { kind_out[L] = LK_SKIP; nsym_out[L] = 0; }
+    }
+    if (seq_len != qual_len) return kFqNone;
+    return L;
+}
+
+__global__ void fastq_anchor_kernel(const u8* __restrict__ text, const u32* __restrict__ line_start, u32 n_lines, const u8* __restrict__ c0,
+                                    const u32* __restrict__ slen, u32 n_seg, u32* __restrict__ anchor) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seg) return;
+    if (i == 0) { anchor[0] = 0; return; }
+    const u32 lo = i * kFqSegLines, hi = min(n_lines, lo + kFqSegLines);
+    u32 found = kFqNone;
+    for (u32 L = lo; L < hi && found == kFqNone; ++L) {
+        if (!(slen[L] > 0 && c0[L] == 1)) continue;
+        u32 p = L;
+        bool ok = true;
+        for (int r = 0; r < kFqLookahead && ok && p < n_lines; ++r) {
+            p = fastq_one_record(text, line_start, n_lines, c0, slen, p, nullptr, nullptr);
+            ok = p != kFqNone;
+        }
+        if (ok) found = L;
+    }
+    anchor[i] = found;
+}
+
+__global__ void fastq_segment_kernel(const u8* __restrict__ text, const u32* __restrict__ line_start, u32 n_lines, const u8* __restrict__ c0,
+                                     const u32* __restrict__ slen, u32 n_seg, const u32* __restrict__ anchor, u8* __restrict__ kind_out,
+                                     u32* __restrict__ nsym_out, u32* __restrict__ failed, u64* __restrict__ n_reads) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seg) return;
+    u32 L = anchor[i];
+    if (L == kFqNone) return;                                  // no record starts in this segment: an earlier one runs through it
+    u32 next = n_lines;                                        // where the next segment that has an anchor takes over
+    for (u32 j = i + 1; j < n_seg; ++j) if (anchor[j] != kFqNone) { next = anchor[j]; break; }
+    u32 reads = 0;
+    while (L < next) {
+        L = fastq_one_record(text, line_start, n_lines, c0, slen, L, kind_out, nsym_out);
+        if (L == kFqNone) { atomicOr(failed, 1u); return; }    // malformed (or truncated) record: the one-thread kernel renders the error
+        ++reads;
+    }
+    if (L != next) { atomicOr(failed, 1u); return; }           // the hand-over does not match: speculation failed
+    if (reads) atomicAdd(n_reads, (u64)reads);
+}
+
 // ------------------------------------------------------------------------------------------
 // K2: pack.  One thread per 32 output symbols -> one u64 of 2-bit codes (symbol j of the word
 // at bits [62-2j, 63-2j]) and one u32 of valid bits (symbol j at bit 31-j).
@@ -542,8 +630,15 @@ void ingest_fill_line_starts(const u8* text, u64 n, const u32* tile_offsets, u32
 
 static inline int line_grid(u32 n) { int g = (int)((n + 255) / 256); return g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g); }
 
+__global__ void fastq_add_reads_kernel(IngestStatus* st, u64 reads) { st->n_reads += reads; }
+
+u64 ingest_fastq_scratch_words(u32 n_lines) {                  // u32 words of scratch for the speculative FASTQ framing
+    const u64 n_seg = (n_lines + kFqSegLines - 1) / kFqSegLines;
+    return ((n_seg + 2 + 1) & ~1ull) + 2 + (u64)n_lines + ((u64)n_lines + 3) / 4 + 4;
+}
+
 void ingest_classify(const u8* text, const u32* line_start, u32 n_lines, int format, int file_start, u64 line_base,
-                     u8* kind, u32* nsym, IngestStatus* st_dev, cudaStream_t s, u64* launches) {
+                     u8* kind, u32* nsym, IngestStatus* st_dev, cudaStream_t s, u64* launches, u32* fq_scratch) {
     if (n_lines == 0) return;
     const int g = line_grid(n_lines);
     if (format == GSB_FMT_FASTA) {
@@ -566,10 +661,39 @@ void ingest_classify(const u8* text, const u32* line_start, u32 n_lines, int for
         }
         if (regular) {
             fastq_apply_regular_kernel<<<g, 256, 0, s>>>(n_lines, kind, nsym, st_dev);
+            ++*launches;
         } else {
-            fastq_sequential_kernel<<<1, 32, 0, s>>>(text, line_start, n_lines, kind, nsym, line_base, st_dev);
+            // irregular layout: speculative parallel framing, verified; the one-thread machine only if that fails
+            bool framed = false;
+            if (fq_scratch && n_lines > kFqSegLines) {
+                const u32 n_seg = (n_lines + kFqSegLines - 1) / kFqSegLines;
+                u32* anchor = fq_scratch;                                       // [n_seg]
+                u32* failed = fq_scratch + n_seg;                               // [1] (+1 pad)
+                u64* reads = reinterpret_cast<u64*>(fq_scratch + ((n_seg + 2 + 1) & ~1u));   // [1], 8-byte aligned
+                u32* nsym_out = reinterpret_cast<u32*>(reads + 1);              // [n_lines]
+                u8* kind_out = reinterpret_cast<u8*>(nsym_out + n_lines);       // [n_lines]
+                GSB_CUDA_TRY(cudaMemsetAsync(failed, 0, 8, s));
+                GSB_CUDA_TRY(cudaMemsetAsync(reads, 0, 8, s));
+                fastq_anchor_kernel<<<(n_seg + 127) / 128, 128, 0, s>>>(text, line_start, n_lines, kind, nsym, n_seg, anchor);
+                fastq_segment_kernel<<<(n_seg + 127) / 128, 128, 0, s>>>(text, line_start, n_lines, kind, nsym, n_seg, anchor, kind_out, nsym_out, failed, reads);
+                *launches += 2;
+                u32 h_failed = 1; u64 h_reads = 0;
+                GSB_CUDA_TRY(cudaMemcpyAsync(&h_failed, failed, 4, cudaMemcpyDeviceToHost, s));
+                GSB_CUDA_TRY(cudaMemcpyAsync(&h_reads, reads, 8, cudaMemcpyDeviceToHost, s));
+                GSB_CUDA_TRY(cudaStreamSynchronize(s));
+                if (!h_failed) {
+                    GSB_CUDA_TRY(cudaMemcpyAsync(kind, kind_out, n_lines, cudaMemcpyDeviceToDevice, s));
+                    GSB_CUDA_TRY(cudaMemcpyAsync(nsym, nsym_out, (size_t)n_lines * 4, cudaMemcpyDeviceToDevice, s));
+                    fastq_add_reads_kernel<<<1, 1, 0, s>>>(st_dev, h_reads);
+                    ++*launches;
+                    framed = true;
+                }
+            }
+            if (!framed) {
+                fastq_sequential_kernel<<<1, 32, 0, s>>>(text, line_start, n_lines, kind, nsym, line_base, st_dev);
+                ++*launches;
+            }
         }
-        ++*launches;
     }
 }
 

@@ -79,7 +79,8 @@ void ingest_count_newlines(const u8* text, u64 n, u32* tile_counts, cudaStream_t
 void ingest_scan_tiles(u32* tile_counts, u32 tiles, u32* total, cudaStream_t s, u64* launches);
 void ingest_fill_line_starts(const u8* text, u64 n, const u32* tile_offsets, u32* line_start, u32 n_lines, cudaStream_t s, u64* launches);
 void ingest_classify(const u8* text, const u32* line_start, u32 n_lines, int format, int file_start, u64 line_base,
-                     u8* kind, u32* nsym, IngestStatus* st_dev, cudaStream_t s, u64* launches);
+                     u8* kind, u32* nsym, IngestStatus* st_dev, cudaStream_t s, u64* launches, u32* fq_scratch = nullptr);
+u64 ingest_fastq_scratch_words(u32 n_lines);     // scratch the irregular-FASTQ framing wants (u32 words); without it: one thread
 void ingest_symbol_offsets(const u32* nsym, u32* sym_off, u32 n_lines, u32* total_dev, u32* tmp, cudaStream_t s, u64* launches);
 void ingest_pack(const u8* text, u64 text_bytes, const u32* line_start, const u8* kind, const u32* sym_off, u32 n_lines,
                  const u8* carry, u32 n_carry, u64 n_sym_total, u64* codes, u32* valid, u64 n_words, u32* word_line /* scratch [n_words] */,

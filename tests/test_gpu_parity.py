@@ -148,6 +148,58 @@ def test_fastq_errors_match_reference_text(text, msg):
     assert str(oe.value) == msg
 
 
+def _irregular_fastq(n_rec, seed, deceptive=False, bad_at=None):
+    """Thousands of lines of FASTQ that is NOT in the four-line layout: wrapped sequence and quality lines, empty reads,
+    quality lines that start with '@' / '+'; deceptive: every quality block contains three well-formed fake records."""
+    rng = np.random.default_rng(seed)
+    g = bytes(S.genome(30_000, seed))
+    out = []
+    for i in range(n_rec):
+        if deceptive:
+            a = int(rng.integers(0, len(g) - 33))
+            seq = g[a:a + 33]
+            qual_lines = [b"@f", b"ACGT", b"+", b"IIII"] * 3                           # 33 characters that read like three records
+            rec = b"@d%d\n" % i + seq[:17] + b"\n" + seq[17:] + b"\n+\n" + b"\n".join(qual_lines) + b"\n"
+        else:
+            n = int(rng.integers(0, 5)) * 37 if i % 13 == 0 else int(rng.integers(60, 140))   # now and then an empty read
+            a = int(rng.integers(0, len(g) - 200))
+            seq = g[a:a + n]
+            width = [60, 1000, 25][i % 3]
+            qual = bytearray(b"I" * n)
+            if n > 61 and i % 5 == 0:
+                qual[60 if width == 60 else 25] = ord("@")
+            if n > 51 and i % 7 == 0:
+                qual[50] = ord("+")
+            sl = [seq[j:j + width] for j in range(0, n, width)] or [b""]
+            ql = [bytes(qual[j:j + width]) for j in range(0, n, width)] or [b""]
+            if bad_at is not None and i == bad_at:
+                ql[-1] = ql[-1] + b"I"                                                   # quality one longer than the sequence
+            rec = b"@q%d extra\n" % i + b"\n".join(sl) + b"\n+" + (b"q%d extra" % i if i % 4 == 0 else b"") + b"\n" + b"\n".join(ql) + b"\n"
+        out.append(rec)
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("kind,n_rec", [("mixed", 9000), ("deceptive", 6000), ("mixed", 700)])
+def test_irregular_fastq_is_framed_in_parallel_and_exactly(kind, n_rec):
+    # blocks of more than 2048 lines outside the four-line layout go through the speculate-and-verify framing (ingest.cu);
+    # the deceptive input makes its anchors fail verification, so the one-thread machine takes over: same reads either way
+    text = _irregular_fastq(n_rec, 3 if kind == "mixed" else 4, deceptive=kind == "deceptive")
+    n_want = len(O.frame([(text, O.FASTQ)]))
+    lo, hi, n_reads = G.debug_extract(text, G.FASTQ, G.GRAPH, 15)
+    olo, ohi, on = O.extract([(text, O.FASTQ)], 16, O.MODE_GRAPH)
+    assert n_reads == n_want == on == n_rec
+    assert sorted(_keys(lo, hi)) == sorted(_fold(_keys(olo, ohi)))
+
+
+def test_irregular_fastq_error_deep_inside_has_the_reference_text():
+    text = _irregular_fastq(9000, 5, bad_at=7000)
+    with pytest.raises(O.OracleParseError) as oe:
+        O.frame([(text, O.FASTQ)])
+    with pytest.raises(G.ParseError) as e:
+        G.debug_extract(text, G.FASTQ, G.GRAPH, 15)
+    assert e.value.message == str(oe.value) and "length mistmatch" in e.value.message
+
+
 def test_fasta_error_matches_reference_text():
     with pytest.raises(G.ParseError) as e:
         G.debug_extract(b"ACGT\n", G.FASTA, G.GRAPH, 3)
