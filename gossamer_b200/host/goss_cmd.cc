@@ -208,10 +208,13 @@ void run_build(const BuildOptions& opt, const GossCmdContext& cxt, int kind) {
     int rc = gsb_create(&cfg, &h.c);
     if (rc != GSB_OK) throw Error{std::string(gsb_last_error(nullptr)) + "\n"};
 
+    // The reference's progress lines (src/GossCmdBuildGraph.cc:310-419, src/GossCmdBuildKmerSet.tcc:221-331) are kept where
+    // they have a meaning here; the hash-table lines (slot bits, table bits, load, spills) have none: nothing is hashed.
+    log(info, "accumulating edges.");
     // line files first, then FASTA, then FASTQ (src/GossCmdBuildGraph.cc:284-300)
     struct Item { const std::vector<std::string>* names; int format; };
     const Item items[3] = {{&opt.lines, GSB_FMT_LINE}, {&opt.fastas, GSB_FMT_FASTA}, {&opt.fastqs, GSB_FMT_FASTQ}};
-    uint64_t n_files = 0;
+    uint64_t n_files = 0, n_blocks = 0;
     for (const Item& it : items)
         for (const std::string& name : *it.names) {
             ++n_files;
@@ -224,6 +227,11 @@ void run_build(const BuildOptions& opt, const GossCmdContext& cxt, int kind) {
                 // block is synchronous, so that a parse error is always reported while its file is the current one
                 rc = gsb_push_block(h.c, data, size, it.format, last ? GSB_BLOCK_LAST_OF_FILE : GSB_BLOCK_ASYNC);
                 if (rc != GSB_OK) fail_from_library(h.c, rc, name);
+                if ((++n_blocks & 15) == 0) {                                    // the reference ticks on its hash-table load (:345-358)
+                    gsb_stats pst;
+                    gsb_get_stats(h.c, &pst);
+                    log(info, "processed " + std::to_string(pst.n_symbols) + " symbols in " + std::to_string(pst.bytes_in) + " input bytes.");
+                }
             }
         }
     if (n_files == 0) throw Error{"No valid reads.\n"};                          // src/ReverseComplementAdapter.hh:77-86
@@ -234,6 +242,11 @@ void run_build(const BuildOptions& opt, const GossCmdContext& cxt, int kind) {
     if (counts.n_reads == 0) throw Error{"No valid reads.\n"};
     log(info, "sorting done.");
     log(info, std::string("estimated number of ") + (kind == GSB_KIND_GRAPH ? "edges" : "kmers") + " is " + std::to_string(counts.n_kept));
+    {
+        gsb_stats bst;
+        gsb_get_stats(h.c, &bst);
+        log(info, bst.n_batches > 1 ? "merging temporary graphs" : "writing out graph (no merging necessary).");   // :390 / :407
+    }
     OutputFiles files;
     rc = gsb_emit(h.c, opt.out.c_str(), files.sink());
     if (rc != GSB_OK) {
@@ -249,6 +262,7 @@ void run_build(const BuildOptions& opt, const GossCmdContext& cxt, int kind) {
        << " merge " << st.ms_merge << " emit " << st.ms_emit << "; " << st.n_batches << " batch(es), " << st.kernel_launches
        << " kernel launches, " << files.bytes_written() << " bytes written";
     log(info, os.str());
+    log(info, "finish graph build");                                             // :418-419
     log(info, "total build time: " + std::to_string(secs));
 }
 
