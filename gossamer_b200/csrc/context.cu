@@ -210,6 +210,12 @@ int g_sampled_survivors = 0;        // test switch: re-partition the survivors w
 
 thread_local std::string g_create_error;
 
+// leaves only when the emitter's writer thread has handed over (or dropped) everything queued: the caller's sink may go away
+struct RingGuard {
+    EmitRing* ring;
+    ~RingGuard() { if (ring && ring->created) ring->wait_idle(); }
+};
+
 template <typename F>
 int guarded(gsb_ctx* ctx, F&& body) {
     try {
@@ -1004,7 +1010,8 @@ int gsb_emit(gsb_ctx* c, const char* prefix, const gsb_sink* sink) {
         if (!c->counted) throw StatusError{GSB_EINVAL, "gsb_emit before gsb_finish_counting"};
         Emitter em;
         em.ws = &c->ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
-        if (sink) { c->ring.create(c->ws); c->ring.drop(); em.ring = &c->ring; }
+        RingGuard ring_guard{sink ? &c->ring : nullptr};           // whatever happens below, the writer thread is done with `sink` on return
+        if (sink) { c->ring.create(c->ws); c->ring.drop(); c->ring.sink = sink; em.ring = &c->ring; }
         if (c->comm && !c->gathered && !c->dist_ready) {
             // peer memory is not available here: fall back to shipping every slice to rank 0
             c->timer.start();
@@ -1183,7 +1190,8 @@ int gsb_kmerset_merge_annotate(gsb_ctx* c, const char* lhs_prefix, const char* r
         c->counted = true;
         Emitter em;
         em.ws = &c->ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
-        if (sink) { c->ring.create(c->ws); c->ring.drop(); em.ring = &c->ring; }
+        RingGuard ring_guard{sink ? &c->ring : nullptr};           // whatever happens below, the writer thread is done with `sink` on return
+        if (sink) { c->ring.create(c->ws); c->ring.drop(); c->ring.sink = sink; em.ring = &c->ring; }
         c->timer.start();
         const std::string out(out_prefix);
         write_kmer_set_files(c, em, out);
@@ -1235,7 +1243,8 @@ int gsb_kmerset_near_kmers(gsb_ctx* c, const char* prefix, const gsb_source* src
         c->timer.stop(c->stats.ms_reduce);
         Emitter em;
         em.ws = &ws; em.sink = sink; em.pinned = c->pinned; em.pinned_bytes = c->pinned_bytes;
-        if (sink) { c->ring.create(ws); c->ring.drop(); em.ring = &c->ring; }
+        RingGuard ring_guard{sink ? &c->ring : nullptr};
+        if (sink) { c->ring.create(ws); c->ring.drop(); c->ring.sink = sink; em.ring = &c->ring; }
         em.put_device(p + ".lhs-bits", nl.p, words * 8);
         em.put_device(p + ".rhs-bits", nr.p, words * 8);
         em.flush();

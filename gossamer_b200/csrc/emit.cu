@@ -41,34 +41,49 @@ static void sink_fail(const std::string& what, const std::string& name) { throw 
 void Emitter::put_host(const std::string& name, const void* data, u64 len) {
     bytes_out += len;
     if (!sink) return;
+    if (ring) { ring_put_host(name, len, 0, data, len); return; }
     void* h = nullptr;
     if (sink->open(sink->user, name.c_str(), len, &h) != 0) sink_fail("open", name);
     if (len && sink->pwrite(sink->user, h, 0, data, len) != 0) sink_fail("pwrite", name);
     if (sink->close(sink->user, h) != 0) sink_fail("close", name);
 }
 
+// ---- the ring and its writer thread ----------------------------------------------------------------------------------
 void EmitRing::create(Workspace& ws) {
     if (created) return;
+    device = ws.device;
     GSB_CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
     for (int i = 0; i < kSlots; ++i) {
         dev[i] = (u8*)ws.alloc(kChunk);
         GSB_CUDA_TRY(cudaMallocHost((void**)&host[i], kChunk));
         GSB_CUDA_TRY(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
         GSB_CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        slot_busy[i] = false;
     }
+    stop = false;
+    worker = std::thread([this] { run(); });
     created = true;
+}
+
+void EmitRing::wait_idle() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv_idle.wait(lk, [this] { return queue.empty(); });
 }
 
 void EmitRing::drop() {
     if (!created) return;
-    cudaStreamSynchronize(copy);
-    for (int i = 0; i < kSlots; ++i) pend[i] = Pending();
-    head = 0;
+    wait_idle();
+    std::lock_guard<std::mutex> lk(mu);
+    error.clear();
+    handles.clear();
 }
 
 void EmitRing::destroy(Workspace& ws) {
     if (!created) return;
-    drop();
+    wait_idle();
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv_work.notify_all();
+    if (worker.joinable()) worker.join();
     for (int i = 0; i < kSlots; ++i) {
         if (dev[i]) ws.release(dev[i], kChunk);
         if (host[i]) cudaFreeHost(host[i]);
@@ -79,50 +94,120 @@ void EmitRing::destroy(Workspace& ws) {
     created = false;
 }
 
-void Emitter::ring_deliver(int slot) {
-    EmitRing::Pending& p = ring->pend[slot];
-    if (!p.busy) return;
-    GSB_CUDA_TRY(cudaEventSynchronize(ring->done[slot]));
-    p.busy = false;
-    if (!p.prefix.empty()) memcpy(ring->host[slot], p.prefix.data(), p.prefix.size());
-    if (p.len && sink->pwrite(sink->user, p.handle, p.file_off, ring->host[slot], p.len) != 0) sink_fail("pwrite", p.name);
-    if (p.close && sink->close(sink->user, p.handle) != 0) sink_fail("close", p.name);
+int EmitRing::acquire_slot() {
+    std::unique_lock<std::mutex> lk(mu);
+    int slot = -1;
+    cv_idle.wait(lk, [&] {
+        for (int i = 0; i < kSlots; ++i) if (!slot_busy[i]) { slot = i; return true; }
+        return false;
+    });
+    slot_busy[slot] = true;
+    return slot;
+}
+
+void EmitRing::push(Job&& j) {
+    { std::lock_guard<std::mutex> lk(mu); queue.push_back(std::move(j)); }
+    cv_work.notify_one();
+}
+
+// Writer thread.  Queues the device -> host copy of every job that has none yet (so PCIe stays busy while a callback
+// runs), then completes the oldest job: waits for its copy, makes the sink calls, frees its slot.
+void EmitRing::run() {
+    cudaSetDevice(device);
+    for (;;) {
+        Job* job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_work.wait(lk, [this] { return stop || !queue.empty(); });
+            if (queue.empty()) return;                            // stop requested and nothing left
+            for (Job& j : queue) {
+                if (j.slot >= 0 && !j.issued) {
+                    if (j.len) {
+                        cudaStreamWaitEvent(copy, ready[j.slot], 0);
+                        cudaMemcpyAsync(host[j.slot], dev[j.slot], j.len, cudaMemcpyDeviceToHost, copy);
+                    }
+                    cudaEventRecord(done[j.slot], copy);
+                    j.issued = true;
+                }
+            }
+            job = &queue.front();                                 // deque: stays valid while the producer appends
+        }
+        std::string fail;
+        bool skip;
+        { std::lock_guard<std::mutex> lk(mu); skip = !error.empty(); }
+        if (job->slot >= 0 && cudaEventSynchronize(done[job->slot]) != cudaSuccess) { fail = "device to host copy failed for " + job->name; cudaGetLastError(); }
+        if (!skip && fail.empty()) {
+            const u8* data = job->slot >= 0 ? host[job->slot] : job->bytes.data();
+            if (job->slot >= 0 && !job->bytes.empty()) memcpy(host[job->slot], job->bytes.data(), job->bytes.size());   // header bytes over the payload
+            void* h = nullptr;
+            if (job->open) {
+                if (sink->open(sink->user, job->name.c_str(), job->size_hint, &h) != 0) fail = "open failed for " + job->name;
+                else handles[job->name] = h;
+            } else {
+                h = handles[job->name];
+            }
+            if (fail.empty() && job->len && sink->pwrite(sink->user, h, job->file_off, data, job->len) != 0) fail = "pwrite failed for " + job->name;
+            if (fail.empty() && job->close) {
+                if (sink->close(sink->user, h) != 0) fail = "close failed for " + job->name;
+                handles.erase(job->name);
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!fail.empty() && error.empty()) error = fail;
+            if (job->slot >= 0) slot_busy[job->slot] = false;
+            queue.pop_front();
+        }
+        cv_idle.notify_all();
+    }
 }
 
 void Emitter::flush() {
     if (!ring || !sink) return;
-    for (int i = 0; i < EmitRing::kSlots; ++i) ring_deliver((ring->head + i) % EmitRing::kSlots);   // oldest first
+    ring->wait_idle();
+    std::string err;
+    { std::lock_guard<std::mutex> lk(ring->mu); err = ring->error; }
+    if (!err.empty()) throw StatusError{GSB_EIO, err};
 }
 
-// [file_off, file_off + len) of an open file from device memory, through the ring; the handle is closed after the last chunk
-void Emitter::ring_put(void* handle, const std::string& name, u64 file_off, const void* dev, u64 len, const void* host_prefix, u64 prefix_len) {
+// [file_off, file_off + len) of file `name` from device memory, through the ring: opened before the first chunk, closed after
+// the last one
+void Emitter::ring_put(const std::string& name, u64 size_hint, u64 file_off, const void* dev, u64 len, const void* host_prefix, u64 prefix_len) {
     for (u64 off = 0; off < len || off == 0; off += EmitRing::kChunk) {
         const u64 chunk = std::min<u64>(EmitRing::kChunk, len - off);
-        const int slot = ring->head;
-        ring_deliver(slot);                                         // the slot's previous chunk goes to the sink first
-        ring->head = (ring->head + 1) % EmitRing::kSlots;
+        EmitRing::Job j;
+        j.name = name; j.size_hint = size_hint; j.file_off = file_off + off; j.len = chunk;
+        j.open = off == 0; j.close = off + chunk >= len;
+        j.slot = ring->acquire_slot();
         if (chunk) {
-            GSB_CUDA_TRY(cudaMemcpyAsync(ring->dev[slot], (const u8*)dev + off, chunk, cudaMemcpyDeviceToDevice, ws->stream));
-            GSB_CUDA_TRY(cudaEventRecord(ring->ready[slot], ws->stream));
-            GSB_CUDA_TRY(cudaStreamWaitEvent(ring->copy, ring->ready[slot], 0));
-            GSB_CUDA_TRY(cudaMemcpyAsync(ring->host[slot], ring->dev[slot], chunk, cudaMemcpyDeviceToHost, ring->copy));
+            cudaError_t e = cudaMemcpyAsync(ring->dev[j.slot], (const u8*)dev + off, chunk, cudaMemcpyDeviceToDevice, ws->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ring->ready[j.slot], ws->stream);
+            if (e != cudaSuccess) {                                 // the slot must not stay taken
+                { std::lock_guard<std::mutex> lk(ring->mu); ring->slot_busy[j.slot] = false; }
+                ring->cv_idle.notify_all();
+                GSB_CUDA_TRY(e);
+            }
         }
-        GSB_CUDA_TRY(cudaEventRecord(ring->done[slot], ring->copy));
-        EmitRing::Pending& p = ring->pend[slot];
-        p.busy = true; p.handle = handle; p.name = name; p.file_off = file_off + off; p.len = chunk;
-        p.close = off + chunk >= len;
-        p.prefix.clear();
-        if (off < prefix_len) p.prefix.assign((const u8*)host_prefix + off, (const u8*)host_prefix + std::min<u64>(prefix_len, off + chunk));
+        if (off < prefix_len) j.bytes.assign((const u8*)host_prefix + off, (const u8*)host_prefix + std::min<u64>(prefix_len, off + chunk));
+        ring->push(std::move(j));
         if (len == 0) break;
     }
+}
+
+void Emitter::ring_put_host(const std::string& name, u64 size_hint, u64 file_off, const void* data, u64 len) {
+    EmitRing::Job j;
+    j.name = name; j.size_hint = size_hint; j.file_off = file_off; j.len = len;
+    j.open = true; j.close = true;
+    j.bytes.assign((const u8*)data, (const u8*)data + len);
+    ring->push(std::move(j));
 }
 
 void Emitter::put_device(const std::string& name, const void* dev, u64 len, const void* host_prefix, u64 prefix_len) {
     bytes_out += len;
     if (!sink) return;
+    if (ring) { ring_put(name, len, 0, dev, len, host_prefix, prefix_len); return; }
     void* h = nullptr;
     if (sink->open(sink->user, name.c_str(), len, &h) != 0) sink_fail("open", name);
-    if (ring) { ring_put(h, name, 0, dev, len, host_prefix, prefix_len); return; }
     for (u64 off = 0; off < len; off += pinned_bytes) {
         u64 chunk = std::min<u64>(pinned_bytes, len - off);
         GSB_CUDA_TRY(cudaMemcpyAsync(pinned, (const u8*)dev + off, chunk, cudaMemcpyDeviceToHost, ws->stream));
@@ -138,9 +223,9 @@ void Emitter::put_device(const std::string& name, const void* dev, u64 len, cons
 void Emitter::put_device_at(const std::string& name, u64 total, u64 offset, const void* dev, u64 len) {
     bytes_out += len;
     if (!sink || !len) return;
+    if (ring) { ring_put(name, total, offset, dev, len, nullptr, 0); return; }
     void* h = nullptr;
     if (sink->open(sink->user, name.c_str(), total, &h) != 0) sink_fail("open", name);
-    if (ring) { ring_put(h, name, offset, dev, len, nullptr, 0); return; }
     for (u64 off = 0; off < len; off += pinned_bytes) {
         u64 chunk = std::min<u64>(pinned_bytes, len - off);
         GSB_CUDA_TRY(cudaMemcpyAsync(pinned, (const u8*)dev + off, chunk, cudaMemcpyDeviceToHost, ws->stream));
@@ -153,6 +238,7 @@ void Emitter::put_device_at(const std::string& name, u64 total, u64 offset, cons
 void Emitter::put_host_at(const std::string& name, u64 total, u64 offset, const void* data, u64 len) {
     bytes_out += len;
     if (!sink || !len) return;
+    if (ring) { ring_put_host(name, total, offset, data, len); return; }
     void* h = nullptr;
     if (sink->open(sink->user, name.c_str(), total, &h) != 0) sink_fail("open", name);
     if (sink->pwrite(sink->user, h, offset, data, len) != 0) sink_fail("pwrite", name);

@@ -1,8 +1,12 @@
 // kernels.h -- internal interface between the CUDA modules (ingest / sort / emit) and the
 // context that owns memory and orchestrates them.  Not part of the public ABI.
 #pragma once
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -208,30 +212,48 @@ void merge_disjoint_runs(Workspace& ws, int key_bytes, const void* ka, const u64
                          void* out_keys, u64* out_counts);
 
 // ---- emit.cu ---------------------------------------------------------------------------------
-// Device -> sink pipeline of the emitter: a ring of staging slots (device + pinned host) and a copy stream.  A file chunk
-// is copied device-to-device into a slot on the library's stream (the producer's buffer is free again at once), crosses
-// PCIe on the copy stream while the next emit kernels run, and is handed to the sink when its slot comes round again or at
-// Emitter::flush() -- the analogue of the reference's writer threads behind Graph::Builder (src/Graph.cc:148-150).
+// Device -> sink pipeline of the emitter: a ring of staging slots (device + pinned host), a copy stream and a WRITER THREAD
+// -- the analogue of the reference's writer threads behind Graph::Builder (src/Graph.cc:148-150).  The emitting thread only
+// copies a finished file chunk device-to-device into a free slot on the library's stream (the producer's buffer is free
+// again at once) and queues a job; the writer thread moves the chunk across PCIe on the copy stream (copies are queued ahead
+// of the callbacks), and makes EVERY sink call (open, pwrite, close), in queue order, so a sink never sees two threads.
 struct EmitRing {
     static const int kSlots = 8;
     static const size_t kChunk = 16ull << 20;
-    struct Pending {
-        bool busy = false, close = false;
-        void* handle = nullptr;
+    // One unit of work for the writer thread, delivered strictly in the order it was queued.
+    struct Job {
         std::string name;
+        u64 size_hint = 0;             // open(name, size_hint) ...
+        bool open = false, close = false;   // ... before / close after this job's write
         u64 file_off = 0, len = 0;
-        std::vector<u8> prefix;        // host bytes that override the start of this chunk (file headers)
+        int slot = -1;                 // >= 0: the bytes come from this staging slot (device -> pinned host); -1: from `bytes`
+        bool issued = false;           // the D2H copy has been queued on the copy stream
+        std::vector<u8> bytes;         // host data (slot < 0), or the host prefix that overrides the start of the chunk
     };
     cudaStream_t copy = nullptr;
+    int device = 0;
     u8* dev[kSlots] = {};
     u8* host[kSlots] = {};
     cudaEvent_t ready[kSlots], done[kSlots];
-    Pending pend[kSlots];
-    int head = 0;
+    bool slot_busy[kSlots] = {};
     bool created = false;
+    // writer thread state (guarded by mu)
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_idle;
+    std::deque<Job> queue;
+    std::map<std::string, void*> handles;      // files currently open at the sink (writer thread only)
+    const gsb_sink* sink = nullptr;
+    bool stop = false;
+    std::string error;                         // first failure on the writer thread; later jobs are dropped
     void create(Workspace& ws);
     void destroy(Workspace& ws);
-    void drop();                   // forget everything pending (after an error); waits for the copy stream
+    void drop();                   // waits until the writer is idle, forgets errors and open handles
+    int acquire_slot();            // blocks until a staging slot is free
+    void push(Job&& j);
+    void wait_idle();              // every queued job has reached the sink (or was dropped after an error)
+private:
+    void run();
 };
 
 struct Emitter {
@@ -240,7 +262,7 @@ struct Emitter {
     u64 bytes_out = 0;
     u8* pinned = nullptr;          // staging for device -> sink copies when there is no ring
     size_t pinned_bytes = 0;
-    EmitRing* ring = nullptr;      // optional: overlapped delivery (gsb_emit)
+    EmitRing* ring = nullptr;      // optional: overlapped delivery by a writer thread (gsb_emit)
     // whole file from host memory
     void put_host(const std::string& name, const void* data, u64 len);
     // whole file = optional host prefix that overrides the first prefix_len bytes + device payload
@@ -248,11 +270,12 @@ struct Emitter {
     // one piece of a file of `total` bytes (multi-GPU emission: every rank hands over its own pieces)
     void put_device_at(const std::string& name, u64 total, u64 offset, const void* dev, u64 len);
     void put_host_at(const std::string& name, u64 total, u64 offset, const void* data, u64 len);
-    // hands every chunk still in the ring to the sink; must be called before the sink's owner looks at the files
+    // waits until everything has reached the sink; throws what the writer thread ran into.  Must be called before the
+    // sink's owner looks at the files
     void flush();
 private:
-    void ring_put(void* handle, const std::string& name, u64 file_off, const void* dev, u64 len, const void* host_prefix, u64 prefix_len);
-    void ring_deliver(int slot);
+    void ring_put(const std::string& name, u64 size_hint, u64 file_off, const void* dev, u64 len, const void* host_prefix, u64 prefix_len);
+    void ring_put_host(const std::string& name, u64 size_hint, u64 file_off, const void* data, u64 len);
 };
 
 struct U128 { u64 lo, hi; };
