@@ -80,7 +80,7 @@ class GraphInfo(C.Structure):
 
 EXPORTS = ["gsb_kmerset_merge_annotate", "gsb_kmerset_near_kmers", "gsb_graph_peek", "gsb_graph_load", "gsb_graph_load_pairs", "gsb_graph_finish", "gsb_graph_dump", "gsb_create", "gsb_destroy", "gsb_last_error", "gsb_push_block", "gsb_push_device_block", "gsb_finish_counting",
            "gsb_emit", "gsb_timer_begin", "gsb_timer_end", "gsb_host_alloc", "gsb_host_free", "gsb_host_bind_near_device", "gsb_get_stats", "gsb_reset", "gsb_comm_make_id", "gsb_comm_attach", "gsb_gather_to_root", "gsb_plan_splitters", "gsb_samples_per_rank",
-           "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_sort_bench", "gsb_debug_set_tuning", "gsb_debug_set_partition", "gsb_debug_set_pairsort", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
+           "gsb_debug_copy_counts", "gsb_debug_sort_keys", "gsb_debug_sort_bench", "gsb_debug_set_tuning", "gsb_debug_set_partition", "gsb_debug_set_pairsort", "gsb_debug_plan", "gsb_debug_emit_sparse_array", "gsb_debug_emit_graph",
            "gsb_debug_extract"]
 
 _lib = None
@@ -546,6 +546,17 @@ def debug_set_partition(max_slots=0, total_bits=0):
 def host_bind_near_device(device):
     """Bind this process to the CPUs of the NUMA node the GPU hangs off (call before allocating pinned buffers)."""
     lib().gsb_host_bind_near_device(int(device))
+
+
+def debug_plan(what, key_bytes, key_bits, n, first_bits=0):
+    """Host-only: (levels, total bits, slots or capacity, [bits per pass]) of the counting (what=0), a streamed build (1), the pair sort (2)."""
+    out = (C.c_uint32 * 11)()
+    f = lib().gsb_debug_plan
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_uint32)]
+    rc = f(what, key_bytes, key_bits, n, first_bits, out)
+    if rc != 0:
+        raise GossamerError(rc, "gsb_debug_plan")
+    return int(out[0]), int(out[1]), int(out[2]), [int(x) for x in out[3:3 + int(out[0])]]
 
 
 def debug_set_pairsort(cap=0, bits=-1):

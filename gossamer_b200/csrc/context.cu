@@ -1563,6 +1563,25 @@ int gsb_debug_sort_bench(int device, uint64_t n, int key_bits, int iters, int tu
 
 int gsb_debug_set_partition(int max_slots, int total_bits) { partition_set_debug((u32)(max_slots < 0 ? 0 : max_slots), total_bits); return GSB_OK; }
 
+// host-only: the pass widths the counting / the pair sort would use (no device needed).  out = {levels, total bits, table
+// slots or bucket capacity, bits[0..7]}
+int gsb_debug_plan(int what, int key_bytes, int key_bits, uint64_t n, int first_bits, uint32_t* out) {
+    if (!out || (key_bytes != 8 && key_bytes != 16)) return GSB_EINVAL;
+    if (what == 0 || what == 1) {
+        const PartitionPlan p = what == 0 ? partition_plan(key_bytes, n) : partition_plan_streamed(key_bytes, n, first_bits);
+        out[0] = (uint32_t)p.levels; out[1] = (uint32_t)p.total_bits; out[2] = p.max_slots;
+        for (int i = 0; i < 8; ++i) out[3 + i] = (uint32_t)p.bits[i];
+        return GSB_OK;
+    }
+    if (what == 2) {
+        const PairSortPlan p = pairsort_plan(key_bytes, key_bits, n, first_bits);
+        out[0] = (uint32_t)p.levels; out[1] = (uint32_t)p.bits; out[2] = p.cap;
+        for (int i = 0; i < 8; ++i) out[3 + i] = (uint32_t)p.lb[i];
+        return GSB_OK;
+    }
+    return GSB_EINVAL;
+}
+
 int gsb_debug_set_pairsort(int cap, int bits) { pairsort_set_debug((u32)(cap < 0 ? 0 : cap), bits); return GSB_OK; }
 
 int gsb_debug_set_tuning(int id) { g_legacy_counting = (id >> 16) & 1; g_sampled_survivors = (id >> 17) & 1; sort_set_tuning(id & 0xFFFF); return GSB_OK; }

@@ -237,6 +237,7 @@ int gsb_debug_sort_bench(int device, uint64_t n, int key_bits, int iters, int tu
 int gsb_debug_set_tuning(int id);   /* bits 0-7 sweep tile shape, 8-15 profiling ablations, bit 16: contexts created afterwards count with the
                                        full LSD sort of raw keys (the round-1 path) instead of by partitioning */
 int gsb_debug_set_partition(int max_slots, int total_bits); /* bucket geometry of the partition counting, 0 = default; results never depend on it */
+int gsb_debug_plan(int what, int key_bytes, int key_bits, uint64_t n, int first_bits, uint32_t* out); /* host-only: pass widths of the counting (what = 0), of a streamed build (1), of the pair sort (2): out[11] = {levels, bits, slots|capacity, bits[8]} */
 int gsb_debug_set_pairsort(int cap, int bits); /* bucket capacity (0 = default) and partition bits (< 0 = default) of the pair sort; results never depend on them */
 int gsb_debug_emit_sparse_array(int device, const uint64_t* key_lo, const uint64_t* key_hi, uint64_t m,
                                 uint64_t universe_lo, uint64_t universe_hi, uint64_t m_est,

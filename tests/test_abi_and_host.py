@@ -160,3 +160,25 @@ def test_compressed_input_readers(tmp_path):
     (tmp_path / "junk.fq.bz2").write_bytes(b"this is not bzip2 data at all, not even close" * 10)
     r = subprocess.run([exe, str(tmp_path / "junk.fq.bz2")], capture_output=True)
     assert r.returncode == 1 and b"bzip2" in r.stderr
+
+
+def test_pass_planning_invariants():
+    """Host logic of partition.cu (no device): the pass widths of the counting, of a streamed build (first pass fixed at 8 bits,
+    run per block) and of the pair sort -- every pass at most 10 bits wide, the widths add up, buckets fit their tables with
+    head room, a streamed plan always has a gathering pass."""
+    import gossamer_b200 as G
+    for kb, key_bits in ((8, 64), (16, 112)):
+        for n in (0, 1, 100, 5_000, 300_000, 30_000_000, 198_333_373, 1_900_000_000, 40_000_000_000):
+            levels, total, slots, bits = G.debug_plan(0, kb, key_bits, n)
+            assert sum(bits) == total and len(bits) == levels and all(1 <= b <= 10 for b in bits)
+            cap = slots - slots // 8 - 2
+            assert n == 0 or (n >> total) <= cap // 2 or total == 40             # mean bucket at most half of what a table holds
+            slevels, stotal, sslots, sbits = G.debug_plan(1, kb, key_bits, n, 8)
+            assert sbits[0] == 8 and slevels >= 2 and sum(sbits) == stotal == max(total, 8) and all(0 <= b <= 10 for b in sbits[1:])
+            assert sslots == slots
+            for first in (0, 10):
+                plevels, ptotal, pcap, pb = G.debug_plan(2, kb, key_bits, n, first)
+                assert sum(pb) == ptotal and all(0 <= b <= 10 for b in pb) and ptotal <= key_bits
+                if first:
+                    assert pb[0] == 10 and plevels >= 1
+                assert n == 0 or ptotal == key_bits or (n >> ptotal) <= pcap // 2
