@@ -70,7 +70,7 @@ typedef struct gsb_config {
     int32_t device;            /* CUDA ordinal */
     uint64_t min_count;        /* 0/1 = keep all.  m>1 == build-graph followed by `trim-graph -C m-1`
                                   (src/GossCmdTrimGraph.cc:97-124); ignored for kmer sets */
-    uint64_t max_batch_keys;   /* 0 = choose from free HBM.  Keys buffered before a sort+reduce+merge
+    uint64_t max_batch_keys;   /* 0 = choose from free HBM.  Keys buffered before a count+merge
                                   round (the -B analogue, src/GossCmdBuildGraph.cc:436-447) */
     gsb_log_fn log;            /* may be NULL */
     void* log_user;
@@ -96,18 +96,20 @@ typedef struct gsb_sink {
 typedef struct gsb_stats {
     /* device time per phase, milliseconds, CUDA events on the library's stream */
     double ms_h2d, ms_scan, ms_extract, ms_sort, ms_reduce, ms_merge, ms_emit, ms_d2h, ms_exchange;
-    double ms_sort_sweeps;      /* sum of the radix sweep kernels alone (events around each launch) */
-    double ms_all_to_all;       /* the NCCL all-to-all alone (inside ms_exchange) */
-    double ms_unfold;           /* graph mode: reverse complements of the folded, filtered run + sort + merge */
-    uint64_t exchange_bytes_sent; /* bytes this rank sent to OTHER ranks in the all-to-all */
-    uint64_t exchange_peer_memory; /* 1 = fused partition+transfer into peer windows over NVLink, 0 = NCCL send/recv */
+    /* ms_sort = the partition passes of the counting (+ sorts of merged batches); ms_reduce = the shared-memory bucket count
+     * with the min-count filter; ms_unfold = reverse complements + pair sort of the survivors */
+    double ms_sort_sweeps;      /* sum of the partition (or radix sweep) kernels alone (events around each launch) */
+    double ms_all_to_all;       /* multi-GPU: the pass that pulls the instances over NVLink, alone (inside ms_exchange) */
+    double ms_unfold;           /* graph mode: reverse complements of the folded, filtered run + ordering by key */
+    uint64_t exchange_bytes_sent; /* instance bytes this rank moved from / to OTHER ranks in the exchange */
+    uint64_t exchange_peer_memory; /* 1 = exchange fused into the partition passes over peer windows (NVLink), 0 = NCCL send/recv */
     uint64_t bytes_in;          /* raw text bytes pushed */
     uint64_t bytes_out;         /* bytes handed to the sink */
     uint64_t n_symbols;         /* bases + separators in the packed symbol stream */
     uint64_t sort_key_bytes;    /* 8 or 16 */
-    uint64_t sort_passes;       /* radix passes actually run (after constant-digit skipping) */
-    uint64_t sort_passes_model; /* ceil(keybits/8) */
-    uint64_t n_batches;         /* sort+reduce rounds */
+    uint64_t sort_passes;       /* partition (or radix) passes actually launched */
+    uint64_t sort_passes_model; /* ceil(keybits/8): the 8-bit LSD passes SURVEY 8d's B_sort charges */
+    uint64_t n_batches;         /* count (+ merge) rounds */
     uint64_t kernel_launches;   /* launches of this library's kernels so far */
     uint64_t hbm_peak_bytes;    /* high-water mark of device allocations */
     uint64_t n_sorted_keys;     /* keys that went through the counting passes (graph mode: one per window,
