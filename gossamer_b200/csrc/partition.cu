@@ -247,13 +247,13 @@ __global__ void __launch_bounds__(kPtThreads, BPT == 1 ? 3 : 2) part_scatter_ker
         }
 #pragma unroll
         for (int j = 0; j < BPT; ++j) sum += c[j];
-        const u32 ex = block_exclusive_scan<u32, kPtThreads>(sum, (u32*)nullptr, scan_s);
         u64 g[BPT];
 #pragma unroll
-        for (int j = 0; j < BPT; ++j) {                                   // consumed after the scatter below
-            g[j] = 0;
+        for (int j = 0; j < BPT; ++j) {                                   // issued before the scan, consumed after the scatter below:
+            g[j] = 0;                                                     // the round trip to L2 overlaps both
             if (c[j]) g[j] = atomicAdd(&a.cursor[(((u64)cur.parent << a.bits) | (u32)(t * BPT + j)) * a.cstride], (u64)c[j]);
         }
+        const u32 ex = block_exclusive_scan<u32, kPtThreads>(sum, (u32*)nullptr, scan_s);
         {
             u32 run = ex;
 #pragma unroll
