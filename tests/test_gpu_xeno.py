@@ -40,11 +40,36 @@ def test_xenome_index_steps_bit_exact(k, n_bases, n_subst):
     assert not _diff(got2, want2)
     assert gray == wgray and gray > 0
     assert _popcount(want["both.lhs-bits"]) - _popcount(got2["both.lhs-bits"]) <= gray
-    if R.available() and k <= 62:
+    if R.available():
         st = R.Store()
         st.put_all(both_in)
         assert not _diff(got, R.merge_and_annotate(st, "ga", "ho", "both"))
         assert not _diff(got2, R.compute_near_kmers(st, "both", threads=2))
+
+
+@pytest.mark.parametrize("case", ["identical", "disjoint"])
+def test_xenome_index_steps_edge_cases(case):
+    import simreads_py as S
+    k = 21
+    graft, host = related_references(4000, 50, 11)
+    if case == "identical":
+        host = graft
+    else:
+        host = b">other\n" + bytes(S.genome(5000, 999)) + b"\n"
+    fg = O.build_kmer_set([(graft, O.FASTA)], k, base="ga")[0].files()
+    fh = O.build_kmer_set([(host, O.FASTA)], k, base="ho")[0].files()
+    both_in = dict(fg)
+    both_in.update(fh)
+    want, wstats = O.merge_and_annotate(both_in, "ga", "ho", "both")
+    got, stats = G.merge_and_annotate_kmer_sets(both_in, "ga", "ho", "both")
+    assert not _diff(got, want) and stats == wstats
+    want2, wgray = O.compute_near_kmers(want, "both")
+    got2, gray = G.compute_near_kmers(want, "both")
+    assert not _diff(got2, want2) and gray == wgray
+    if case == "identical":
+        assert stats[2] == stats[3] and gray == 0
+    else:
+        assert stats[2] == 0
 
 
 def test_xenome_errors():

@@ -197,3 +197,35 @@ def test_xenome_index_steps_equal_reference_commands(k, n_bases, n_subst):
     before = sum(bin(b).count("1") for b in ours["both.lhs-bits"])
     after = sum(bin(b).count("1") for b in ours2["both.lhs-bits"])
     assert gray > 0 and before - after <= gray
+
+
+@pytest.mark.parametrize("case", ["identical", "disjoint", "k63"])
+def test_xenome_index_steps_edge_cases_equal_reference(case):
+    """Both sets the same (everything common, nothing can turn gray), unrelated sets (nothing common), and the widest k."""
+    from xeno_cases import related_references
+    import simreads_py as S
+    k = 63 if case == "k63" else 21
+    graft, host = related_references(4000, 50, 11)
+    if case == "identical":
+        host = graft
+    elif case == "disjoint":
+        host = b">other\n" + bytes(S.genome(5000, 999)) + b"\n"
+    st1, f1 = R.build_kmer_set([(graft, 0)], k, base="ga")
+    st2, f2 = R.build_kmer_set([(host, 0)], k, base="ho")
+    st = R.Store()
+    st.put_all(f1)
+    st.put_all(f2)
+    theirs = R.merge_and_annotate(st, "ga", "ho", "both")
+    both_in = dict(f1)
+    both_in.update(f2)
+    ours, stats = O.merge_and_annotate(both_in, "ga", "ho", "both")
+    assert not _diff(ours, theirs)
+    if case == "identical":
+        assert stats[0] == stats[1] == stats[2] == stats[3]
+    if case == "disjoint":
+        assert stats[2] == 0
+    theirs2 = R.compute_near_kmers(st, "both", threads=2)
+    ours2, gray = O.compute_near_kmers(ours, "both")
+    assert not _diff(ours2, theirs2)
+    if case == "identical":
+        assert gray == 0
