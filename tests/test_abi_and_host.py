@@ -98,6 +98,39 @@ def test_cli_usage_errors_exit_1(tmp_path):
     assert _goss("help").returncode == 0
 
 
+def test_cli_file_set_commands_usage(tmp_path):
+    """Option surface of the commands that read existing file sets (host/goss_rewrite.cc): every one of these fails (or prints
+    its help) before a device is touched."""
+    r = _goss("trim-graph", "-G", "in", "-O", str(tmp_path / "out"))
+    assert r.returncode == 1 and "--cutoff" in r.stderr
+    r = _goss("trim-graph", "-O", str(tmp_path / "out"), "-C", "1")
+    assert r.returncode == 1 and "--graph-in" in r.stderr
+    r = _goss("trim-graph", "-G", "a", "-G", "b", "-O", str(tmp_path / "out"), "-C", "1")
+    assert r.returncode == 1 and "only be given once" in r.stderr
+    r = _goss("trim-graph", "-G", "a", "-O", str(tmp_path / "out"), "-C", "minus-one")
+    assert r.returncode == 1 and "is invalid" in r.stderr
+    r = _goss("merge-graphs", "-O", str(tmp_path / "out"))
+    assert r.returncode == 1 and "At least one input graph" in r.stderr
+    r = _goss("merge-kmer-sets", "-G", "a", "-G", "b")
+    assert r.returncode == 1 and "--graph-out" in r.stderr
+    r = _goss("merge-and-annotate-kmer-sets", "-G", "a", "-O", str(tmp_path / "out"))
+    assert r.returncode == 1 and "exactly twice" in r.stderr
+    r = _goss("merge-and-annotate-kmer-sets", "-G", "a", "-G", "b", "-G", "c", "-O", str(tmp_path / "out"))
+    assert r.returncode == 1 and "exactly twice" in r.stderr
+    r = _goss("compute-near-kmers")
+    assert r.returncode == 1 and "--graph-in" in r.stderr
+    r = _goss("dump-graph", "-G", "a", "--max-merge", "3")
+    assert r.returncode == 1 and "unrecognised option" in r.stderr
+    r = _goss("restore-graph", "-f", str(tmp_path / "missing.txt"), "-O", str(tmp_path / "nodir" / "g"))
+    assert r.returncode == 1 and "cannot create filenames with prefix" in r.stderr
+    for cmd in ("trim-graph", "merge-graphs", "merge-kmer-sets", "dump-graph", "restore-graph", "merge-and-annotate-kmer-sets", "compute-near-kmers"):
+        r = _goss(cmd, "-h")
+        assert r.returncode == 0 and r.stdout.startswith("usage: goss " + cmd), cmd
+    # a file set that does not exist: the message names it, exit code 1 (no device needed to find that out)
+    r = _goss("trim-graph", "-G", str(tmp_path / "nothing"), "-O", str(tmp_path / "out"), "-C", "1")
+    assert r.returncode == 1 and "error performing trim-graph" in r.stderr and "nothing" in r.stderr
+
+
 @pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
 def test_cli_without_gpu_fails_loudly(tmp_path):
     fa = tmp_path / "a.fa"
