@@ -57,3 +57,43 @@ def test_gpu_matches_reference_golden(name):
     else:
         sink, _, _ = G.build_kmer_set(_inputs(e), e["k"], prefix="g")
     _check(sink.as_bytes(), e)
+
+
+# ---- xenome index steps (tests/golden/make_golden_xeno.py) ---------------------------------------------------------------
+XENO = json.load(open(os.path.join(HERE, "golden", "xeno_golden.json")))
+
+
+def _xeno_inputs(e):
+    from xeno_cases import related_references
+    graft, host = related_references(e["n_bases"], e["n_subst"], e["seed"])
+    fg = O.build_kmer_set([(graft, O.FASTA)], e["k"], base="ga")[0].files()
+    fh = O.build_kmer_set([(host, O.FASTA)], e["k"], base="ho")[0].files()
+    both = dict(fg)
+    both.update(fh)
+    return both
+
+
+def _check_digest(files, want):
+    assert sorted(files) == sorted(want)
+    for n, meta in want.items():
+        assert len(files[n]) == meta["size"] and hashlib.sha256(files[n]).hexdigest() == meta["sha256"], n
+
+
+@pytest.mark.parametrize("name", sorted(XENO))
+def test_oracle_xenome_steps_match_reference_golden(name):
+    e = XENO[name]
+    merged, _ = O.merge_and_annotate(_xeno_inputs(e), "ga", "ho", "both")
+    _check_digest(merged, e["merged"])
+    near, _ = O.compute_near_kmers(merged, "both")
+    _check_digest(near, e["near"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(XENO))
+def test_gpu_xenome_steps_match_reference_golden(name):
+    import gossamer_b200 as G
+    e = XENO[name]
+    merged, _ = G.merge_and_annotate_kmer_sets(_xeno_inputs(e), "ga", "ho", "both")
+    _check_digest(merged, e["merged"])
+    near, _ = G.compute_near_kmers(merged, "both")
+    _check_digest(near, e["near"])
